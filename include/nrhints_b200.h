@@ -1,0 +1,138 @@
+/* nrhints_b200 -- C ABI of the B200-native NRHints ray-march hot path.
+ *
+ * The reference (iamNCJ/NRHints, commit 291800d) has no FFI layer: its boundary for this path
+ * is the Python nn.Module `NeuSHintRenderer` (models/neus_hint_model.py:236-267, :653-758).
+ * This header is the C boundary a maintainer binds (ctypes stub in INTEGRATION.md) to replace
+ * the bodies of:
+ *   NeuSHintRenderer.forward            models/neus_hint_model.py:653-751   -> nrh_render_forward
+ *   SDFNetwork.forward/.sdf/.gradient   fields/sdf_field.py:106-148         -> nrh_sdf_query
+ *   extract_fields (mesh grid queries)  models/neus_hint_model.py:68-83     -> nrh_sdf_query
+ *   weight_norm materialisation         fields/sdf_field.py:81-82,100-101   -> done by the caller
+ *                                       (torch._weight_norm), then nrh_pack_weights
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer.
+ *  - The library allocates nothing persistent, never synchronises the stream, keeps no
+ *    global state besides a thread-local error string.
+ *  - All tensors are contiguous fp32, row-major, shapes as in the reference (torch) API.
+ *  - Return value: 0 on success, negative NRH_ERR_* otherwise; nrh_last_error() describes it.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - Network architecture is the reference default and fixed at compile time:
+ *    SDF  : Fourier(6) -> 8 x 256 softplus(beta=100), skip-concat at layer 4, heads 1 + 256
+ *    Color: 361(316/325/352)-in -> 4 x 256 ReLU -> 3 sigmoid, Fourier(4) on view/light/hints
+ *    nrh_check_config() reports anything else as NRH_ERR_UNSUPPORTED.
+ */
+#ifndef NRHINTS_B200_H
+#define NRHINTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRH_ABI_VERSION 1
+
+#define NRH_OK 0
+#define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
+#define NRH_ERR_UNSUPPORTED (-2) /* config outside what the kernels implement             */
+#define NRH_ERR_WORKSPACE (-3)   /* workspace too small                                    */
+#define NRH_ERR_CUDA (-4)        /* a CUDA runtime call / kernel launch failed             */
+
+#define NRH_MAX_ROUGHNESS 4
+#define NRH_MAX_SAMPLES 128      /* n_samples + n_importance (and the shadow pair) <= 128   */
+
+/* MLP engine selection */
+#define NRH_MLP_AUTO 0
+#define NRH_MLP_FP32_SIMT 1      /* fp32 FFMA register-tiled fused MLP (always-correct path)   */
+#define NRH_MLP_TCGEN05 2        /* tcgen05 tensor-core fused MLP, fp16 hi/lo split operands   */
+
+/* Knobs of NeuSRendererConfig (models/neus_hint_model.py:133-174) the path honours. */
+typedef struct NrhConfig {
+    int32_t n_samples;            /* coarse samples per primary ray (64)                      */
+    int32_t n_importance;         /* importance samples per primary ray (64)                  */
+    int32_t up_sample_steps;      /* importance steps (4); n_importance % steps == 0          */
+    int32_t n_shadow_samples;     /* coarse samples per shadow ray (64)                       */
+    int32_t n_shadow_importance;  /* importance samples per shadow ray (64), 4 steps          */
+    int32_t shadow_hint;          /* reflectance net consumes the shadow hint                 */
+    int32_t specular_hint;        /* reflectance net consumes the specular hint               */
+    int32_t n_roughness;          /* <= NRH_MAX_ROUGHNESS                                     */
+    float roughness[NRH_MAX_ROUGHNESS];
+    float shadow_ray_offset;      /* 1e-2                                                     */
+    int32_t normalized_normals;   /* 1: NormalizedAnalytic feeds the reflectance net, 0: Analytic */
+    int32_t mlp_impl;             /* NRH_MLP_*                                                */
+} NrhConfig;
+
+/* Effective (weight-norm already applied) weights, torch layout W[out][in], b[out]. */
+typedef struct NrhRawWeights {
+    const float* sdf_W[8];        /* [256,39] [256,256]x2 [217,256] [256,256]x4               */
+    const float* sdf_b[8];
+    const float* sdf_out_W;       /* [1,256]                                                  */
+    const float* sdf_out_b;       /* [1]                                                      */
+    const float* feat_W;          /* [256,256]                                                */
+    const float* feat_b;          /* [256]                                                    */
+    const float* col_W[5];        /* [256,Cin] [256,256]x3 [3,256]; Cin = 316 + 9*shadow + 9*n_rough*specular */
+    const float* col_b[5];
+    const float* variance;        /* device scalar: deviation_network.variance                */
+} NrhRawWeights;
+
+typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-235)           */
+    const float* origins;         /* [R,3] */
+    const float* directions;      /* [R,3] unit */
+    const float* pl_positions;    /* [R,3] */
+    const float* nears;           /* [R,1] */
+    const float* fars;            /* [R,1] */
+} NrhRays;
+
+typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance */
+    float* rgb;                   /* [R,3]   */
+    float* depth;                 /* [R,1]   */
+    float* weights;               /* [R,S]   */
+    float* inside_sphere;         /* [R,S]   (relax_inside_sphere aliases it, reference quirk :746) */
+    float* analytic_normals;      /* [R,S,3] */
+    float* normalized_normals;    /* [R,S,3] */
+    float* visibilities;          /* [R,1]   nullable when !shadow_hint                        */
+    float* specular_cue;          /* [R,S,n_roughness] nullable when !specular_hint            */
+    float* inv_s;                 /* [1]     exp(10*variance) clipped to [1e-6,1e6]; s_val = 1/inv_s broadcast by the caller */
+    float* z_vals;                /* [R,S]   nullable; final primary sample positions (debug / backward) */
+    float* z_shadow;              /* [R,Ss]  nullable; final shadow-ray sample positions                   */
+    float* sampled_color;         /* [R,S,3] nullable; per-sample reflectance output                       */
+} NrhOutputs;
+
+int nrh_version(void);
+const char* nrh_last_error(void);
+
+/* Validate a config against what this build implements. */
+int nrh_check_config(const NrhConfig* cfg);
+
+/* Packed (kernel-layout) weights: size in bytes, and the packing pass (device-side transposes
+ * / splits, asynchronous on `stream`). Re-run whenever the parameters change. */
+size_t nrh_packed_weights_bytes(const NrhConfig* cfg);
+int nrh_pack_weights(const NrhConfig* cfg, const NrhRawWeights* raw, void* packed, size_t packed_bytes, void* stream);
+
+/* Scratch requirement of one nrh_render_forward call over R rays / one nrh_sdf_query over N points. */
+size_t nrh_workspace_bytes(const NrhConfig* cfg, int64_t R);
+size_t nrh_query_workspace_bytes(const NrhConfig* cfg, int64_t N);
+
+/* NeuSHintRenderer.forward.  jitter_primary [R] and jitter_shadow [R,n_shadow_samples] are the two
+ * torch.rand draws of training mode (:682, :394) made by the caller; NULL = inference (no perturbation).
+ * bg_rgb: device [3] or NULL.  cos_anneal = min(1, step/anneal_end) in training, 1 otherwise.
+ * warmup != 0 zeroes both hints (geometry warm-up, :577-579,:617-619). */
+int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* rays, int64_t R,
+                       const float* bg_rgb, const float* jitter_primary, const float* jitter_shadow,
+                       float cos_anneal, int warmup, const NrhOutputs* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* SDFNetwork.sdf / .gradient / .forward on arbitrary points: pts [N,3] ->
+ * sdf [N] (required), grad [N,3] (nullable), feat [N,256] (nullable). */
+int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N,
+                  float* sdf, float* grad, float* feat, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
+int nrh_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRHINTS_B200_H */

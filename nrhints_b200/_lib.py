@@ -1,0 +1,125 @@
+"""ctypes binding of libnrhints_b200.so (the C ABI declared in include/nrhints_b200.h).
+
+The library is plain CUDA-runtime code with no torch types in its signatures; PyTorch is used by
+the callers only to own device memory and streams.  There is NO CPU fallback: if the shared
+library is missing the import of the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+_LIB_PATH = _CSRC / "libnrhints_b200.so"
+_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu"]
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "../../include/nrhints_b200.h"]
+
+NRH_MAX_ROUGHNESS = 4
+NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
+MLP_IMPLS = {"auto": NRH_MLP_AUTO, "fp32": NRH_MLP_FP32_SIMT, "tcgen05": NRH_MLP_TCGEN05}
+
+
+class NrhConfig(C.Structure):
+    _fields_ = [
+        ("n_samples", C.c_int32), ("n_importance", C.c_int32), ("up_sample_steps", C.c_int32),
+        ("n_shadow_samples", C.c_int32), ("n_shadow_importance", C.c_int32),
+        ("shadow_hint", C.c_int32), ("specular_hint", C.c_int32), ("n_roughness", C.c_int32),
+        ("roughness", C.c_float * NRH_MAX_ROUGHNESS), ("shadow_ray_offset", C.c_float),
+        ("normalized_normals", C.c_int32), ("mlp_impl", C.c_int32),
+    ]
+
+
+class NrhRawWeights(C.Structure):
+    _fields_ = [
+        ("sdf_W", C.c_void_p * 8), ("sdf_b", C.c_void_p * 8),
+        ("sdf_out_W", C.c_void_p), ("sdf_out_b", C.c_void_p),
+        ("feat_W", C.c_void_p), ("feat_b", C.c_void_p),
+        ("col_W", C.c_void_p * 5), ("col_b", C.c_void_p * 5),
+        ("variance", C.c_void_p),
+    ]
+
+
+class NrhRays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("origins", "directions", "pl_positions", "nears", "fars")]
+
+
+class NrhOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rgb", "depth", "weights", "inside_sphere", "analytic_normals", "normalized_normals",
+        "visibilities", "specular_cue", "inv_s", "z_vals", "z_shadow", "sampled_color")]
+
+
+EXPORTS = {
+    "nrh_version": (C.c_int, []),
+    "nrh_last_error": (C.c_char_p, []),
+    "nrh_check_config": (C.c_int, [C.POINTER(NrhConfig)]),
+    "nrh_packed_weights_bytes": (C.c_size_t, [C.POINTER(NrhConfig)]),
+    "nrh_pack_weights": (C.c_int, [C.POINTER(NrhConfig), C.POINTER(NrhRawWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_workspace_bytes": (C.c_size_t, [C.POINTER(NrhConfig), C.c_int64]),
+    "nrh_query_workspace_bytes": (C.c_size_t, [C.POINTER(NrhConfig), C.c_int64]),
+    "nrh_render_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.POINTER(NrhRays), C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                     C.POINTER(NrhOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_sdf_query": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_last_launch_count": (C.c_int, []),
+}
+
+
+def nvcc_command(out: Path = _LIB_PATH):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-shared", "-Xcompiler", "-fPIC", "-o", str(out)] + [str(_CSRC / s) for s in _SOURCES]
+
+
+def needs_build() -> bool:
+    if not _LIB_PATH.exists():
+        return True
+    t = _LIB_PATH.stat().st_mtime
+    return any((_CSRC / s).resolve().stat().st_mtime > t for s in _SOURCES + _HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force or needs_build():
+        cmd = nvcc_command()
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it first if nvcc is around and sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if os.path.exists(nvcc):
+            build()
+    if not _LIB_PATH.exists():
+        raise ImportError(f"nrhints_b200: CUDA library {_LIB_PATH} is missing and could not be built; "
+                          "run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI drift: fail loudly
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class NrhError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().nrh_last_error()
+        raise NrhError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

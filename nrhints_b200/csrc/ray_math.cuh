@@ -1,0 +1,278 @@
+// Per-ray sampler / compositor math shared by the CUDA kernels and the host test harness
+// (tests/host_harness.cpp compiles this header with g++ so the sampler logic is
+// unit-tested against the oracle without a GPU).
+//
+// Reference semantics restated here (all in /root/reference/models/neus_hint_model.py):
+//   sample_pdf(det=True)      :21-65      -> nrh::upsample_new_z (second pass)
+//   up_sample                 :269-315    -> nrh::upsample_new_z (first pass)
+//   cat_z_vals                :317-331    -> nrh::merge_sorted
+//   get_alpha                 :333-357    -> nrh::neus_alpha
+//   get_visibility            :373-432    -> nrh::shadow_ray_init / nrh::shadow_transmittance
+//   render_core               :475-651    -> nrh::composite_primary / nrh::specular_cue
+//   forward (coarse z)        :673-683    -> nrh::coarse_z
+// Encoding: /root/reference/fields/encodings.py:168-176 -> nrh::fourier_encode
+//
+// All per-ray arrays are "sample-major": element j of ray r lives at base[j*stride + r]
+// (stride = number of rays), so that one-thread-per-ray kernels are fully coalesced.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NRH_HD __host__ __device__ __forceinline__
+#else
+#define NRH_HD inline
+#endif
+
+namespace nrh {
+
+struct SoA {                      // strided view of one ray's samples
+    float* p; int64_t stride;
+    NRH_HD float& operator[](int j) const { return p[(int64_t)j * stride]; }
+};
+struct CSoA {
+    const float* p; int64_t stride;
+    NRH_HD float operator[](int j) const { return p[(int64_t)j * stride]; }
+};
+
+// torch.linspace(0, 1, n)[j] in fp32 (ATen RangeFactories: symmetric evaluation about the middle;
+// the upper half is a fused multiply-add in ATen's vectorised kernel -- verified bitwise in tests).
+NRH_HD float linspace01(int j, int n) {
+    if (n <= 1) return 0.0f;
+    const float step = 1.0f / (float)(n - 1);
+    return (j < n / 2) ? step * (float)j : fmaf(-step, (float)(n - 1 - j), 1.0f);
+}
+
+NRH_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+NRH_HD float relu_(float x) { return x > 0.0f ? x : 0.0f; }
+NRH_HD float norm3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }
+
+// [x, sin(x 2^k), sin(x 2^k + pi/2)] for ONE scalar input, written with the reference's
+// interleaving handled by the caller: out_sin[k], out_cos[k], k < F.
+NRH_HD void fourier_scalar(float x, int F, float* out_sin, float* out_cos) {
+    float f = 1.0f;
+    for (int k = 0; k < F; ++k) {
+        const float s = x * f;
+        out_sin[k] = sinf(s);
+        out_cos[k] = sinf(s + 1.57079637050628662109375f);
+        f *= 2.0f;
+    }
+}
+
+// NeRFEncoding over a D-vector: layout [x(D), sin(d-major,k-minor)(D*F), cos(D*F)]; dst strided.
+NRH_HD void fourier_encode(const float* x, int D, int F, float* dst, int64_t dst_stride) {
+    for (int d = 0; d < D; ++d) dst[(int64_t)d * dst_stride] = x[d];
+    for (int d = 0; d < D; ++d) {
+        float f = 1.0f;
+        for (int k = 0; k < F; ++k) {
+            const float s = x[d] * f;
+            dst[(int64_t)(D + d * F + k) * dst_stride] = sinf(s);
+            dst[(int64_t)(D + D * F + d * F + k) * dst_stride] = sinf(s + 1.57079637050628662109375f);
+            f *= 2.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// coarse samples: z_j = near + (far-near) * linspace01(j) (+ (jit-0.5)*2/n when training)
+// ------------------------------------------------------------------------------------------
+NRH_HD void coarse_z(float near, float far, int n, bool has_jitter, float jitter, SoA z) {
+    const float span = far - near;
+    const float off = has_jitter ? (jitter - 0.5f) * 2.0f / (float)n : 0.0f;
+    for (int j = 0; j < n; ++j) {
+        float v = near + span * linspace01(j, n);
+        if (has_jitter) v = v + off;
+        z[j] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// one importance step: (z sorted[k], sdf[k]) -> n_new new z (non-decreasing).
+// wbuf: scratch for k-1 interval weights (+1e-5).
+// ------------------------------------------------------------------------------------------
+NRH_HD void upsample_new_z(const float o[3], const float d[3], int k, CSoA z, CSoA sdf,
+                           float inv_s, int n_new, SoA wbuf, SoA z_new) {
+    // pass 1: interval weights
+    float zj = z[0], sj = sdf[0];
+    float rj = norm3(o[0] + d[0] * zj, o[1] + d[1] * zj, o[2] + d[2] * zj);
+    float prev_cos = 0.0f, T = 1.0f, wsum = 0.0f;
+    for (int j = 0; j + 1 < k; ++j) {
+        const float zn = z[j + 1], sn = sdf[j + 1];
+        const float rn = norm3(o[0] + d[0] * zn, o[1] + d[1] * zn, o[2] + d[2] * zn);
+        const float inside = (rj < 1.0f || rn < 1.0f) ? 1.0f : 0.0f;
+        const float mid_sdf = (sj + sn) * 0.5f;
+        const float dist = zn - zj;
+        const float cos_raw = (sn - sj) / (dist + 1e-5f);
+        float c = fminf(prev_cos, cos_raw);
+        c = fminf(fmaxf(c, -1e3f), 0.0f) * inside;
+        prev_cos = cos_raw;
+        const float half = c * dist * 0.5f;
+        const float prev_cdf = sigmoidf_((mid_sdf - half) * inv_s);
+        const float next_cdf = sigmoidf_((mid_sdf + half) * inv_s);
+        const float alpha = (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
+        const float w = alpha * T + 1e-5f;
+        T = T * (1.0f - alpha + 1e-7f);
+        wbuf[j] = w;
+        wsum += w;
+        zj = zn; sj = sn; rj = rn;
+    }
+    // pass 2: inverse CDF at u = linspace(0,1,n_new); cdf has k entries, cdf[0]=0.
+    int m = 0;                 // running searchsorted(right=True) result
+    float c_m = 0.0f;          // cdf[m]
+    float c_below = 0.0f;      // cdf[m-1]
+    for (int t = 0; t < n_new; ++t) {
+        const float u = linspace01(t, n_new);
+        while (m < k && c_m <= u) {
+            c_below = c_m;
+            ++m;
+            if (m < k) c_m = c_below + wbuf[m - 1] / wsum;
+        }
+        const int below = m - 1 > 0 ? m - 1 : 0;
+        const int above = m < k - 1 ? m : k - 1;
+        const float c_above = (m < k) ? c_m : c_below;
+        float denom = c_above - c_below;
+        if (denom < 1e-5f) denom = 1.0f;
+        const float tt = (u - c_below) / denom;
+        const float zb = z[below], za = z[above];
+        z_new[t] = zb + tt * (za - zb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge two sorted runs (ties: old first). sdf arrays optional (last step merges z only).
+// ------------------------------------------------------------------------------------------
+NRH_HD void merge_sorted(int k, CSoA z_old, CSoA s_old, int n, CSoA z_new, CSoA s_new,
+                         SoA z_out, SoA s_out, bool with_sdf) {
+    int a = 0, b = 0;
+    float za = z_old[0], zb = z_new[0];
+    for (int i = 0; i < k + n; ++i) {
+        const bool take_old = (b >= n) || (a < k && za <= zb);
+        if (take_old) {
+            z_out[i] = za;
+            if (with_sdf) s_out[i] = s_old[a];
+            ++a; if (a < k) za = z_old[a];
+        } else {
+            z_out[i] = zb;
+            if (with_sdf) s_out[i] = s_new[b];
+            ++b; if (b < n) zb = z_new[b];
+        }
+    }
+}
+
+// section length / mid-point of sample j (render_core :491-493, get_visibility :416-418)
+NRH_HD void section(CSoA z, int j, int S, float last_dist, float& dist, float& mid) {
+    const float zj = z[j];
+    dist = (j + 1 < S) ? (z[j + 1] - zj) : last_dist;
+    mid = zj + dist * 0.5f;
+}
+
+// get_alpha :339-356
+NRH_HD float neus_alpha(float sdf, float gx, float gy, float gz, const float d[3], float dist,
+                        float inv_s, float cos_anneal) {
+    const float true_cos = d[0] * gx + d[1] * gy + d[2] * gz;
+    const float iter_cos = -(relu_(-true_cos * 0.5f + 0.5f) * (1.0f - cos_anneal) + relu_(-true_cos) * cos_anneal);
+    const float half = iter_cos * dist * 0.5f;
+    const float prev_cdf = sigmoidf_((sdf - half) * inv_s);
+    const float next_cdf = sigmoidf_((sdf + half) * inv_s);
+    const float a = (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
+    return fminf(fmaxf(a, 0.0f), 1.0f);
+}
+
+struct PrimaryComposite {
+    float wsum, depth, nsum[3];
+};
+
+// weights, inside mask, normals, depth (render_core :508-533, :583-587).
+// sdf/grad are the fine-pass MLP outputs at the section mid-points.
+NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], int S, CSoA z, float last_dist,
+                                          CSoA sdf, CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal,
+                                          SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz) {
+    PrimaryComposite r; r.wsum = 0.f; r.depth = 0.f; r.nsum[0] = r.nsum[1] = r.nsum[2] = 0.f;
+    float T = 1.0f;
+    for (int j = 0; j < S; ++j) {
+        float dist, mid; section(z, j, S, last_dist, dist, mid);
+        const float px = o[0] + d[0] * mid, py = o[1] + d[1] * mid, pz = o[2] + d[2] * mid;
+        const float g0 = gx[j], g1 = gy[j], g2 = gz[j];
+        const float a = neus_alpha(sdf[j], g0, g1, g2, d, dist, inv_s, cos_anneal);
+        const float w = a * T;
+        T = T * (1.0f - a + 1e-7f);
+        w_out[j] = w;
+        inside_out[j] = norm3(px, py, pz) < 1.0f ? 1.0f : 0.0f;
+        const float gn = fmaxf(norm3(g0, g1, g2), 1e-12f);       // F.normalize eps
+        const float n0 = g0 / gn, n1 = g1 / gn, n2 = g2 / gn;
+        nx[j] = n0; ny[j] = n1; nz[j] = n2;
+        r.wsum += w; r.depth += mid * w;
+        r.nsum[0] += n0 * w; r.nsum[1] += n1 * w; r.nsum[2] += n2 * w;
+    }
+    return r;
+}
+
+// shadow ray from the light to the hit point (get_visibility :380-395). Returns L (light distance).
+NRH_HD float shadow_ray_init(const float pl[3], const float hit[3], int n, float offset, bool has_jitter,
+                             CSoA jitter, float dir_out[3], SoA z) {
+    const float vx = hit[0] - pl[0], vy = hit[1] - pl[1], vz = hit[2] - pl[2];
+    const float L = norm3(vx, vy, vz);
+    dir_out[0] = vx / L; dir_out[1] = vy / L; dir_out[2] = vz / L;
+    const float keep = 1.0f - offset;
+    if (!has_jitter) {
+        for (int j = 0; j < n; ++j) z[j] = linspace01(j, n) * L * keep;
+    } else {
+        float zprev = 0.f, zcur = linspace01(0, n) * L * keep;
+        for (int j = 0; j < n; ++j) {
+            const float znext = (j + 1 < n) ? linspace01(j + 1, n) * L * keep : zcur;
+            const float lower = (j == 0) ? zcur : 0.5f * (zcur + zprev);
+            const float upper = (j + 1 < n) ? 0.5f * (znext + zcur) : zcur;
+            z[j] = lower + (upper - lower) * jitter[j];
+            zprev = zcur; zcur = znext;
+        }
+    }
+    return L;
+}
+
+// taus[:, -1]: transmittance in front of the last sample (get_visibility :427-432)
+NRH_HD float shadow_transmittance(const float d[3], int S, CSoA z, float last_dist, CSoA sdf,
+                                  CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal) {
+    float T = 1.0f;
+    for (int j = 0; j + 1 < S; ++j) {
+        float dist, mid; section(z, j, S, last_dist, dist, mid);
+        const float a = neus_alpha(sdf[j], gx[j], gy[j], gz[j], d, dist, inv_s, cos_anneal);
+        T = T * (1.0f - a + 1e-7f);
+    }
+    return T;
+}
+
+NRH_HD void normalize3(const float v[3], float out[3]) {
+    const float n = fmaxf(norm3(v[0], v[1], v[2]), 1e-12f);
+    out[0] = v[0] / n; out[1] = v[1] / n; out[2] = v[2] / n;
+}
+NRH_HD float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// Cook-Torrance cue for each roughness (render_core :588-616)
+NRH_HD void specular_cue(const float hit_n[3], const float pl[3], const float hit[3], const float d[3],
+                         int n_rough, const float* rough, float* cue) {
+    float lv[3] = {pl[0] - hit[0], pl[1] - hit[1], pl[2] - hit[2]}, l[3], v[3], h[3];
+    normalize3(lv, l);
+    float nd[3] = {-d[0], -d[1], -d[2]};
+    normalize3(nd, v);
+    float hv[3] = {l[0] + v[0], l[1] + v[1], l[2] + v[2]};
+    normalize3(hv, h);
+    const float n_l = clamp01(hit_n[0] * l[0] + hit_n[1] * l[1] + hit_n[2] * l[2]);
+    const float n_v = clamp01(hit_n[0] * v[0] + hit_n[1] * v[1] + hit_n[2] * v[2]);
+    const float n_h = clamp01(hit_n[0] * h[0] + hit_n[1] * h[1] + hit_n[2] * h[2]);
+    const float h_v = clamp01(h[0] * v[0] + h[1] * v[1] + h[2] * v[2]);
+    const float n_h2 = n_h * n_h;
+    const float om = 1.0f - h_v;
+    const float om5 = (om * om) * (om * om) * om;
+    const float fres = 0.04f + 0.96f * om5;
+    for (int i = 0; i < n_rough; ++i) {
+        const float r = rough[i];
+        const float k = (r + 1.0f) * (r + 1.0f) / 8.0f;
+        const float g = (n_v / (n_v * (1.0f - k) + k)) * (n_l / (n_l * (1.0f - k) + k));
+        const float a2 = r * r;
+        const float den = n_h2 * (a2 - 1.0f) + 1.0f;
+        const float ndf = a2 / (3.14159274101257324f * (den * den));
+        cue[i] = ndf * g * fres / (4.0f * n_v + 1e-3f);
+    }
+}
+
+}  // namespace nrh

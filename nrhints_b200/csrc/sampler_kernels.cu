@@ -1,0 +1,247 @@
+// Per-ray sampler / compositor kernels: one thread per ray over sample-major workspace arrays
+// (element j of ray r at [j*R + r]) so every access is coalesced.  All arithmetic lives in
+// ray_math.cuh (shared with the host test harness); this file only moves data.
+//
+// Reference call sites: /root/reference/models/neus_hint_model.py:673-713 (coarse + importance
+// loop), :475-651 (render_core), :373-432 (get_visibility).
+#include "nrh_common.cuh"
+#include "ray_math.cuh"
+#include "sampler_kernels.cuh"
+
+namespace nrh {
+namespace {
+
+constexpr int TPB = 128;
+
+__device__ __forceinline__ void write_points(const float o[3], const float d[3], float z, int64_t idx,
+                                             float* px, float* py, float* pz) {
+    px[idx] = o[0] + d[0] * z; py[idx] = o[1] + d[1] * z; pz[idx] = o[2] + d[2] * z;
+}
+
+// ---- primary rays: load the bundle, coarse z, coarse points --------------------------------------
+__global__ void k_coarse_primary(NrhRays rays, int64_t R, int n, const float* __restrict__ jitter,
+                                 MarchState m) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float o[3], d[3];
+    for (int c = 0; c < 3; ++c) {
+        o[c] = rays.origins[r * 3 + c]; d[c] = rays.directions[r * 3 + c];
+        m.o[c][r] = o[c]; m.d[c][r] = d[c];
+    }
+    SoA z{m.z[0] + r, R};
+    coarse_z(rays.nears[r], rays.fars[r], n, jitter != nullptr, jitter ? jitter[r] : 0.f, z);
+    for (int j = 0; j < n; ++j) write_points(o, d, z[j], (int64_t)j * R + r, m.px, m.py, m.pz);
+}
+
+// ---- one importance step (merge previous new samples, draw new ones, emit their points; on the
+//      last step also merge them and emit the section mid-points of the final sample set) ---------
+__global__ void k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool merge_first,
+                                  float inv_s, bool last, float last_dist_const, const float* last_dist_ray) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float o[3], d[3];
+    for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
+    int k = k_old;
+    if (merge_first) {
+        merge_sorted(k_old, CSoA{m.z[cur] + r, R}, CSoA{m.s[cur] + r, R}, n_new, CSoA{m.znew + r, R},
+                     CSoA{m.snew + r, R}, SoA{m.z[cur ^ 1] + r, R}, SoA{m.s[cur ^ 1] + r, R}, true);
+        cur ^= 1; k = k_old + n_new;
+    }
+    upsample_new_z(o, d, k, CSoA{m.z[cur] + r, R}, CSoA{m.s[cur] + r, R}, inv_s, n_new,
+                   SoA{m.wbuf + r, R}, SoA{m.znew + r, R});
+    if (!last) {
+        for (int t = 0; t < n_new; ++t) write_points(o, d, m.znew[(int64_t)t * R + r], (int64_t)t * R + r, m.px, m.py, m.pz);
+    } else {
+        merge_sorted(k, CSoA{m.z[cur] + r, R}, CSoA{nullptr, 0}, n_new, CSoA{m.znew + r, R}, CSoA{nullptr, 0},
+                     SoA{m.z[cur ^ 1] + r, R}, SoA{nullptr, 0}, false);
+        cur ^= 1;
+        const int S = k + n_new;
+        const float last_dist = last_dist_ray ? last_dist_ray[r] : last_dist_const;
+        CSoA z{m.z[cur] + r, R};
+        for (int j = 0; j < S; ++j) {
+            float dist, mid; section(z, j, S, last_dist, dist, mid);
+            write_points(o, d, mid, (int64_t)j * R + r, m.px, m.py, m.pz);
+        }
+    }
+}
+
+// no importance samples at all: just emit the section mid-points of the coarse set
+__global__ void k_sections_only(int64_t R, MarchState m, int cur, int S, float last_dist_const, const float* last_dist_ray) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float o[3], d[3];
+    for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
+    const float last_dist = last_dist_ray ? last_dist_ray[r] : last_dist_const;
+    CSoA z{m.z[cur] + r, R};
+    for (int j = 0; j < S; ++j) {
+        float dist, mid; section(z, j, S, last_dist, dist, mid);
+        write_points(o, d, mid, (int64_t)j * R + r, m.px, m.py, m.pz);
+    }
+}
+
+// ---- primary composite + shadow-ray setup ----------------------------------------------------------
+__global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, float last_dist,
+                                    const float* __restrict__ inv_s_ptr, float cos_anneal, FineBuffers f,
+                                    RayState rs, const float* __restrict__ pl, bool do_shadow, MarchState sh,
+                                    int n_shadow, float shadow_offset, const float* __restrict__ jitter_shadow) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float o[3], d[3];
+    for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
+    const float inv_s = inv_s_ptr[0];
+    PrimaryComposite pc = composite_primary(o, d, S, CSoA{m.z[cur] + r, R}, last_dist, CSoA{f.sdf + r, R},
+                                            CSoA{f.gx + r, R}, CSoA{f.gy + r, R}, CSoA{f.gz + r, R}, inv_s, cos_anneal,
+                                            SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R});
+    rs.depth[r] = pc.depth; rs.wsum[r] = pc.wsum;
+    float hit[3], hn[3];
+    for (int c = 0; c < 3; ++c) hit[c] = o[c] + d[c] * pc.depth;
+    normalize3(pc.nsum, hn);
+    for (int c = 0; c < 3; ++c) { rs.hit[c][r] = hit[c]; rs.hitn[c][r] = hn[c]; }
+    if (do_shadow) {
+        float l[3] = {pl[r * 3 + 0], pl[r * 3 + 1], pl[r * 3 + 2]}, sd[3];
+        SoA z{sh.z[0] + r, R};
+        const float L = shadow_ray_init(l, hit, n_shadow, shadow_offset, jitter_shadow != nullptr,
+                                        CSoA{jitter_shadow ? jitter_shadow + r * (int64_t)n_shadow : nullptr, 1}, sd, z);
+        rs.light_dist[r] = L / (float)n_shadow;        // sample_dist of the shadow ray (:383)
+        for (int c = 0; c < 3; ++c) { sh.o[c][r] = l[c]; sh.d[c][r] = sd[c]; }
+        for (int j = 0; j < n_shadow; ++j) write_points(l, sd, z[j], (int64_t)j * R + r, sh.px, sh.py, sh.pz);
+    }
+}
+
+// ---- shadow transmittance, specular cue, per-ray reflectance inputs ---------------------------------
+__global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, int S_shadow,
+                             const float* __restrict__ inv_s_ptr, float cos_anneal, const float* __restrict__ ssdf,
+                             const float* __restrict__ sgx, const float* __restrict__ sgy, const float* __restrict__ sgz,
+                             RayState rs, const float* __restrict__ pl, const float* __restrict__ dirs, int warmup,
+                             bool shadow_marched, float* __restrict__ rayfeat) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float vis = 0.f;
+    if (shadow_marched) {
+        float sd[3] = {sh.d[0][r], sh.d[1][r], sh.d[2][r]};
+        vis = shadow_transmittance(sd, S_shadow, CSoA{sh.z[cur] + r, R}, rs.light_dist[r], CSoA{ssdf + r, R},
+                                   CSoA{sgx + r, R}, CSoA{sgy + r, R}, CSoA{sgz + r, R}, inv_s_ptr[0], cos_anneal);
+    }
+    rs.vis[r] = vis;
+    float d[3] = {dirs[r * 3 + 0], dirs[r * 3 + 1], dirs[r * 3 + 2]};
+    float l[3] = {pl[r * 3 + 0], pl[r * 3 + 1], pl[r * 3 + 2]};
+    float cue[NRH_MAX_ROUGHNESS] = {0.f, 0.f, 0.f, 0.f};
+    if (cfg.specular_hint && !warmup) {
+        float hit[3] = {rs.hit[0][r], rs.hit[1][r], rs.hit[2][r]};
+        float hn[3] = {rs.hitn[0][r], rs.hitn[1][r], rs.hitn[2][r]};
+        specular_cue(hn, l, hit, d, cfg.n_roughness, cfg.roughness, cue);
+    }
+    for (int i = 0; i < NRH_MAX_ROUGHNESS; ++i) rs.spec[i][r] = cue[i];
+    // per-ray encoded reflectance inputs: PE(view) 27 | PE(light) 27 | PE(vis) 9 | PE(spec) 36
+    fourier_encode(d, 3, COL_FREQ, rayfeat + r, R);
+    fourier_encode(l, 3, COL_FREQ, rayfeat + (int64_t)COL_PE3 * R + r, R);
+    float* vis_dst = rayfeat + (int64_t)(2 * COL_PE3) * R + r;
+    float* spec_dst = rayfeat + (int64_t)(2 * COL_PE3 + 9) * R + r;
+    if (cfg.shadow_hint) fourier_encode(&vis, 1, COL_FREQ, vis_dst, R);
+    else for (int i = 0; i < 9; ++i) vis_dst[(int64_t)i * R] = 0.f;
+    for (int i = 0; i < 36; ++i) spec_dst[(int64_t)i * R] = 0.f;
+    if (cfg.specular_hint) fourier_encode(cue, cfg.n_roughness, COL_FREQ, spec_dst, R);
+}
+
+// ---- rgb = sum_j w_j c_j + bg (1 - sum w) ---------------------------------------------------------------
+__global__ void k_final_rgb(int64_t R, int S, FineBuffers f, RayState rs, const float* __restrict__ cr,
+                            const float* __restrict__ cg, const float* __restrict__ cb, const float* __restrict__ bg,
+                            float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ vis_out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < S; ++j) {
+        const int64_t i = (int64_t)j * R + r;
+        const float w = f.w[i];
+        a0 += cr[i] * w; a1 += cg[i] * w; a2 += cb[i] * w;
+    }
+    if (bg) {
+        const float rest = 1.0f - rs.wsum[r];
+        a0 += bg[0] * rest; a1 += bg[1] * rest; a2 += bg[2] * rest;
+    }
+    rgb[r * 3 + 0] = a0; rgb[r * 3 + 1] = a1; rgb[r * 3 + 2] = a2;
+    depth[r] = rs.depth[r];
+    if (vis_out) vis_out[r] = rs.vis[r];
+}
+
+// ---- sample-major [S][R] (x C channels) -> ray-major [R][S][C] -------------------------------------------
+struct TransposeArgs { const float* src[4]; int C; int broadcast; };   // broadcast: src[c] is per-ray [R]
+
+__global__ void k_to_ray_major(TransposeArgs a, int64_t R, int S, float* __restrict__ dst) {
+    __shared__ float tile[4][32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    for (int c = 0; c < a.C; ++c)
+        for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+            const int j = j0 + jj; const int64_t r = r0 + threadIdx.x;
+            float v = 0.f;
+            if (j < S && r < R) v = a.broadcast ? a.src[c][r] : a.src[c][(int64_t)j * R + r];
+            tile[c][jj][threadIdx.x] = v;
+        }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t r = r0 + rr; const int j = j0 + threadIdx.x;
+        if (r < R && j < S)
+            for (int c = 0; c < a.C; ++c) dst[(r * S + j) * a.C + c] = tile[c][threadIdx.x][rr];
+    }
+}
+
+inline int blocks_for(int64_t R) { return (int)((R + TPB - 1) / TPB); }
+
+}  // namespace
+
+int launch_coarse_primary(const NrhRays& rays, int64_t R, int n, const float* jitter, const MarchState& m, cudaStream_t st) {
+    k_coarse_primary<<<blocks_for(R), TPB, 0, st>>>(rays, R, n, jitter, m);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_importance_step(int64_t R, const MarchState& m, int cur, int k_old, int n_new, bool merge_first, float inv_s,
+                           bool last, float last_dist_const, const float* last_dist_ray, cudaStream_t st) {
+    k_importance_step<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_sections_only(int64_t R, const MarchState& m, int cur, int S, float last_dist_const, const float* last_dist_ray, cudaStream_t st) {
+    k_sections_only<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, last_dist_const, last_dist_ray);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, float last_dist, const float* inv_s,
+                             float cos_anneal, const FineBuffers& f, const RayState& rs, const float* pl, bool do_shadow,
+                             const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow, cudaStream_t st) {
+    k_composite_primary<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, last_dist, inv_s, cos_anneal, f, rs, pl, do_shadow, sh,
+                                                       n_shadow, shadow_offset, jitter_shadow);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int cur, int S_shadow, const float* inv_s,
+                      float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
+                      const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,
+                      float* rayfeat, cudaStream_t st) {
+    k_shade_prep<<<blocks_for(R), TPB, 0, st>>>(R, cfg, sh, cur, S_shadow, inv_s, cos_anneal, ssdf, sgx, sgy, sgz, rs, pl, dirs,
+                                                warmup, shadow_marched, rayfeat);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, const float* cr, const float* cg,
+                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, cudaStream_t st) {
+    k_final_rgb<<<blocks_for(R), TPB, 0, st>>>(R, S, f, rs, cr, cg, cb, bg, rgb, depth, vis_out);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_to_ray_major(const float* const* src, int C, bool broadcast, int64_t R, int S, float* dst, cudaStream_t st) {
+    TransposeArgs a; a.C = C; a.broadcast = broadcast ? 1 : 0;
+    for (int c = 0; c < 4; ++c) a.src[c] = c < C ? src[c] : nullptr;
+    dim3 grid((unsigned)((R + 31) / 32), (unsigned)((S + 31) / 32)), block(32, 8);
+    k_to_ray_major<<<grid, block, 0, st>>>(a, R, S, dst);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+}  // namespace nrh

@@ -1,0 +1,424 @@
+"""Host-side mirror of the reference's renderer interface for the ray-march hot path.
+
+`NeuSHintRenderer` keeps the reference module's constructor, attribute names, parameter names /
+shapes / registration order (so reference checkpoints and optimizer states load) and its
+`forward(ray_bundle, is_training, background_rgb, global_step) -> RenderOutput` signature
+(/root/reference/models/neus_hint_model.py:236-267, :653-758), but every per-sample computation
+runs in the hand-written sm_100a CUDA library behind the C ABI of include/nrhints_b200.h.
+PyTorch only owns device memory, the stream and the parameters.  There is no CPU fallback.
+
+Mirrored reference pieces:
+  SDFNetwork            /root/reference/fields/sdf_field.py:39-148        (params, geometric init, sdf/gradient/forward)
+  ReflectanceNetwork    /root/reference/fields/reflectance_network.py:25-96 (params)
+  SingleVarianceNetwork /root/reference/models/neus_hint_model.py:104-110
+  RenderOutput          /root/reference/models/neus_hint_model.py:216-233
+  extract_fields/_geometry  /root/reference/models/neus_hint_model.py:68-93,753-758
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .config import (DepthComputationType, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig, SDFNetConfig)
+
+
+# ------------------------------------------------------------------------------------------------
+# output type
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RenderOutput:
+    """Same fields / shapes as the reference RenderOutput (a nerfstudio TensorDataclass there).
+    `RenderOutput.cast(cls)` re-wraps the tensors in the reference's own class when the caller is
+    the unmodified reference pipeline."""
+    rgb: torch.Tensor                          # [R,3]
+    depth: torch.Tensor                        # [R,1]
+    weights: torch.Tensor                      # [R,S]
+    s_val: torch.Tensor                        # [R,S]
+    inside_sphere: torch.Tensor                # [R,S]
+    relax_inside_sphere: torch.Tensor          # [R,S]
+    analytic_normals: torch.Tensor             # [R,S,3]
+    normalized_analytic_normals: torch.Tensor  # [R,S,3]
+    visibilities: Optional[torch.Tensor] = None   # [R,1]
+    specular_cue: Optional[torch.Tensor] = None   # [R,S,n_rough]
+    # extras (not in the reference type): final sample positions, useful for parity debugging
+    z_vals: Optional[torch.Tensor] = None
+    z_shadow: Optional[torch.Tensor] = None
+    sampled_color: Optional[torch.Tensor] = None
+
+    _REFERENCE_FIELDS = ("rgb", "depth", "weights", "s_val", "inside_sphere", "relax_inside_sphere",
+                         "analytic_normals", "normalized_analytic_normals", "visibilities", "specular_cue")
+
+    def as_dict(self) -> Dict[str, Optional[torch.Tensor]]:
+        return {f.name: getattr(self, f.name) for f in dataclasses.fields(self)}
+
+    def to(self, device, non_blocking: bool = False) -> "RenderOutput":
+        return RenderOutput(**{k: (v.to(device, non_blocking=non_blocking) if v is not None else None)
+                               for k, v in self.as_dict().items()})
+
+    def detach(self) -> "RenderOutput":
+        return RenderOutput(**{k: (v.detach() if v is not None else None) for k, v in self.as_dict().items()})
+
+    def cast(self, cls):
+        return cls(**{k: getattr(self, k) for k in self._REFERENCE_FIELDS})
+
+    @property
+    def shape(self):
+        return tuple(self.rgb.shape[:-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers
+# ------------------------------------------------------------------------------------------------
+class WNLinear(nn.Module):
+    """Parameters of a weight-normalised Linear: `bias`, `weight_g` [out,1], `weight_v` [out,in],
+    registered in the order nn.utils.weight_norm leaves them (bias, weight_g, weight_v)."""
+
+    def __init__(self, lin: nn.Linear, weight_norm: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = lin.in_features, lin.out_features
+        self.weight_normed = weight_norm
+        self.bias = nn.Parameter(lin.bias.detach().clone())
+        if weight_norm:
+            v = lin.weight.detach().clone()
+            self.weight_g = nn.Parameter(torch.norm_except_dim(v, 2, 0))
+            self.weight_v = nn.Parameter(v)
+        else:
+            self.weight = nn.Parameter(lin.weight.detach().clone())
+
+    def effective_weight(self) -> torch.Tensor:
+        if self.weight_normed:
+            return torch._weight_norm(self.weight_v, self.weight_g, 0)
+        return self.weight
+
+
+def _check_sdf_arch(cfg: SDFNetConfig):
+    ok = (cfg.d_in == 3 and cfg.d_out_feat == 256 and cfg.d_hidden == 256 and cfg.n_layers == 8
+          and list(cfg.skip_in) == [4] and cfg.multi_res == 6 and float(cfg.scale) == 3.0)
+    if not ok:
+        raise NotImplementedError("nrhints_b200 kernels implement the reference-default SDF network "
+                                  "(8x256, skip_in=[4], multi_res=6, scale=3, d_out_feat=256); got " + repr(cfg))
+
+
+class SDFNetwork(nn.Module):
+    """Parameter container + point-query API of the SDF field (fields/sdf_field.py:39-148)."""
+
+    def __init__(self, config: SDFNetConfig):
+        super().__init__()
+        _check_sdf_arch(config)
+        self.config = config
+        d_pe = config.d_in * (2 * config.multi_res + 1)
+        dims = [d_pe] + [config.d_hidden] * config.n_layers + [config.d_out_feat + 1]
+        self.num_layers = len(dims)
+        self.skip_in = list(config.skip_in)
+        self.scale = config.scale
+        bias = config.init_bias * config.scale
+        for l in range(self.num_layers - 2):
+            out_dim = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
+            if config.geometric_init:
+                std = np.sqrt(2) / np.sqrt(out_dim)
+                nn.init.constant_(lin.bias, 0.0)
+                if l == 0:
+                    nn.init.constant_(lin.weight[:, 3:], 0.0)
+                    nn.init.normal_(lin.weight[:, :3], 0.0, std)
+                else:
+                    nn.init.normal_(lin.weight, 0.0, std)
+                    if l in self.skip_in:
+                        nn.init.constant_(lin.weight[:, -(dims[0] - 3):], 0.0)
+            setattr(self, f"lin{l}", WNLinear(lin, config.weight_norm))
+        for name, out_dim in (("sdf", 1), ("feat", dims[-1] - 1)):
+            lin = nn.Linear(dims[-2], out_dim)
+            if config.geometric_init:
+                sign = -1.0 if config.inside_outside else 1.0
+                nn.init.normal_(lin.weight, mean=sign * np.sqrt(np.pi) / np.sqrt(dims[-1]), std=0.0001)
+                nn.init.constant_(lin.bias, -sign * bias)
+            setattr(self, f"out_{name}", WNLinear(lin, config.weight_norm))
+        self._owner = None           # set by NeuSHintRenderer (plain attribute, not a submodule)
+
+    def _renderer(self):
+        if self._owner is None:
+            raise RuntimeError("SDFNetwork point queries run through the owning NeuSHintRenderer's CUDA context")
+        return self._owner()
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        sdf, _, feat = self._renderer().sdf_query(inputs, want_grad=False, want_feat=True)
+        return torch.cat([sdf[:, None], feat], dim=-1)
+
+    def sdf(self, x: torch.Tensor) -> torch.Tensor:
+        return self._renderer().sdf_query(x)[0][:, None]
+
+    def sdf_hidden_appearance(self, x: torch.Tensor) -> torch.Tensor:
+        return self._renderer().sdf_query(x, want_feat=True)[2]
+
+    def gradient(self, x: torch.Tensor) -> torch.Tensor:
+        return self._renderer().sdf_query(x, want_grad=True)[1].unsqueeze(1)
+
+    def freeze_geometry(self):
+        for name, p in self.named_parameters():
+            if "lin" in name or "out_sdf" in name:
+                p.requires_grad = False
+
+
+class ReflectanceNetwork(nn.Module):
+    """Parameter container of the hint-conditioned radiance MLP (fields/reflectance_network.py:25-66).
+    Evaluated only inside the fused render pipeline."""
+
+    def __init__(self, d_feature, d_in, d_out, config: ReflectanceNetConfig, shadow_hint=True, specular_hint=True,
+                 specular_hint_len=4):
+        super().__init__()
+        if not (config.d_hidden == 256 and config.n_layers == 4 and config.multi_res == 4 and config.squeeze_out
+                and d_feature == 256 and d_out == 3):
+            raise NotImplementedError("nrhints_b200 kernels implement the reference-default reflectance network "
+                                      "(4x256, multi_res=4, squeeze_out); got " + repr(config))
+        self.config = config
+        self.shadow_hint, self.specular_hint = shadow_hint, specular_hint
+        pe3 = 3 * (2 * config.multi_res + 1)
+        dims = [d_in + d_feature] + [config.d_hidden] * config.n_layers + [d_out]
+        dims[0] += (pe3 - 3) * 2
+        if shadow_hint:
+            dims[0] += (2 * config.multi_res + 1) - 1
+        if specular_hint:
+            dims[0] += specular_hint_len * (2 * config.multi_res + 1) - specular_hint_len
+        self.num_layers = len(dims)
+        self.d_in_total = dims[0]
+        for l in range(self.num_layers - 1):
+            setattr(self, f"lin{l}", WNLinear(nn.Linear(dims[l], dims[l + 1]), config.weight_norm))
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("ReflectanceNetwork is evaluated inside NeuSHintRenderer.forward (fused CUDA pipeline)")
+
+
+class SingleVarianceNetwork(nn.Module):
+    def __init__(self, init_val):
+        super().__init__()
+        self.register_parameter("variance", nn.Parameter(torch.tensor(init_val)))
+
+    def forward(self, x):
+        return torch.ones([len(x), 1], device=x.device) * torch.exp(self.variance * 10.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the renderer
+# ------------------------------------------------------------------------------------------------
+class NeuSHintRenderer(nn.Module):
+    def __init__(self, config: NeuSModelConfig = None, mlp_impl: str = "auto"):
+        super().__init__()
+        config = config if config is not None else NeuSModelConfig()
+        r = config.renderer
+        if r.use_outside_nerf:
+            raise NotImplementedError("use_outside_nerf=True is outside the B200 hot path (SURVEY.md section 8a row A15)")
+        if getattr(r.depth_type, "value", r.depth_type) != DepthComputationType.AlphaBlend.value:
+            raise NotImplementedError("only depth_type=AlphaBlend is implemented (reference default)")
+        if r.n_shadow_importance_clip != -1:
+            raise NotImplementedError("n_shadow_importance_clip != -1 is not implemented (reference default is -1)")
+        if r.shadow_hint_gradient or r.specular_hint_gradient:
+            raise NotImplementedError("hint gradients are not implemented (reference default is off)")
+        if (r.force_shadow_map and not r.shadow_hint) or (r.force_specular_cue and not r.specular_hint):
+            raise NotImplementedError("force_shadow_map / force_specular_cue without the hint crash in the reference "
+                                      "(width mismatch, SURVEY.md section 8a) and are rejected here")
+        self.has_shadow_hint = r.shadow_hint or r.force_shadow_map
+        self.has_specular_hint = r.specular_hint or r.force_specular_cue
+        self.sdf_network = SDFNetwork(config.sdf_network)
+        self.deviation_network = SingleVarianceNetwork(init_val=config.deviation_network.init_val)
+        color_d_in = 12 + (1 if self.has_shadow_hint else 0) + (len(r.specular_roughness) if self.has_specular_hint else 0)
+        self.color_network = ReflectanceNetwork(
+            d_feature=config.sdf_network.d_out_feat, d_in=color_d_in, d_out=3, config=config.reflectance_network,
+            shadow_hint=r.shadow_hint, specular_hint=r.specular_hint, specular_hint_len=len(r.specular_roughness))
+        self.has_outside_nerf = False
+        self.config = config
+        self.mlp_impl = mlp_impl
+        import weakref
+        self.sdf_network._owner = weakref.ref(self)
+        # kernel-side state (not parameters / buffers; rebuilt lazily per device)
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+        self.last_launch_count = 0
+
+    # -- C-ABI plumbing ---------------------------------------------------------------------------
+    def _c_config(self) -> _lib.NrhConfig:
+        r = self.config.renderer
+        c = _lib.NrhConfig()
+        c.n_samples, c.n_importance, c.up_sample_steps = r.n_samples, r.n_importance_samples, r.up_sample_steps
+        c.n_shadow_samples, c.n_shadow_importance = r.n_shadow_samples, r.n_shadow_importance_samples
+        c.shadow_hint, c.specular_hint = int(r.shadow_hint), int(r.specular_hint)
+        rough = list(r.specular_roughness)
+        if r.specular_hint and len(rough) > _lib.NRH_MAX_ROUGHNESS:
+            raise NotImplementedError(f"at most {_lib.NRH_MAX_ROUGHNESS} specular roughness lobes are supported")
+        c.n_roughness = len(rough) if r.specular_hint else 0
+        for i, v in enumerate(rough[:_lib.NRH_MAX_ROUGHNESS]):
+            c.roughness[i] = float(v)
+        c.shadow_ray_offset = float(r.shadow_ray_offset)
+        c.normalized_normals = int(getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value)
+        c.mlp_impl = _lib.MLP_IMPLS[self.mlp_impl]
+        return c
+
+    def _weight_tensors(self) -> List[torch.Tensor]:
+        ws = []
+        for l in range(8):
+            lin = getattr(self.sdf_network, f"lin{l}")
+            ws += [lin.effective_weight(), lin.bias]
+        ws += [self.sdf_network.out_sdf.effective_weight(), self.sdf_network.out_sdf.bias,
+               self.sdf_network.out_feat.effective_weight(), self.sdf_network.out_feat.bias]
+        for l in range(5):
+            lin = getattr(self.color_network, f"lin{l}")
+            ws += [lin.effective_weight(), lin.bias]
+        ws.append(self.deviation_network.variance)
+        return ws
+
+    def _ensure_packed(self, device: torch.device) -> torch.Tensor:
+        if device.type != "cuda":
+            raise RuntimeError("nrhints_b200 runs on CUDA devices only (there is no CPU fallback); "
+                               f"got tensors on {device}")
+        key = (device, self.mlp_impl, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        lib = _lib.load()
+        cfg = self._c_config()
+        with torch.no_grad():
+            ws = [w.detach().to(device=device, dtype=torch.float32).contiguous() for w in self._weight_tensors()]
+        raw = _lib.NrhRawWeights()
+        for l in range(8):
+            raw.sdf_W[l], raw.sdf_b[l] = ws[2 * l].data_ptr(), ws[2 * l + 1].data_ptr()
+        raw.sdf_out_W, raw.sdf_out_b, raw.feat_W, raw.feat_b = (w.data_ptr() for w in ws[16:20])
+        for l in range(5):
+            raw.col_W[l], raw.col_b[l] = ws[20 + 2 * l].data_ptr(), ws[21 + 2 * l].data_ptr()
+        raw.variance = ws[30].data_ptr()
+        nbytes = lib.nrh_packed_weights_bytes(C.byref(cfg))
+        if self._packed is None or self._packed.numel() < nbytes or self._packed.device != device:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(lib.nrh_pack_weights(C.byref(cfg), C.byref(raw), self._packed.data_ptr(), nbytes, stream),
+                       "nrh_pack_weights")
+        self._packed_key = key
+        self._pack_keepalive = ws            # keep sources alive until the stream has consumed them
+        return self._packed
+
+    def _ensure_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._workspace
+
+    # -- point queries (SDFNetwork.sdf / .gradient / .forward, extract_fields) --------------------------
+    @torch.no_grad()
+    def sdf_query(self, pts: torch.Tensor, want_grad: bool = False, want_feat: bool = False):
+        lib = _lib.load()
+        device = pts.device
+        packed = self._ensure_packed(device)
+        cfg = self._c_config()
+        x = pts.detach().to(torch.float32).reshape(-1, 3).contiguous()
+        N = x.shape[0]
+        sdf = torch.empty(N, dtype=torch.float32, device=device)
+        grad = torch.empty(N, 3, dtype=torch.float32, device=device) if want_grad else None
+        feat = torch.empty(N, 256, dtype=torch.float32, device=device) if want_feat else None
+        wsb = lib.nrh_query_workspace_bytes(C.byref(cfg), N)
+        ws = self._ensure_workspace(wsb, device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.nrh_sdf_query(C.byref(cfg), packed.data_ptr(), x.data_ptr(), N, sdf.data_ptr(),
+                                         grad.data_ptr() if want_grad else None, feat.data_ptr() if want_feat else None,
+                                         ws.data_ptr(), ws.numel(), stream), "nrh_sdf_query")
+        self.last_launch_count = lib.nrh_last_launch_count()
+        return sdf, grad, feat
+
+    # -- the hot path ------------------------------------------------------------------------------------
+    def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
+                global_step: int = 0, return_extras: bool = False) -> RenderOutput:
+        lib = _lib.load()
+        rays_o = ray_bundle.origins
+        device = rays_o.device
+        packed = self._ensure_packed(device)
+        cfg = self._c_config()
+        r = self.config.renderer
+        R = rays_o.shape[0]
+        S = r.n_samples + r.n_importance_samples
+        Ss = r.n_shadow_samples + r.n_shadow_importance_samples
+        f32 = dict(dtype=torch.float32, device=device)
+
+        def prep(t):
+            return t.detach().to(**f32).contiguous()
+        o, d, pl = prep(rays_o), prep(ray_bundle.directions), prep(ray_bundle.pl_positions)
+        near, far = prep(ray_bundle.nears), prep(ray_bundle.fars)
+        bg = prep(background_rgb).reshape(-1) if background_rgb is not None else None
+
+        warmup = bool(is_training and global_step < self.config.geometry_warmup_end)
+        cos_anneal = 1.0
+        if is_training and self.config.anneal_end > 0:
+            cos_anneal = min(1.0, global_step / self.config.anneal_end)
+        # RNG draws in the reference's order (:682 then :394)
+        jit_p = jit_s = None
+        if is_training:
+            jit_p = torch.rand([R, 1], device=device)
+            if self.has_shadow_hint and not warmup and r.shadow_hint:
+                jit_s = torch.rand([R, r.n_shadow_samples], device=device)
+
+        out = dict(
+            rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, 1, **f32), weights=torch.empty(R, S, **f32),
+            inside_sphere=torch.empty(R, S, **f32), analytic_normals=torch.empty(R, S, 3, **f32),
+            normalized_normals=torch.empty(R, S, 3, **f32),
+            visibilities=torch.empty(R, 1, **f32) if r.shadow_hint else None,
+            specular_cue=torch.empty(R, S, len(r.specular_roughness), **f32) if r.specular_hint else None,
+            inv_s=torch.empty(1, **f32),
+            z_vals=torch.empty(R, S, **f32) if return_extras else None,
+            z_shadow=torch.zeros(R, Ss, **f32) if (return_extras and r.shadow_hint) else None,
+            sampled_color=torch.empty(R, S, 3, **f32) if return_extras else None)
+        c_rays = _lib.NrhRays(o.data_ptr(), d.data_ptr(), pl.data_ptr(), near.data_ptr(), far.data_ptr())
+        c_out = _lib.NrhOutputs(**{k: (v.data_ptr() if v is not None else None) for k, v in out.items()})
+        wsb = lib.nrh_workspace_bytes(C.byref(cfg), R)
+        ws = self._ensure_workspace(wsb, device)
+        if R > 0:
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(lib.nrh_render_forward(
+                    C.byref(cfg), packed.data_ptr(), C.byref(c_rays), R, bg.data_ptr() if bg is not None else None,
+                    jit_p.data_ptr() if jit_p is not None else None, jit_s.data_ptr() if jit_s is not None else None,
+                    float(cos_anneal), int(warmup), C.byref(c_out), ws.data_ptr(), ws.numel(), stream),
+                    "nrh_render_forward")
+            self.last_launch_count = lib.nrh_last_launch_count()
+
+        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6).to(device)
+        s_val = (1.0 / inv_s).reshape(1, 1).expand(R, S)
+        return RenderOutput(
+            rgb=out["rgb"], depth=out["depth"], weights=out["weights"], s_val=s_val,
+            inside_sphere=out["inside_sphere"], relax_inside_sphere=out["inside_sphere"],      # reference quirk (:746)
+            analytic_normals=out["analytic_normals"], normalized_analytic_normals=out["normalized_normals"],
+            visibilities=out["visibilities"] if self.has_shadow_hint else None,
+            specular_cue=out["specular_cue"] if self.has_specular_hint else None,
+            z_vals=out["z_vals"], z_shadow=out["z_shadow"], sampled_color=out["sampled_color"])
+
+    # -- meshing helpers (models/neus_hint_model.py:68-93,753-758) -------------------------------------------
+    @torch.no_grad()
+    def extract_fields(self, bound_min, bound_max, resolution: int, chunk: int = 1 << 22) -> np.ndarray:
+        """-sdf on a resolution^3 grid (the reference walks 64^3 blocks; here the grid is streamed in
+        `chunk`-point slabs straight through the SDF kernel)."""
+        device = next(self.parameters()).device
+        xs = [torch.linspace(float(bound_min[i]), float(bound_max[i]), resolution, device=device) for i in range(3)]
+        u = np.zeros([resolution] * 3, dtype=np.float32)
+        rows = max(1, chunk // (resolution * resolution))
+        for x0 in range(0, resolution, rows):
+            xx, yy, zz = torch.meshgrid(xs[0][x0:x0 + rows], xs[1], xs[2], indexing="ij")
+            pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+            val = -self.sdf_query(pts)[0]
+            u[x0:x0 + rows] = val.reshape(xx.shape).cpu().numpy()
+        return u
+
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        try:
+            import mcubes
+        except ImportError as e:          # same dependency as the reference (models/neus_hint_model.py:6)
+            raise ImportError("extract_geometry needs PyMCubes (`mcubes`), as the reference does") from e
+        u = self.extract_fields(bound_min, bound_max, resolution)
+        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        b_max = torch.as_tensor(bound_max).detach().cpu().numpy()
+        b_min = torch.as_tensor(bound_min).detach().cpu().numpy()
+        vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
+        return vertices, triangles

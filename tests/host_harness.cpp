@@ -1,0 +1,58 @@
+// Host build of nrhints_b200/csrc/ray_math.cuh for the CPU test-suite (g++, no CUDA):
+// the per-ray sampler / compositor math is header-only host+device code, so the exact
+// functions the kernels call are unit-tested against the oracle without a GPU.
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product.
+#include "../nrhints_b200/csrc/ray_math.cuh"
+
+using namespace nrh;
+
+extern "C" {
+
+void h_linspace01(int n, float* out) { for (int j = 0; j < n; ++j) out[j] = linspace01(j, n); }
+
+void h_coarse_z(float near, float far, int n, int has_jitter, float jitter, float* z) {
+    coarse_z(near, far, n, has_jitter != 0, jitter, SoA{z, 1});
+}
+
+void h_fourier_encode(const float* x, int D, int F, float* dst) { fourier_encode(x, D, F, dst, 1); }
+
+void h_upsample(const float* o, const float* d, int k, const float* z, const float* sdf, float inv_s, int n_new,
+                float* wbuf, float* z_new) {
+    upsample_new_z(o, d, k, CSoA{z, 1}, CSoA{sdf, 1}, inv_s, n_new, SoA{wbuf, 1}, SoA{z_new, 1});
+}
+
+void h_merge(int k, const float* z_old, const float* s_old, int n, const float* z_new, const float* s_new,
+             float* z_out, float* s_out, int with_sdf) {
+    merge_sorted(k, CSoA{z_old, 1}, CSoA{s_old, 1}, n, CSoA{z_new, 1}, CSoA{s_new, 1}, SoA{z_out, 1}, SoA{s_out, 1}, with_sdf != 0);
+}
+
+void h_sections(const float* z, int S, float last_dist, float* dist, float* mid) {
+    for (int j = 0; j < S; ++j) section(CSoA{z, 1}, j, S, last_dist, dist[j], mid[j]);
+}
+
+// returns wsum, depth, nsum[3] in res[5]
+void h_composite_primary(const float* o, const float* d, int S, const float* z, float last_dist, const float* sdf,
+                         const float* gx, const float* gy, const float* gz, float inv_s, float cos_anneal,
+                         float* w, float* inside, float* nx, float* ny, float* nz, float* res) {
+    PrimaryComposite pc = composite_primary(o, d, S, CSoA{z, 1}, last_dist, CSoA{sdf, 1}, CSoA{gx, 1}, CSoA{gy, 1}, CSoA{gz, 1},
+                                            inv_s, cos_anneal, SoA{w, 1}, SoA{inside, 1}, SoA{nx, 1}, SoA{ny, 1}, SoA{nz, 1});
+    res[0] = pc.wsum; res[1] = pc.depth; res[2] = pc.nsum[0]; res[3] = pc.nsum[1]; res[4] = pc.nsum[2];
+}
+
+float h_shadow_init(const float* pl, const float* hit, int n, float offset, int has_jitter, const float* jitter,
+                    float* dir_out, float* z) {
+    return shadow_ray_init(pl, hit, n, offset, has_jitter != 0, CSoA{jitter, 1}, dir_out, SoA{z, 1});
+}
+
+float h_shadow_transmittance(const float* d, int S, const float* z, float last_dist, const float* sdf, const float* gx,
+                             const float* gy, const float* gz, float inv_s, float cos_anneal) {
+    return shadow_transmittance(d, S, CSoA{z, 1}, last_dist, CSoA{sdf, 1}, CSoA{gx, 1}, CSoA{gy, 1}, CSoA{gz, 1}, inv_s, cos_anneal);
+}
+
+void h_specular_cue(const float* hit_n, const float* pl, const float* hit, const float* d, int n_rough, const float* rough, float* cue) {
+    specular_cue(hit_n, pl, hit, d, n_rough, rough, cue);
+}
+
+void h_normalize3(const float* v, float* out) { normalize3(v, out); }
+
+}  // extern "C"

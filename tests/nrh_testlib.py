@@ -1,0 +1,173 @@
+"""Shared helpers of the test-suite: seeded weights / rays / cases, and the tolerance-based
+comparison used for every parity check (oracle vs reference goldens, CUDA vs oracle)."""
+from __future__ import annotations
+
+import hashlib
+import sys
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+GOLDEN_DIR = ROOT / "tests" / "golden"
+
+import nrhints_b200 as nb                      # noqa: E402
+from oracle import nrh_oracle as orc           # noqa: E402
+
+# ---- cases: (name, renderer-config overrides, R, mode) -------------------------------------------------
+CASES = {
+    # BASELINE.json config #1: 64 rays x 32 samples plumbing case
+    "cfg1_64x32": dict(R=64, renderer=dict(n_samples=16, n_importance_samples=16, n_shadow_samples=16,
+                                           n_shadow_importance_samples=16), weights="init", ray_seed=0),
+    # BASELINE.json config #2 shape (64+64 samples, both hints), small ray count
+    "cfg2_32x128": dict(R=32, renderer=dict(), weights="init", ray_seed=3407),
+    # trained-like: sharp s (inv_s ~ 403) and a non-spherical perturbed SDF
+    "sharp_32x128": dict(R=32, renderer=dict(), weights="sharp", ray_seed=11),
+    # training-mode forward: jitter on both marches, cos annealing half way
+    "train_16x128": dict(R=16, renderer=dict(), weights="init", ray_seed=5, training=True, global_step=25000, rng_seed=123),
+    # PLNaive preset: no hints (316-wide reflectance input)
+    "nohint_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, shadow_hint=False, specular_hint=False),
+                         weights="init", ray_seed=7),
+    # shadow hint only (325-wide input), analytic (un-normalised) normals, black background
+    "shadowonly_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, n_shadow_samples=32,
+                                                 n_shadow_importance_samples=32, specular_hint=False,
+                                                 normal_type=nb.NormalComputationType.Analytic),
+                             weights="sharp", ray_seed=9, bg=0.0),
+}
+
+
+def make_config(case: dict) -> nb.NeuSModelConfig:
+    return nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(**case.get("renderer", {})))
+
+
+def make_state(kind: str, cfg: nb.NeuSModelConfig) -> Dict[str, torch.Tensor]:
+    """Seeded renderer state_dict.  'init' = geometric init at the reference's seed 3407
+    (configs/main_config.py:44); 'sharp' = the same plus a deterministic perturbation of every
+    direction tensor and variance 0.6 (inv_s ~ 403) to mimic a trained, non-spherical field."""
+    torch.manual_seed(3407)
+    m = nb.NeuSHintRenderer(cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    if kind == "sharp":
+        g = torch.Generator().manual_seed(99)
+        for k in sorted(sd):
+            if k.endswith("weight_v"):
+                sd[k] = sd[k] + 0.02 * sd[k].std() * torch.randn(sd[k].shape, generator=g)
+            elif k.endswith("bias") and "out_" not in k:
+                sd[k] = sd[k] + 0.01 * torch.randn(sd[k].shape, generator=g)
+        sd["deviation_network.variance"] = torch.tensor(0.6)
+    return sd
+
+
+def state_digest(sd: Dict[str, torch.Tensor]) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def case_inputs(case: dict):
+    rays = orc.synthetic_rays(case["R"], seed=case["ray_seed"], crop=case.get("crop", 300))
+    bg = torch.full((1, 3), float(case.get("bg", 1.0)))
+    return rays, bg
+
+
+def case_jitters(case: dict, cfg: nb.NeuSModelConfig):
+    """The two torch.rand draws of training mode, in the reference's order."""
+    if not case.get("training"):
+        return None, None
+    torch.manual_seed(case["rng_seed"])
+    jp = torch.rand([case["R"], 1])
+    js = torch.rand([case["R"], cfg.renderer.n_shadow_samples]) if cfg.renderer.shadow_hint else None
+    return jp, js
+
+
+def run_oracle(case: dict, dtype=torch.float32):
+    cfg = make_config(case)
+    sd = make_state(case["weights"], cfg)
+    rays, bg = case_inputs(case)
+    jp, js = case_jitters(case, cfg)
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    training = bool(case.get("training"))
+    cos_anneal = min(1.0, case.get("global_step", 0) / cfg.anneal_end) if training else 1.0
+    with torch.no_grad():
+        out = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
+                                 rays["fars"], is_training=training, background_rgb=bg, cos_anneal=cos_anneal,
+                                 jitter_primary=jp, jitter_shadow=js, dtype=dtype)
+    return out
+
+
+OUT_FIELDS = ["rgb", "depth", "weights", "s_val", "inside_sphere", "analytic_normals",
+              "normalized_analytic_normals", "visibilities", "specular_cue"]
+
+
+def to_np(out) -> Dict[str, np.ndarray]:
+    get = (lambda k: out.get(k)) if isinstance(out, dict) else (lambda k: getattr(out, k, None))
+    res = {}
+    for k in OUT_FIELDS + ["z_vals", "z_shadow"]:
+        v = get(k)
+        if v is not None:
+            res[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    return res
+
+
+# fp32 noise floor: two valid fp32 evaluation orders of the same network (reference autograd vs the
+# oracle's explicit reverse sweep) differ by up to 2e-4 (init weights) / 1.7e-3 (perturbed "sharp"
+# weights, inv_s ~ 403) on per-sample normals, 4e-4 on depth and 5e-5 on rgb -- measured in
+# tests/golden/make_golden.py.  Gates below sit above that floor and at/below the BASELINE.json bar.
+TOL = {
+    "init": dict(per_ray_tol=1e-3, per_sample_tol=1e-3, normals_tol=1e-3),
+    "sharp": dict(per_ray_tol=1e-3, per_sample_tol=1e-3, normals_tol=6e-3),
+}
+TOL_ORACLE_VS_REF = {
+    "init": dict(per_ray_tol=1e-4, per_sample_tol=1e-4, normals_tol=5e-4),
+    "sharp": dict(per_ray_tol=5e-4, per_sample_tol=5e-4, normals_tol=4e-3),
+}
+
+
+def compare_outputs(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], per_ray_tol=1e-3, per_sample_tol=1e-3,
+                    normals_tol=None, max_displaced_frac=0.05, label="") -> Dict[str, float]:
+    """Parity gate (BASELINE.json: per-pixel max |d rgb| < 1e-3, PSNR delta < 0.01 dB), plus depth /
+    visibility (all rays, strict) and the per-sample RenderOutput fields.
+
+    Per-sample arrays are indexed by sorted sample position.  The reference's inverse-CDF sampler is
+    discontinuous on float noise: when the fp32 cumsum of the pdf rounds above 1.0 the last new sample of
+    an importance step lands one coarse bin earlier (sample_pdf's `denom < 1e-5 -> 1` branch,
+    models/neus_hint_model.py:60-63) -- two fp32 evaluations of the same ray (even the reference on CPU vs
+    GPU) disagree on that far-end, zero-weight sample for ~30% of the rays.  Samples whose own position or
+    whose successor's position (it defines the section mid-point) differ are therefore masked out; the
+    masked fraction must stay below `max_displaced_frac` of all samples."""
+    stats = {}
+    for k in ("rgb", "depth", "visibilities"):
+        if k in a and k in b:
+            d = float(np.max(np.abs(a[k].astype(np.float64) - b[k].astype(np.float64))))
+            stats[k] = d
+            assert d < per_ray_tol, f"{label}: max |d {k}| = {d:.3e} >= {per_ray_tol}"
+    mse = float(np.mean((a["rgb"].astype(np.float64) - b["rgb"].astype(np.float64)) ** 2))
+    stats["psnr_between"] = float(10 * np.log10(1.0 / max(mse, 1e-30)))
+    R, S = a["weights"].shape
+    ok = np.ones((R, S), dtype=bool)
+    if "z_vals" in a and "z_vals" in b:
+        same = np.abs(a["z_vals"] - b["z_vals"]) < 2e-5
+        ok = same & np.concatenate([same[:, 1:], np.ones((R, 1), dtype=bool)], axis=1)
+        stats["displaced_sample_frac"] = float(1.0 - ok.mean())
+        stats["displaced_ray_frac"] = float(1.0 - same.all(axis=1).mean())
+        assert stats["displaced_sample_frac"] <= max_displaced_frac, \
+            f"{label}: {stats['displaced_sample_frac']:.4f} of the samples are displaced"
+    for k in ("weights", "inside_sphere", "analytic_normals", "normalized_analytic_normals", "specular_cue", "s_val"):
+        if k in a and k in b:
+            d = np.abs(a[k].astype(np.float64) - b[k].astype(np.float64))
+            d = d.reshape(R, S, -1).max(axis=-1)[ok]
+            if k == "inside_sphere":      # 0/1 mask: a point within float noise of the unit sphere may flip
+                stats[k + "_flips"] = float((d > 0.5).mean()) if d.size else 0.0
+                assert stats[k + "_flips"] < 1e-3, f"{label}: inside_sphere flips {stats[k + '_flips']}"
+                continue
+            tol = normals_tol if ("normals" in k and normals_tol is not None) else per_sample_tol
+            m = float(d.max()) if d.size else 0.0
+            stats[k] = m
+            assert m < tol, f"{label}: max |d {k}| = {m:.3e} >= {tol}"
+    return stats

@@ -1,0 +1,66 @@
+"""The oracle against the committed reference fixtures (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from the unmodified reference).  This is what pins oracle/nrh_oracle.py."""
+import numpy as np
+import pytest
+import torch
+
+import nrh_testlib as T
+
+
+@pytest.mark.parametrize("name", list(T.CASES))
+def test_oracle_matches_reference_fixture(name):
+    case = T.CASES[name]
+    fx = np.load(T.GOLDEN_DIR / f"{name}.npz")
+    cfg = T.make_config(case)
+    sd = T.make_state(case["weights"], cfg)
+    assert T.state_digest(sd) == str(fx["digest"]), "seeded weights differ from the ones the fixture was made with"
+    rays, bg = T.case_inputs(case)
+    for k, v in rays.items():
+        np.testing.assert_array_equal(v.numpy(), fx["in_" + k])
+    got = T.to_np(T.run_oracle(case))
+    want = {k[4:]: fx[k] for k in fx.files if k.startswith("out_")}
+    stats = T.compare_outputs(got, want, label=f"oracle-vs-fixture[{name}]", **T.TOL_ORACLE_VS_REF[case["weights"]])
+    assert stats["psnr_between"] > 80.0
+
+
+def test_fixture_quirks():
+    """Behaviours of the reference recorded in SURVEY.md section 8c."""
+    fx = np.load(T.GOLDEN_DIR / "cfg2_32x128.npz")
+    assert fx["out_rgb"].shape == (32, 3) and fx["out_weights"].shape == (32, 128)
+    assert fx["out_specular_cue"].shape == (32, 128, 4) and fx["out_visibilities"].shape == (32, 1)
+    # specular cue / s_val are per-ray values broadcast over the samples
+    assert np.all(fx["out_specular_cue"] == fx["out_specular_cue"][:, :1])
+    assert np.all(fx["out_s_val"] == fx["out_s_val"][0, 0])
+
+
+def test_manual_reverse_matches_autograd():
+    """The oracle's explicit reverse sweep == autograd.grad of the forward (fields/sdf_field.py:136-148)."""
+    from oracle import nrh_oracle as orc
+    cfg = T.make_config(T.CASES["cfg2_32x128"])
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    W = orc.effective_weights(T.make_state("sharp", cfg), torch.float64)
+    g = torch.Generator().manual_seed(0)
+    pts = (torch.rand(257, 3, generator=g, dtype=torch.float64) - 0.5) * 2.4
+    manual = orc.sdf_mlp(W, pts, ocfg, want_grad=True)["grad"]
+    x = pts.clone().requires_grad_(True)
+    y = orc.sdf_mlp(W, x, ocfg)["sdf"]
+    auto = torch.autograd.grad(y.sum(), x)[0]
+    assert torch.allclose(manual, auto, rtol=1e-9, atol=1e-11)
+
+
+def test_oracle_edge_cases():
+    """Rays that miss the unit sphere entirely and a single-ray... (reference needs >= 2 points for squeeze(),
+    quirk Q7) batch of 2."""
+    from oracle import nrh_oracle as orc
+    cfg = T.make_config(T.CASES["cfg1_64x32"])
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    sd = T.make_state("init", cfg)
+    o = torch.tensor([[0.0, 0.0, 4.0], [3.0, 3.0, 4.0]])
+    d = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, -1.0]]), dim=-1)
+    pl = torch.tensor([[0.0, 4.5, 0.0], [4.5, 0.0, 0.0]])
+    mid = -(o * d).sum(-1, keepdim=True)
+    out = orc.render_forward(sd, ocfg, o, d, pl, mid - 1.0, mid + 1.0, background_rgb=torch.ones(1, 3))
+    assert out["weights"][0].sum() > 0.9          # hits the init sphere
+    assert out["weights"][1].sum() < 1e-2          # passes far outside
+    assert torch.allclose(out["rgb"][1], torch.ones(3), atol=2e-2)
+    assert torch.isfinite(out["rgb"]).all() and torch.isfinite(out["analytic_normals"]).all()
