@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark of the NRHints ray-march hot path (BASELINE.json config #2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R] [--mlp auto|fp32|tcgen05]
+
+A step = one NeuSHintRenderer.forward over 4096 rays x 128 samples (64 coarse + 64 importance, one shadow
+ray of 64 + 64 samples per primary ray, both hints, white background, inference mode) of the synthetic
+800x800 workload (nrhints_b200/workload.py), random-init (geometric) weights at seed 3407.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+
+--impl reference times the reference algorithm on the host cores: the reference is pure Python/PyTorch and
+cannot travel to the GPU box, so the timed code is the oracle port (oracle/nrh_oracle.py, pinned to the
+reference by the golden fixtures), on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+FLOP_PER_RAY = 766.6e6          # algorithmic, de-duplicated forward FLOPs per ray
+BYTES_PER_RAY = 7240            # 52 B in + 7188 B out
+# dominant kernel = the fine-pass SDF kernel (forward with feature head + reverse sweep) over R*128 points
+FLOP_PER_FINE_POINT = 1049088.0 + 918016.0
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(n_rays: int, repeats: int):
+    """The reference algorithm (oracle port) on the host cores, all threads, on `n_rays` rays of the workload."""
+    from oracle import nrh_oracle as orc
+    import nrhints_b200 as nb
+    from nrhints_b200.workload import synthetic_rays
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = nb.NeuSModelConfig()
+    torch.manual_seed(3407)
+    state = {k: v.detach().clone() for k, v in nb.NeuSHintRenderer(cfg).state_dict().items()}
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    rays = synthetic_rays(n_rays, seed=3407)
+    bg = torch.ones(1, 3)
+    times = []
+    for i in range(repeats + 1):                   # first pass = warm-up
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.render_forward(state, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
+                               rays["fars"], background_rgb=bg)
+        times.append(time.perf_counter() - t0)
+    times = sorted(times[1:]) if repeats > 0 else times
+    med = times[len(times) // 2]
+    return {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n_rays} rays x 128 samples of the same workload, 1 warm-up + median of {max(repeats, 1)} passes, "
+                      f"torch {torch.get_num_threads()} threads (oracle port of the reference PyTorch path)"}, med
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = 256
+    per_step = []
+    base, _ = cpu_reference_leg(n_rays, 0)           # warm-up pass
+    from oracle import nrh_oracle as orc  # noqa: F401
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_reference_leg(n_rays, 0)
+    vals = []
+    for _ in range(args.steps):
+        b, med = cpu_reference_leg(n_rays, 0)
+        vals.append(med)
+    ms = 1e3 * sum(vals) / len(vals)
+    value = n_rays / (sum(vals) / len(vals))
+    base.update(value=value)
+    line = {"impl": "reference", "metric": "rays/sec (4096 rays x 128 samples forward render)", "value": value, "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NRHints forward render, 64+64 samples, shadow 64+64, both hints, 800x800 synthetic scene, "
+                                   f"bounded sample of {n_rays} rays per step on host CPU", "rays_per_step": n_rays},
+            "cpu_baseline": base, "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import nrhints_b200 as nb
+    from nrhints_b200 import _lib
+    from nrhints_b200.workload import synthetic_rays
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    R = args.rays
+
+    cfg = nb.NeuSModelConfig()
+    torch.manual_seed(3407)
+    model = nb.NeuSHintRenderer(cfg, mlp_impl=args.mlp).to(dev)
+    host_rays = nb.RayBundle(**synthetic_rays(R, seed=3407 + rank)).pin_memory()      # each rank renders its own rays
+    dev_rays = host_rays.to(dev)
+    bg = torch.ones(1, 3, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                       # > 126 MB L2
+
+    def step():
+        return model(dev_rays, is_training=False, background_rgb=bg)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = model.last_launch_count + 5          # + the torch ops of the wrapper (s_val, inv_s)
+    lib = _lib.load()
+    import ctypes as C
+    ccfg = model._c_config()
+    engine = "tcgen05-fp16x3" if (args.mlp == "tcgen05" or (args.mlp == "auto" and _engine_is_tc(lib, ccfg))) else "fp32-simt"
+
+    # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed between steps ----------
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * R / (ms_per_step * 1e-3)
+
+    # ---- e2e: host (pinned) rays -> device -> forward -> full RenderOutput back on the host -------------------
+    e2e_steps = max(3, min(K, 5))
+    out_host = None
+    for _ in range(2):
+        out_host = model(host_rays.to(dev, non_blocking=True), background_rgb=bg).to("cpu")
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        o = model(host_rays.to(dev, non_blocking=True), is_training=False, background_rgb=bg)
+        out_host = o.to("cpu")
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = sum(v.numel() * 4 for v in (host_rays.origins, host_rays.directions, host_rays.pl_positions, host_rays.nears, host_rays.fars))
+    d2h = sum(v.numel() * v.element_size() for k, v in out_host.as_dict().items() if v is not None and k != "relax_inside_sphere")
+
+    # ---- roofline of the dominant kernel: fine-pass SDF kernel (forward + feature head + reverse sweep) --------
+    roof = None
+    if rank == 0:
+        peaks = measured_peaks()
+        pts = (torch.rand(R * 128, 3, device=dev) - 0.5) * 2.0
+        for _ in range(2):
+            model.sdf_query(pts, want_grad=True, want_feat=True)
+        torch.cuda.synchronize()
+        ks = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib_rc = model.sdf_query(pts, want_grad=True, want_feat=True)
+            b.record()
+            torch.cuda.synchronize()
+            ks.append(a.elapsed_time(b))
+            del lib_rc
+        k_ms = sum(ks) / len(ks)          # includes three tiny torch.empty allocations (cached allocator, no kernel)
+        achieved = FLOP_PER_FINE_POINT * R * 128 / (k_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "sdf_mlp (fine pass: forward + feature head + reverse sweep)", "engine": engine,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_kind": f"cuBLAS bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); the fp16x3 split issues 3 MMAs per "
+                             "logical product, the fp32-simt engine runs on FFMA (75 TFLOP/s nominal)",
+                "kernel_ms": k_ms, "flop_per_launch": FLOP_PER_FINE_POINT * R * 128, "traffic": None,
+                "whole_step": {"achieved_tflops": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12,
+                               "frac_of_tensor_peak": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12 / peak,
+                               "hbm_algorithmic_gbs": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_leg(256, 1)
+
+    if rank == 0:
+        line = {
+            "metric": "rays/sec (4096 rays x 128 samples forward render)", "value": value, "unit": "rays/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if engine == "fp32-simt" else "f32 (fp16 hi/lo split operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "NRHints NeuSHintRenderer.forward, BASELINE config #2: 4096 rays x (64+64) samples, shadow ray 64+64, "
+                                   "shadow+specular hints, white bg, 800x800 synthetic scene, geometric-init weights seed 3407",
+                       "rays_per_gpu": R, "samples_per_ray": 128, "mlp_engine": engine, "parallelism": f"rays sharded x{world}, no data-path collective",
+                       "l2": "256 MiB buffer rewritten between timed steps (L2 flush); per-step working set ~0.9 GB > 126 MB L2"},
+            "e2e": {"value": world * R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "pinned host RayBundle -> device, forward, full RenderOutput -> host (pipelines/base_pipeline.py:114-120 pattern)"},
+            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _engine_is_tc(lib, ccfg):
+    import ctypes as C
+    from nrhints_b200 import _lib
+    c2 = _lib.NrhConfig.from_buffer_copy(ccfg)
+    c2.mlp_impl = _lib.NRH_MLP_TCGEN05
+    return lib.nrh_check_config(C.byref(c2)) == 0
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+"""Parity tests proper: the CUDA path (through the C ABI, via the host mirror of NeuSHintRenderer)
+against the oracle on the same seeded inputs, and against the committed reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+import nrh_testlib as T
+import nrhints_b200 as nb
+from oracle import nrh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+IMPLS = ["fp32", "auto"]
+
+
+def build_module(case, impl):
+    cfg = T.make_config(case)
+    sd = T.make_state(case["weights"], cfg)
+    m = nb.NeuSHintRenderer(cfg, mlp_impl=impl)
+    m.load_state_dict(sd)
+    return m.cuda(), cfg, sd
+
+
+def run_cuda(case, impl):
+    m, cfg, sd = build_module(case, impl)
+    rays, bg = T.case_inputs(case)
+    bundle = nb.RayBundle(**rays).to("cuda")
+    training = bool(case.get("training"))
+    if training:
+        torch.manual_seed(case["rng_seed"])
+        torch.cuda.manual_seed(case["rng_seed"])
+    out = m(bundle, is_training=training, background_rgb=bg.cuda(), global_step=case.get("global_step", 0),
+            return_extras=True)
+    torch.cuda.synchronize()
+    assert m.last_launch_count > 10
+    return out, m
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", [n for n in T.CASES if not T.CASES[n].get("training")])
+def test_forward_matches_oracle_and_fixture(name, impl):
+    case = T.CASES[name]
+    out, _ = run_cuda(case, impl)
+    got = T.to_np(out)
+    for k, v in got.items():
+        assert np.isfinite(v).all(), k
+    tol = T.TOL[case["weights"]]
+    want = T.to_np(T.run_oracle(case))
+    s1 = T.compare_outputs(got, want, label=f"cuda[{impl}]-vs-oracle[{name}]", **tol)
+    fx = np.load(T.GOLDEN_DIR / f"{name}.npz")
+    ref = {k[4:]: fx[k] for k in fx.files if k.startswith("out_")}
+    s2 = T.compare_outputs(got, ref, label=f"cuda[{impl}]-vs-reference-fixture[{name}]", **tol)
+    # BASELINE.json gate: PSNR delta < 0.01 dB against any ground truth <=> the two images are > 60 dB apart
+    assert s1["psnr_between"] > 60 and s2["psnr_between"] > 60
+    print(name, impl, {k: f"{v:.2e}" for k, v in s2.items()})
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_training_mode_forward(impl):
+    """jitter on both marches + cos annealing; the jitters are drawn by torch.rand on the device, so the oracle
+    is fed the very same numbers."""
+    case = T.CASES["train_16x128"]
+    m, cfg, sd = build_module(case, impl)
+    rays, bg = T.case_inputs(case)
+    R = case["R"]
+    torch.manual_seed(7)
+    jp = torch.rand([R, 1], device="cuda")
+    js = torch.rand([R, cfg.renderer.n_shadow_samples], device="cuda")
+    torch.manual_seed(7)
+    out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"],
+            return_extras=True)
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    with torch.no_grad():
+        want = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
+                                  rays["fars"], is_training=True, background_rgb=bg, cos_anneal=0.5,
+                                  jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
+    T.compare_outputs(T.to_np(out), T.to_np(want), label=f"cuda[{impl}]-train", **T.TOL["init"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_warmup_zeroes_hints(impl):
+    case = dict(T.CASES["cfg1_64x32"])
+    cfg = nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(**case["renderer"]), geometry_warmup_end=100)
+    m = nb.NeuSHintRenderer(cfg, mlp_impl=impl)
+    m.load_state_dict(T.make_state("init", cfg)); m.cuda()
+    rays, bg = T.case_inputs(case)
+    out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=10)
+    assert float(out.visibilities.abs().max()) == 0.0 and float(out.specular_cue.abs().max()) == 0.0
+    assert torch.isfinite(out.rgb).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kind", ["init", "sharp"])
+def test_sdf_query_matches_oracle(kind, impl):
+    """SDFNetwork.sdf / .gradient / .forward on arbitrary points, ragged N (not a multiple of the tile)."""
+    cfg = nb.NeuSModelConfig()
+    sd = T.make_state(kind, cfg)
+    m = nb.NeuSHintRenderer(cfg, mlp_impl=impl); m.load_state_dict(sd); m.cuda()
+    g = torch.Generator().manual_seed(1)
+    pts = torch.cat([(torch.rand(1000, 3, generator=g) - 0.5) * 2.6,                 # inside the unit sphere region
+                     4.5 * torch.nn.functional.normalize(torch.randn(77, 3, generator=g), dim=-1)])   # at light distance
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    W = orc.effective_weights(sd)
+    want = orc.sdf_mlp(W, pts, ocfg, want_feat=True, want_grad=True)
+    full = m.sdf_network(pts.cuda())
+    grad = m.sdf_network.gradient(pts.cuda())
+    sdf = m.sdf_network.sdf(pts.cuda())
+    assert full.shape == (1077, 257) and grad.shape == (1077, 1, 3) and sdf.shape == (1077, 1)
+    # fp32 noise grows with |x| (Fourier arguments up to 430 rad at the light distance)
+    assert (sdf.cpu() - want["sdf"]).abs().max() < 2e-5
+    assert (full[:, 1:].cpu() - want["feat"]).abs().max() < 2e-4
+    assert (grad[:, 0].cpu() - want["grad"]).abs().max() < (2e-3 if kind == "sharp" else 3e-4)
+    w64 = orc.sdf_mlp(orc.effective_weights(sd, torch.float64), pts.double(), ocfg, want_grad=True)
+    print(kind, impl, "sdf err vs fp64:", float((sdf.cpu().double() - w64["sdf"]).abs().max()),
+          "grad err vs fp64:", float((grad[:, 0].cpu().double() - w64["grad"]).abs().max()))
+
+
+def test_edge_cases():
+    """R = 1, R not a multiple of anything, rays that miss the sphere, R = 0."""
+    cfg = nb.NeuSModelConfig()
+    m = nb.NeuSHintRenderer(cfg, mlp_impl="auto"); m.load_state_dict(T.make_state("init", cfg)); m.cuda()
+    rays = orc.synthetic_rays(37, seed=2, crop=800)
+    full = m(nb.RayBundle(**rays).to("cuda"), background_rgb=torch.ones(1, 3).cuda())
+    one = m(nb.RayBundle(**{k: v[5:6] for k, v in rays.items()}).to("cuda"), background_rgb=torch.ones(1, 3).cuda())
+    assert torch.allclose(one.rgb, full.rgb[5:6], atol=1e-5)           # rays are independent
+    empty = m(nb.RayBundle(**{k: v[:0] for k, v in rays.items()}).to("cuda"))
+    assert empty.rgb.shape == (0, 3)
+    assert torch.equal(full.relax_inside_sphere, full.inside_sphere)     # reference quirk Q1
+
+
+def test_full_size_properties():
+    """BASELINE.json config #2 size (4096 x 128): size-independent properties."""
+    cfg = nb.NeuSModelConfig()
+    m = nb.NeuSHintRenderer(cfg, mlp_impl="auto"); m.load_state_dict(T.make_state("init", cfg)); m.cuda()
+    rays = orc.synthetic_rays(4096, seed=3407, crop=800)
+    b = nb.RayBundle(**rays).to("cuda")
+    out = m(b, background_rgb=torch.ones(1, 3).cuda(), return_extras=True)
+    assert torch.isfinite(out.rgb).all() and out.rgb.min() >= 0 and out.rgb.max() <= 1.0 + 1e-5
+    assert (out.weights >= 0).all() and (out.weights.sum(-1) <= 1.0 + 1e-4).all()
+    assert (out.z_vals[:, 1:] >= out.z_vals[:, :-1]).all()                               # sortedness
+    assert (out.visibilities >= 0).all() and (out.visibilities <= 1.0 + 1e-5).all()
+    n = out.normalized_analytic_normals.norm(dim=-1)
+    assert (n - 1).abs().max() < 1e-4
+    # determinism + batch-composition independence (a chunked render equals the full one)
+    out2 = m(b, background_rgb=torch.ones(1, 3).cuda())
+    assert torch.equal(out.rgb, out2.rgb)
+    chunk = m(nb.RayBundle(**{k: v[512:1024] for k, v in rays.items()}).to("cuda"), background_rgb=torch.ones(1, 3).cuda())
+    assert torch.allclose(chunk.rgb, out.rgb[512:1024], atol=1e-5)
+    # a 512-ray slice against the oracle
+    sl = {k: v[:256] for k, v in rays.items()}
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    with torch.no_grad():
+        want = orc.render_forward(T.make_state("init", cfg), ocfg, sl["origins"], sl["directions"], sl["pl_positions"],
+                                  sl["nears"], sl["fars"], background_rgb=torch.ones(1, 3))
+    assert (out.rgb[:256].cpu() - want["rgb"]).abs().max() < 1e-3
+    assert (out.depth[:256].cpu() - want["depth"]).abs().max() < 1e-3
