@@ -270,7 +270,7 @@ int nrh_pack_weights(const NrhConfig* cfg, const NrhRawWeights* raw, void* packe
     }
     if ((rc = transpose_slice(raw->col_W[4], 256, 3, 0, 256, P + L.col_w4t, 4, 0, st))) return rc;
     if ((rc = copy_rows(raw->col_b[4], 1, 3, P + L.col_b4, 4, st))) return rc;
-    if (tc_available()) { if ((rc = tc_pack(*cfg, L, packed, st))) return rc; }
+    if (tc_available()) { if ((rc = tc_pack(*cfg, L, *raw, packed, st))) return rc; }
     return NRH_OK;
 }
 

@@ -1,21 +1,738 @@
-// tcgen05 tensor-core MLP engine -- placeholder until the split-fp16 kernel lands.
+// tcgen05 tensor-core MLP engine (NRH_MLP_TCGEN05) for sm_100a.
+//
+// One persistent CTA per SM owns a tile of 128 points (the UMMA M dimension).  Activations never leave the
+// SM: they live in shared memory as fp16 K-major SWIZZLE_128B operand tiles, accumulators live in TMEM
+// (two 128x256 fp32 accumulators = all 512 columns, ping-ponged across layers so the epilogue of layer l
+// overlaps the MMAs of layer l+1 chunk by chunk).  Weights are pre-packed as ready-to-use operand images and
+// streamed from L2 by the TMA unit (cp.async.bulk) through a 3-stage mbarrier ring.
+//
+// Precision: the SDF network needs fp32-grade operands (hard part 1), so every logical product
+// is issued as three fp16 MMAs on hi/lo splits (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, ~22-bit operands, fp32
+// accumulate); operands are pre-scaled by powers of two so the lo parts stay normal.  The reflectance network
+// enters the pixel through a sigmoid and is safe in a single fp16 pass.
+//
+// Warp roles (320 threads): warp 0 = weight producer (TMA), warp 1 = MMA issuer (one elected thread),
+// warps 2..9 = epilogue (TMEM -> registers -> bias/activation/split -> swizzled smem operand for the next layer).
+//
+// Reference semantics: /root/reference/fields/sdf_field.py:106-148, fields/reflectance_network.py:68-96,
+// fields/encodings.py:168-176.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
 #include "mlp_tc.cuh"
+#include "tc_primitives.cuh"
 
 namespace nrh {
 
-bool tc_available() { return false; }
-size_t tc_packed_bytes(const NrhConfig&) { return 0; }
-size_t tc_scratch_bytes(int) { return 0; }
-int tc_pack(const NrhConfig&, const PackedLayout&, void*, cudaStream_t) { return NRH_OK; }
-int sdf_mlp_tc(const void*, const PackedLayout&, Strided3, int64_t, float*, float*, float*, float*, int64_t, float*,
-               float*, size_t, int, cudaStream_t) {
-    set_error("tcgen05 engine not built");
-    return NRH_ERR_UNSUPPORTED;
+namespace {
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int NTHREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr int NSTAGES = 3;
+constexpr uint32_t IMG = 32768;            // one [256 x 64] fp16 weight image
+constexpr uint32_t IMG_SMALL = 8192;       // one [64 x 64] fp16 weight image (reverse layer 0)
+constexpr uint32_t A_CHUNK = 16384;        // one [128 x 64] fp16 activation chunk
+constexpr float W_SCALE = 64.0f;           // weights are stored * 2^6
+constexpr float ACT_SCALE = 16.0f;         // forward activations are stored * 2^4
+constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
+constexpr float SQRT2F = 1.41421354f;
+
+// ---- tensor-core section of the packed weight buffer (byte offsets from the section start) ----------------
+struct TcLayout {
+    uint32_t fwd[SDF_LAYERS];     // l = 0: 2 images (hi, lo); l >= 1: 4 chunks x (hi, lo)
+    uint32_t feat;                // 8 images
+    uint32_t rev[SDF_LAYERS];     // l >= 1: 8 images of W_l^T; l = 0: 8 small images
+    uint32_t col[4];              // reflectance hidden layers: 6 / 4 / 4 / 4 images (single pass)
+    uint32_t total;
+};
+__host__ __device__ inline TcLayout tc_layout() {
+    TcLayout t{};
+    uint32_t off = 0;
+    for (int l = 0; l < SDF_LAYERS; ++l) { t.fwd[l] = off; off += (l == 0 ? 2 : 8) * IMG; }
+    t.feat = off; off += 8 * IMG;
+    for (int l = 0; l < SDF_LAYERS; ++l) { t.rev[l] = off; off += (l == 0 ? 8 * IMG_SMALL : 8 * IMG); }
+    for (int l = 0; l < 4; ++l) { t.col[l] = off; off += (l == 0 ? 6 : 4) * IMG; }
+    t.total = off;
+    return t;
 }
-int color_mlp_tc(const void*, const PackedLayout&, Strided3, Strided3, const float*, const float*, int64_t, int64_t,
-                 float*, float*, float*, float*, size_t, int, cudaStream_t) {
-    set_error("tcgen05 engine not built");
-    return NRH_ERR_UNSUPPORTED;
+
+// ---- shared memory map ---------------------------------------------------------------------------------------
+constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * IMG;    // sdf kernel
+constexpr uint32_t SMC_A = 0, SMC_B = 6 * A_CHUNK, SMC_MISC = SMC_B + NSTAGES * IMG;                 // color kernel
+constexpr uint32_t SM_MISC_BYTES = 2048;
+constexpr size_t SDF_SMEM = SM_MISC + SM_MISC_BYTES + 1024;     // + slack for manual 1024-B alignment
+constexpr size_t COL_SMEM = SMC_MISC + SM_MISC_BYTES + 1024;
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float softplus100(float x, float& dsig) {
+    const float t = x * 100.0f;
+    const float e = __expf(-fabsf(t));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    dsig = (t > 0.0f) ? r : e * r;
+    float sp = fmaxf(x, 0.0f) + __logf(1.0f + e) * 0.01f;
+    if (t > 20.0f) { dsig = 1.0f; sp = x; }
+    return sp;
+}
+
+// split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows
+__device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, const float (&x)[8]) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+__device__ __forceinline__ void store_half8(uint8_t* a, uint32_t off, const float (&x)[8]) {
+    uint32_t hw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(a + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+}
+__device__ __forceinline__ void put_split1(uint8_t* a_hi, uint8_t* a_lo, uint32_t row, uint32_t col, float x) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    const uint32_t off = sw128_offset(row, col);
+    *reinterpret_cast<__half*>(a_hi + off) = h;
+    *reinterpret_cast<__half*>(a_lo + off) = l;
+}
+
+// ===============================================================================================================
+// SDF network
+// ===============================================================================================================
+struct SdfTcParams {
+    const uint8_t* tc;                 // tensor-core section (operand images)
+    const float* bias[SDF_LAYERS];     // fp32 section
+    const float* head_w; const float* head_b; const float* feat_b;
+};
+
+struct Gemm { uint32_t b_off; int nchunks; int ksteps; int n; uint32_t img_bytes; };
+
+template <bool GRAD, bool FEAT>
+__device__ __forceinline__ constexpr int num_gemms() { return SDF_LAYERS + (FEAT ? 1 : 0) + (GRAD ? SDF_LAYERS : 0); }
+
+// gemm sequence of one tile: L0..L7, [feature head], [R7..R1, R0]
+template <bool GRAD, bool FEAT>
+__device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
+    Gemm g;
+    g.nchunks = 4; g.ksteps = 4; g.n = 256; g.img_bytes = IMG;
+    if (idx < SDF_LAYERS) {
+        g.b_off = T.fwd[idx];
+        if (idx == 0) { g.nchunks = 1; g.ksteps = 3; }
+        return g;
+    }
+    idx -= SDF_LAYERS;
+    if (FEAT) { if (idx == 0) { g.b_off = T.feat; return g; } idx -= 1; }
+    const int l = SDF_LAYERS - 1 - idx;          // 7 .. 0
+    g.b_off = T.rev[l];
+    if (l == 0) { g.n = 64; g.img_bytes = IMG_SMALL; }
+    return g;
+}
+
+template <bool GRAD, bool FEAT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_out, float* __restrict__ gx,
+              float* __restrict__ gy, float* __restrict__ gz, int64_t gstride, float* __restrict__ feat_out,
+              float* __restrict__ scratch) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* A_hi = smem + SM_A_HI;
+    uint8_t* A_lo = smem + SM_A_LO;
+    uint8_t* Bst = smem + SM_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC);
+    uint64_t* b_full = bars;            // [3]
+    uint64_t* b_empty = bars + 3;       // [3]
+    uint64_t* a_ready = bars + 6;       // [4]
+    uint64_t* acc_full = bars + 10;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* part = reinterpret_cast<float*>(bars + 16);          // [128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NG = num_gemms<GRAD, FEAT>();
+    const TcLayout T = tc_layout();
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], EPI_THREADS);
+        for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t ntiles = (N + TM - 1) / TM;
+
+    if (warp == 0) {
+        // ======================= weight producer =======================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int gi = 0; gi < NG; ++gi) {
+                    const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
+                    for (int img = 0; img < G.nchunks * 2; ++img, ++it) {
+                        const uint32_t s = it % NSTAGES, u = it / NSTAGES;
+                        mbar_wait(&b_empty[s], (u & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
+                        bulk_g2s(Bst + s * IMG, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            uint32_t it = 0, a_par = 0, gc = 0;
+            const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo), b_addr = smem_u32(Bst);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int gi = 0; gi < NG; ++gi, ++gc) {
+                    const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
+                    const uint32_t acc = tmem_base + (gc & 1) * 256;
+                    const uint32_t idesc = make_idesc_f16(TM, G.n);
+                    for (int c = 0; c < G.nchunks; ++c) {
+                        mbar_wait(&a_ready[c], (a_par >> c) & 1);
+                        a_par ^= (1u << c);
+                        tc_fence_after();
+                        {   // W_hi image: A_hi * W_hi + A_lo * W_hi
+                            const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
+                            mbar_wait(&b_full[s], u & 1);
+                            tc_fence_after();
+                            for (int ks = 0; ks < G.ksteps; ++ks)
+                                umma_f16(acc, make_desc_sw128(a_hi_addr + c * A_CHUNK + ks * 32),
+                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, (c | ks) != 0);
+                            for (int ks = 0; ks < G.ksteps; ++ks)
+                                umma_f16(acc, make_desc_sw128(a_lo_addr + c * A_CHUNK + ks * 32),
+                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, true);
+                            umma_commit(&b_empty[s]);
+                        }
+                        {   // W_lo image: A_hi * W_lo
+                            const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
+                            mbar_wait(&b_full[s], u & 1);
+                            tc_fence_after();
+                            for (int ks = 0; ks < G.ksteps; ++ks)
+                                umma_f16(acc, make_desc_sw128(a_hi_addr + c * A_CHUNK + ks * 32),
+                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, true);
+                            umma_commit(&b_empty[s]);
+                        }
+                    }
+                    umma_commit(&acc_full[gc & 1]);
+                }
+        }
+    } else {
+        // ======================= epilogue warps =======================
+        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int r = q * 32 + lane;                        // row of the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float* sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM);
+        float* pe_s = sig + (size_t)SDF_LAYERS * 256 * TM;            // [40][128] fp32 encoding (skip + final chain)
+        float* ge_s = pe_s + PE_PAD * TM;                             // [40][128] skip-path gradient (G_SCALE units)
+        constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);
+        constexpr float OS_R = 1.0f / W_SCALE;
+        uint32_t gc = 0;
+
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t p = tile * TM + r;
+            const bool valid = p < N;
+            // ---------------- Fourier encoding -> A chunk 0 (hi/lo) + fp32 copy ----------------
+            {
+                float x[3];
+                x[0] = valid ? pts.x[p * pts.stride] * SDF_SCALE : 0.f;
+                x[1] = valid ? pts.y[p * pts.stride] * SDF_SCALE : 0.f;
+                x[2] = valid ? pts.z[p * pts.stride] * SDF_SCALE : 0.f;
+                auto put = [&](int col, float v) {
+                    put_split1(A_hi, A_lo, r, col, v * ACT_SCALE);
+                    pe_s[col * TM + r] = v;
+                };
+                auto put_sin = [&](int d) {
+                    float f = 1.0f;
+#pragma unroll
+                    for (int k = 0; k < SDF_FREQ; ++k) { put(3 + d * SDF_FREQ + k, sinf(x[d] * f)); f *= 2.0f; }
+                };
+                auto put_cos = [&](int d) {
+                    float f = 1.0f;
+#pragma unroll
+                    for (int k = 0; k < SDF_FREQ; ++k) {
+                        put(3 + 3 * SDF_FREQ + d * SDF_FREQ + k, sinf(x[d] * f + 1.57079637050628662109375f)); f *= 2.0f;
+                    }
+                };
+                if (g == 0) {
+                    put(0, x[0]); put(1, x[1]); put(2, x[2]);
+                    put_sin(0); put_cos(0); put_sin(1);
+                } else {
+                    put_cos(1); put_sin(2); put_cos(2);
+                    put_split1(A_hi, A_lo, r, 39, 0.f);
+                    pe_s[39 * TM + r] = 0.f;
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int k8 = 40; k8 < 64; k8 += 8) {
+                        *reinterpret_cast<uint4*>(A_hi + sw128_offset(r, k8)) = z;
+                        *reinterpret_cast<uint4*>(A_lo + sw128_offset(r, k8)) = z;
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&a_ready[0]);
+                epi_bar_sync();                       // pe_s visible to every epilogue thread
+            }
+
+            float dot = 0.f;
+            for (int gi = 0; gi < NG; ++gi, ++gc) {
+                mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256;
+                // ---- classify this gemm ----
+                int kind, l;                          // kind: 0 forward, 1 feature head, 2 reverse, 3 reverse layer 0
+                if (gi < SDF_LAYERS) { kind = 0; l = gi; }
+                else if (FEAT && gi == SDF_LAYERS) { kind = 1; l = 0; }
+                else { l = SDF_LAYERS - 1 - (gi - SDF_LAYERS - (FEAT ? 1 : 0)); kind = (l == 0) ? 3 : 2; }
+
+                if (kind == 3) {
+                    // ---- final: chain through the encoding (g == 0 warps; 39 columns) ----
+                    epi_bar_sync();                   // ge_s written by other threads in the R4 epilogue
+                    if (g == 0) {
+                        float v0[32], v1[32];
+                        tmem_ld32(acc, v0);
+                        tmem_ld32(acc + 32, v1);
+                        tmem_wait_ld();
+                        float gsum[3];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) gsum[d] = v0[d] * OS_R + ge_s[d * TM + r];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const float x = pe_s[d * TM + r];
+                            float f = 1.0f;
+#pragma unroll
+                            for (int k = 0; k < SDF_FREQ; ++k) {
+                                const int js = 3 + d * SDF_FREQ + k, jc = 3 + 3 * SDF_FREQ + d * SDF_FREQ + k;
+                                const float gs = (js < 32 ? v0[js] : v1[js - 32]) * OS_R + ge_s[js * TM + r];
+                                const float gcv = (jc < 32 ? v0[jc] : v1[jc - 32]) * OS_R + ge_s[jc * TM + r];
+                                const float s = x * f;
+                                gsum[d] += gs * cosf(s) * f + gcv * cosf(s + 1.57079637050628662109375f) * f;
+                                f *= 2.0f;
+                            }
+                        }
+                        if (valid) {
+                            gx[p * gstride] = gsum[0] * (SDF_SCALE / G_SCALE);
+                            gy[p * gstride] = gsum[1] * (SDF_SCALE / G_SCALE);
+                            gz[p * gstride] = gsum[2] * (SDF_SCALE / G_SCALE);
+                        }
+                    }
+                    tc_fence_before();
+                    continue;
+                }
+
+                const bool next_exists = (gi + 1 < NG);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col0 = c * 64 + g * 32;
+                    float v[32];
+                    tmem_ld32(acc + col0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = col0 + j8 * 8 + i;
+                            const float a = v[j8 * 8 + i];
+                            if (kind == 0) {
+                                float s;
+                                float h = softplus100(a * OS_F + __ldg(P.bias[l] + col), s);
+                                if (GRAD) sig[((size_t)l * 256 + col) * TM + r] = s;
+                                if (l == SDF_SKIP - 1) h = (col < SKIP_H) ? h / SQRT2F : pe_s[(col - SKIP_H) * TM + r] / SQRT2F;
+                                if (l == SDF_LAYERS - 1) {
+                                    const float w = __ldg(P.head_w + col);
+                                    dot = fmaf(h, w, dot);
+                                    o[i] = (FEAT || !GRAD) ? h * ACT_SCALE : (w / SDF_SCALE) * s * G_SCALE;
+                                } else {
+                                    o[i] = h * ACT_SCALE;
+                                }
+                            } else if (kind == 1) {
+                                o[i] = a * OS_F + __ldg(P.feat_b + col);          // feature value (written below)
+                            } else {
+                                float gval = a * OS_R;
+                                if (l == SDF_SKIP) {
+                                    gval = gval / SQRT2F;
+                                    if (col >= SKIP_H) { ge_s[(col - SKIP_H) * TM + r] = gval; gval = 0.f; }
+                                    else gval *= sig[((size_t)(l - 1) * 256 + col) * TM + r];
+                                } else {
+                                    gval *= sig[((size_t)(l - 1) * 256 + col) * TM + r];
+                                }
+                                o[i] = gval;
+                            }
+                        }
+                        if (kind == 1) {
+                            if (valid) {
+                                float* dst = feat_out + p * 256 + col0 + j8 * 8;
+                                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                            }
+                            if (GRAD) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int col = col0 + j8 * 8 + i;
+                                    o[i] = (__ldg(P.head_w + col) / SDF_SCALE) * sig[((size_t)(SDF_LAYERS - 1) * 256 + col) * TM + r] * G_SCALE;
+                                }
+                            }
+                        }
+                        if (next_exists) store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, g * 32 + j8 * 8), o);
+                    }
+                    if (next_exists) {
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&a_ready[c]);
+                    }
+                }
+                if (kind == 0 && l == SDF_LAYERS - 1) {
+                    // ---- sdf head: combine the two column halves ----
+                    if (g == 1) part[r] = dot;
+                    epi_bar_sync();
+                    if (g == 0 && valid) sdf_out[p] = (dot + part[r] + __ldg(P.head_b)) / SDF_SCALE;
+                    dot = 0.f;
+                }
+                tc_fence_before();
+            }
+            epi_bar_sync();                           // scratch / part reuse across tiles
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ===============================================================================================================
+// Reflectance network (single fp16 pass)
+// ===============================================================================================================
+struct ColTcParams {
+    const uint8_t* tc;
+    const float* b0; const float* b[3]; const float* w4t; const float* b4;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restrict__ feat, const float* __restrict__ rayfeat,
+                int64_t R, int64_t N, float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* A = smem + SMC_A;
+    uint8_t* Bst = smem + SMC_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMC_MISC);
+    uint64_t* b_full = bars;            // [3]
+    uint64_t* b_empty = bars + 3;       // [3]
+    uint64_t* a_ready = bars + 6;       // [6]
+    uint64_t* acc_full = bars + 12;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    float* part = reinterpret_cast<float*>(bars + 16);          // [3][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TcLayout T = tc_layout();
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 6; ++i) mbar_init(&a_ready[i], EPI_THREADS);
+        for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t ntiles = (N + TM - 1) / TM;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int gi = 0; gi < 4; ++gi) {
+                    const int nimg = gi == 0 ? 6 : 4;
+                    for (int img = 0; img < nimg; ++img, ++it) {
+                        const uint32_t s = it % NSTAGES, u = it / NSTAGES;
+                        mbar_wait(&b_empty[s], (u & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], IMG);
+                        bulk_g2s(Bst + s * IMG, P.tc + T.col[gi] + (size_t)img * IMG, IMG, &b_full[s]);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, a_par = 0, gc = 0;
+            const uint32_t a_addr = smem_u32(A), b_addr = smem_u32(Bst);
+            const uint32_t idesc = make_idesc_f16(TM, 256);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int gi = 0; gi < 4; ++gi, ++gc) {
+                    const uint32_t acc = tmem_base + (gc & 1) * 256;
+                    const int nch = gi == 0 ? 6 : 4;
+                    for (int c = 0; c < nch; ++c) {
+                        mbar_wait(&a_ready[c], (a_par >> c) & 1);
+                        a_par ^= (1u << c);
+                        tc_fence_after();
+                        const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
+                        mbar_wait(&b_full[s], u & 1);
+                        tc_fence_after();
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(acc, make_desc_sw128(a_addr + c * A_CHUNK + ks * 32),
+                                     make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, (c | ks) != 0);
+                        umma_commit(&b_empty[s]);
+                    }
+                    umma_commit(&acc_full[gc & 1]);
+                }
+        }
+    } else {
+        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        constexpr float OS = 1.0f / (W_SCALE * ACT_SCALE);
+        uint32_t gc = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t p = tile * TM + r;
+            const bool valid = p < N;
+            // ---- stage the inputs: features -> chunks 0..3, [pts | PE(view) | n | PE(light) | PE(vis) | PE(spec)] -> chunks 4,5 ----
+            {
+                const float* frow = feat + p * 256 + g * 128;
+#pragma unroll 4
+                for (int k8 = 0; k8 < 128; k8 += 8) {
+                    float o[8];
+                    if (valid) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(frow + k8));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(frow + k8 + 4));
+                        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] *= ACT_SCALE;
+                    const int kk = g * 128 + k8;                   // feature index 0..255
+                    store_half8(A + (kk >> 6) * A_CHUNK, sw128_offset(r, kk & 63), o);
+                }
+                const int64_t ray = valid ? (p % R) : 0;
+                for (int k8 = 0; k8 < 64; k8 += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = g * 64 + k8 + i;                 // aux row 0..127
+                        float v = 0.f;
+                        if (valid) {
+                            if (j < 3) v = (j == 0 ? pts.x : (j == 1 ? pts.y : pts.z))[p * pts.stride];
+                            else if (j < AUX_NORMAL) v = rayfeat[(int64_t)(j - AUX_VIEW) * R + ray];
+                            else if (j < AUX_LIGHT) { const int d = j - AUX_NORMAL; v = (d == 0 ? nrm.x : (d == 1 ? nrm.y : nrm.z))[p * nrm.stride]; }
+                            else if (j < 105) v = rayfeat[(int64_t)(j - AUX_LIGHT + COL_PE3) * R + ray];
+                        }
+                        o[i] = v * ACT_SCALE;
+                    }
+                    store_half8(A + (4 + g) * A_CHUNK, sw128_offset(r, k8), o);
+                }
+                fence_proxy_async_smem();
+#pragma unroll
+                for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
+            }
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            for (int gi = 0; gi < 4; ++gi, ++gc) {
+                mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256;
+                const float* bias = gi == 0 ? P.b0 : P.b[gi - 1];
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col0 = c * 64 + g * 32;
+                    float v[32];
+                    tmem_ld32(acc + col0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = col0 + j8 * 8 + i;
+                            const float h = fmaxf(v[j8 * 8 + i] * OS + __ldg(bias + col), 0.f);
+                            if (gi == 3) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + col * 4));
+                                d0 = fmaf(h, w.x, d0); d1 = fmaf(h, w.y, d1); d2 = fmaf(h, w.z, d2);
+                            }
+                            o[i] = h * ACT_SCALE;
+                        }
+                        if (gi < 3) store_half8(A + c * A_CHUNK, sw128_offset(r, g * 32 + j8 * 8), o);
+                    }
+                    if (gi < 3) {
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&a_ready[c]);
+                    }
+                }
+                tc_fence_before();
+            }
+            if (g == 1) { part[r] = d0; part[TM + r] = d1; part[2 * TM + r] = d2; }
+            epi_bar_sync();
+            if (g == 0 && valid) {
+                const float s0 = d0 + part[r] + __ldg(P.b4 + 0), s1 = d1 + part[TM + r] + __ldg(P.b4 + 1), s2 = d2 + part[2 * TM + r] + __ldg(P.b4 + 2);
+                cr[p] = 1.0f / (1.0f + expf(-s0));
+                cg[p] = 1.0f / (1.0f + expf(-s1));
+                cb[p] = 1.0f / (1.0f + expf(-s2));
+            }
+            epi_bar_sync();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ===============================================================================================================
+// operand-image builders (weight packing)
+// ===============================================================================================================
+struct Seg { int dst_k0, src_col0, len; };
+struct ImgJob {
+    const float* src; int src_ld;        // element (n, kcol) = src[n*src_ld + kcol]
+    int nrows_valid;                     // rows beyond are zero
+    int nrows_img;                       // 256 or 64
+    Seg seg[4]; int nseg;                // k-range mapping inside this 64-wide chunk
+    int lo;                              // 0: hi part, 1: lo part (x - fp16(x))
+    float scale;
+    __half* dst;
+};
+
+__global__ void k_build_image(ImgJob J) {
+    const int total = J.nrows_img * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        float v = 0.f;
+        if (n < J.nrows_valid)
+            for (int s = 0; s < J.nseg; ++s)
+                if (k >= J.seg[s].dst_k0 && k < J.seg[s].dst_k0 + J.seg[s].len)
+                    v = J.src[(size_t)n * J.src_ld + J.seg[s].src_col0 + (k - J.seg[s].dst_k0)] * J.scale;
+        const __half h = __float2half_rn(v);
+        const __half out = J.lo ? __float2half_rn(v - __half2float(h)) : h;
+        J.dst[sw128_offset(n, k) >> 1] = out;
+    }
+}
+
+int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
+                uint8_t* dst, cudaStream_t st) {
+    ImgJob J; J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
+    for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0};
+    J.lo = lo; J.scale = W_SCALE; J.dst = reinterpret_cast<__half*>(dst);
+    k_build_image<<<(nrows_img * 64 + 255) / 256, 256, 0, st>>>(J);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+// a plain K-major matrix [nrows_valid x kcols] -> `nchunks` chunks, each as (hi, lo) or hi-only images
+int build_matrix(const float* src, int src_ld, int nrows_valid, int nrows_img, int kcols, int nchunks, bool split,
+                 uint8_t* dst, uint32_t img_bytes, cudaStream_t st) {
+    int rc;
+    for (int c = 0; c < nchunks; ++c) {
+        int len = kcols - c * 64; if (len > 64) len = 64; if (len < 0) len = 0;
+        Seg s{0, c * 64, len};
+        if (split) {
+            if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 0, dst + (size_t)(2 * c) * img_bytes, st))) return rc;
+            if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 1, dst + (size_t)(2 * c + 1) * img_bytes, st))) return rc;
+        } else {
+            if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 0, dst + (size_t)c * img_bytes, st))) return rc;
+        }
+    }
+    return NRH_OK;
+}
+
+}  // namespace
+
+bool tc_available() { return true; }
+size_t tc_packed_bytes(const NrhConfig&) { return tc_layout().total; }
+size_t tc_scratch_bytes(int num_sms) { return (size_t)num_sms * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM) * sizeof(float); }
+
+int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& raw, void* packed, cudaStream_t st) {
+    uint8_t* tcb = reinterpret_cast<uint8_t*>(packed) + L.tc_offset_bytes;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    const TcLayout T = tc_layout();
+    int rc;
+    // forward: B[n = out][k = in] = W native [out][in]
+    for (int l = 0; l < SDF_LAYERS; ++l) {
+        const int in = (l == 0) ? PE_DIM : 256, out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
+        if ((rc = build_matrix(raw.sdf_W[l], in, out, 256, in, l == 0 ? 1 : 4, true, tcb + T.fwd[l], IMG, st))) return rc;
+    }
+    if ((rc = build_matrix(raw.feat_W, 256, 256, 256, 256, 4, true, tcb + T.feat, IMG, st))) return rc;
+    // reverse: B[n = in][k = out] = W^T, taken from the fp32 section's k-major copy Wt[in_pad][256]
+    for (int l = 1; l < SDF_LAYERS; ++l) {
+        const int out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
+        if ((rc = build_matrix(Pf + L.sdf_wt[l], 256, 256, 256, out, 4, true, tcb + T.rev[l], IMG, st))) return rc;
+    }
+    if ((rc = build_matrix(Pf + L.sdf_wt[0], 256, PE_DIM, 64, 256, 4, true, tcb + T.rev[0], IMG_SMALL, st))) return rc;
+    // reflectance layer 0: K order = [feat 256 | pts 3, PE(view) 27, n 3, PE(light) 27, PE(vis) 9, PE(spec) 36 | pad]
+    const int cin = 316 + (cfg.shadow_hint ? 9 : 0) + (cfg.specular_hint ? 9 * cfg.n_roughness : 0);
+    for (int c = 0; c < 4; ++c) {
+        Seg s{0, 60 + c * 64, 64};
+        if ((rc = build_image(raw.col_W[0], cin, 256, 256, &s, 1, 0, tcb + T.col[0] + (size_t)c * IMG, st))) return rc;
+    }
+    {
+        // aux rows 0..63 -> chunk 4: rows 0..59 = source columns 0..59, rows 60..63 = PE(vis)[0..3]
+        Seg s4[2] = {{0, 0, 60}, {60, 316, cfg.shadow_hint ? 4 : 0}};
+        if ((rc = build_image(raw.col_W[0], cin, 256, 256, s4, 2, 0, tcb + T.col[0] + (size_t)4 * IMG, st))) return rc;
+        // aux rows 64..127 -> chunk 5: rows 64..68 = PE(vis)[4..8], rows 69..104 = PE(spec)
+        const int spec0 = 316 + (cfg.shadow_hint ? 9 : 0);
+        Seg s5[2] = {{0, 320, cfg.shadow_hint ? 5 : 0}, {5, spec0, cfg.specular_hint ? 9 * cfg.n_roughness : 0}};
+        if ((rc = build_image(raw.col_W[0], cin, 256, 256, s5, 2, 0, tcb + T.col[0] + (size_t)5 * IMG, st))) return rc;
+    }
+    for (int l = 1; l < 4; ++l)
+        if ((rc = build_matrix(raw.col_W[l], 256, 256, 256, 256, 4, false, tcb + T.col[l], IMG, st))) return rc;
+    return NRH_OK;
+}
+
+int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
+               float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat,
+               float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+    if (N <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    SdfTcParams P;
+    P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    for (int l = 0; l < SDF_LAYERS; ++l) P.bias[l] = Pf + L.sdf_b[l];
+    P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
+    const bool grad = gx != nullptr, wfeat = feat != nullptr;
+#define NRH_LAUNCH_TC(G, F)                                                                                        \
+    do {                                                                                                           \
+        NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM)); \
+        sdf_tc_kernel<G, F><<<grid, NTHREADS, SDF_SMEM, st>>>(P, pts, N, sdf, gx, gy, gz, grad_stride, feat, scratch);          \
+    } while (0)
+    if (grad && wfeat) NRH_LAUNCH_TC(true, true);
+    else if (grad) NRH_LAUNCH_TC(true, false);
+    else if (wfeat) NRH_LAUNCH_TC(false, true);
+    else NRH_LAUNCH_TC(false, false);
+#undef NRH_LAUNCH_TC
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Strided3 normals,
+                 const float* feat, const float* rayfeat, int64_t R, int64_t N,
+                 float* cr, float* cg, float* cb, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+    (void)scratch; (void)scratch_bytes;
+    if (N <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    ColTcParams P;
+    P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    P.b0 = Pf + L.col_b0;
+    for (int l = 0; l < 3; ++l) P.b[l] = Pf + L.col_b[l];
+    P.w4t = Pf + L.col_w4t; P.b4 = Pf + L.col_b4;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
+    color_tc_kernel<<<grid, NTHREADS, COL_SMEM, st>>>(P, pts, normals, feat, rayfeat, R, N, cr, cg, cb);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
 }
 
 }  // namespace nrh

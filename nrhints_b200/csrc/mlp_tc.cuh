@@ -8,7 +8,7 @@ bool tc_available();
 size_t tc_packed_bytes(const NrhConfig& cfg);
 size_t tc_scratch_bytes(int num_sms);
 // builds the tensor-core operand images (fp16 hi/lo, UMMA tile order) from the fp32 section
-int tc_pack(const NrhConfig& cfg, const PackedLayout& L, void* packed, cudaStream_t st);
+int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& raw, void* packed, cudaStream_t st);
 
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
                float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat,

@@ -32,8 +32,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// Bounded spin: a protocol bug must abort the kernel (trap -> CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 27)) asm volatile("trap;");
+    }
 }
 
 // ---- bulk async copy global -> shared (TMA unit, no tensor map), completion on an mbarrier ----------
