@@ -11,8 +11,8 @@
 // accumulate); operands are pre-scaled by powers of two so the lo parts stay normal.  The reflectance network
 // enters the pixel through a sigmoid and is safe in a single fp16 pass.
 //
-// Warp roles (320 threads): warp 0 = weight producer (TMA), warp 1 = MMA issuer (one elected thread),
-// warps 2..9 = epilogue (TMEM -> registers -> bias/activation/split -> swizzled smem operand for the next layer).
+// Warp roles (576 threads): warp 0 = weight producer (TMA), warp 1 = MMA issuer (one elected thread),
+// warps 2..17 = epilogue (TMEM -> registers -> bias/activation/split -> swizzled smem operand for the next layer).
 //
 // Reference semantics: /root/reference/fields/sdf_field.py:106-148, fields/reflectance_network.py:68-96,
 // fields/encodings.py:168-176.
@@ -28,8 +28,9 @@ namespace {
 using namespace tc;
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 320;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;     // 512
+constexpr int NTHREADS = 64 + EPI_THREADS;       // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue
 constexpr int NSTAGES = 3;
 constexpr uint32_t IMG = 32768;            // one [256 x 64] fp16 weight image
 constexpr uint32_t IMG_SMALL = 8192;       // one [64 x 64] fp16 weight image (reverse layer 0)
@@ -37,7 +38,9 @@ constexpr uint32_t A_CHUNK = 16384;        // one [128 x 64] fp16 activation chu
 constexpr float W_SCALE = 64.0f;           // weights are stored * 2^6
 constexpr float ACT_SCALE = 16.0f;         // forward activations are stored * 2^4
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
-constexpr float SQRT2F = 1.41421354f;
+constexpr float INV_SQRT2 = 0.70710678f;
+constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
+constexpr float OS_R = 1.0f / W_SCALE;                 // accumulator -> reverse signal (stays in G_SCALE units)
 
 // ---- tensor-core section of the packed weight buffer (byte offsets from the section start) ----------------
 struct TcLayout {
@@ -61,27 +64,37 @@ __host__ __device__ inline TcLayout tc_layout() {
 // ---- shared memory map ---------------------------------------------------------------------------------------
 constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * IMG;    // sdf kernel
 constexpr uint32_t SMC_A = 0, SMC_B = 6 * A_CHUNK, SMC_MISC = SMC_B + NSTAGES * IMG;                 // color kernel
-constexpr uint32_t SM_MISC_BYTES = 2048;
+constexpr uint32_t SM_MISC_BYTES = 2048, SMC_MISC_BYTES = 8192;
 constexpr size_t SDF_SMEM = SM_MISC + SM_MISC_BYTES + 1024;     // + slack for manual 1024-B alignment
-constexpr size_t COL_SMEM = SMC_MISC + SM_MISC_BYTES + 1024;
+constexpr size_t COL_SMEM = SMC_MISC + SMC_MISC_BYTES + 1024;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// softplus(beta = 100): max(x,0) + log1p(exp(-100|x|))/100 -- identical to the thresholded torch form in fp32
+// (beyond 100x = 20 the log term underflows to 0).  abs error < 3e-9.
+__device__ __forceinline__ float softplus100(float x) {
+    const float e = ex2_approx(-144.269504f * fabsf(x));
+    return fmaf(lg2_approx(1.0f + e), 6.93147181e-3f, fmaxf(x, 0.0f));
+}
+template <bool WANT_D>
 __device__ __forceinline__ float softplus100(float x, float& dsig) {
-    const float t = x * 100.0f;
-    const float e = __expf(-fabsf(t));
-    const float r = __fdividef(1.0f, 1.0f + e);
-    dsig = (t > 0.0f) ? r : e * r;
-    float sp = fmaxf(x, 0.0f) + __logf(1.0f + e) * 0.01f;
-    if (t > 20.0f) { dsig = 1.0f; sp = x; }
-    return sp;
+    const float e = ex2_approx(-144.269504f * fabsf(x));
+    if (WANT_D) {
+        const float rr = rcp_approx(1.0f + e);
+        dsig = x > 0.0f ? rr : e * rr;
+    }
+    return fmaf(lg2_approx(1.0f + e), 6.93147181e-3f, fmaxf(x, 0.0f));
 }
 
 // split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows
-__device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, const float (&x)[8]) {
+__device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, const float* x) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -94,7 +107,7 @@ __device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, uint3
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
-__device__ __forceinline__ void store_half8(uint8_t* a, uint32_t off, const float (&x)[8]) {
+__device__ __forceinline__ void store_half8(uint8_t* a, uint32_t off, const float* x) {
     uint32_t hw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -109,6 +122,13 @@ __device__ __forceinline__ void put_split1(uint8_t* a_hi, uint8_t* a_lo, uint32_
     const uint32_t off = sw128_offset(row, col);
     *reinterpret_cast<__half*>(a_hi + off) = h;
     *reinterpret_cast<__half*>(a_lo + off) = l;
+}
+__device__ __forceinline__ void ldg16(const float* p, float (&b)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+    }
 }
 
 // ===============================================================================================================
@@ -143,6 +163,134 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
     return g;
 }
 
+// per-thread view of the epilogue: row r of the tile (== TMEM lane), column quarter gq of every 64-wide chunk
+struct Epi {
+    uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;
+    float* sig; float* pe_s; float* ge_s;
+    int r, gq;
+    __device__ __forceinline__ void publish(int c, const float* o) const {        // 16 values -> A chunk c, then signal
+        const uint32_t k0 = gq * 16;
+        store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, k0), o);
+        store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, k0 + 8), o + 8);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&a_ready[c]);
+    }
+};
+
+// forward layer epilogue.  LT: 0 = plain, 1 = lin3 (skip concat + 1/sqrt2), 2 = lin7 (sdf head dot).
+// OUT: 0 = no operand for a next gemm, 1 = activations, 2 = reverse seed (w_s/3 * softplus' * G_SCALE)
+template <bool GRAD, int LT, int OUT>
+__device__ __forceinline__ void epi_forward(const Epi& E, uint32_t acc, int l, const float* __restrict__ bias,
+                                            const float* __restrict__ head_w, float& dot) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + E.gq * 16;
+        float v[16], b[16];
+        tmem_ld16(acc + col0, v);
+        ldg16(bias + col0, b);
+        float w[16];
+        if (LT == 2) ldg16(head_w + col0, w);
+        tmem_wait_ld();
+        float s[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = softplus100<GRAD>(fmaf(v[i], OS_F, b[i]), s[i]);
+        if (GRAD) {
+            float* sp = E.sig + ((size_t)l * 256 + col0) * TM + E.r;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sp[i * TM] = s[i];
+        }
+        if (LT == 1) {
+            if (col0 + 16 <= SKIP_H) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] *= INV_SQRT2;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = col0 + i;
+                    v[i] = (col < SKIP_H ? v[i] : E.pe_s[(col < SKIP_H ? 0 : col - SKIP_H) * TM + E.r]) * INV_SQRT2;
+                }
+            }
+        }
+        if (LT == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dot = fmaf(v[i], w[i], dot);
+        }
+        if (OUT == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= ACT_SCALE;
+            E.publish(c, v);
+        } else if (OUT == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (G_SCALE / SDF_SCALE);
+            E.publish(c, v);
+        }
+    }
+}
+
+// feature head epilogue: write feat (fp32, row-major) and, with GRAD, seed the reverse sweep
+template <bool GRAD>
+__device__ __forceinline__ void epi_feat(const Epi& E, uint32_t acc, const float* __restrict__ bias, const float* __restrict__ head_w,
+                                         float* __restrict__ feat_row, bool valid) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + E.gq * 16;
+        float v[16], b[16];
+        tmem_ld16(acc + col0, v);
+        ldg16(bias + col0, b);
+        float w[16], s[16];
+        if (GRAD) {
+            ldg16(head_w + col0, w);
+            const float* sp = E.sig + ((size_t)(SDF_LAYERS - 1) * 256 + col0) * TM + E.r;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[i] = sp[i * TM];
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(feat_row + col0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (G_SCALE / SDF_SCALE);
+            E.publish(c, v);
+        }
+    }
+}
+
+// reverse layer epilogue (l = 7..1): g_pre_{l-1} = (W_l^T g_pre_l) * softplus'_{l-1}; SKIP = (l == 4)
+template <bool SKIP>
+__device__ __forceinline__ void epi_reverse(const Epi& E, uint32_t acc, int l) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + E.gq * 16;
+        float v[16], s[16];
+        tmem_ld16(acc + col0, v);
+        const float* sp = E.sig + ((size_t)(l - 1) * 256 + col0) * TM + E.r;
+        if (!SKIP || col0 < SKIP_H) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[i] = (!SKIP || col0 + i < SKIP_H) ? sp[i * TM] : 0.f;
+        }
+        tmem_wait_ld();
+        if (!SKIP) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] * OS_R * s[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int col = col0 + i;
+                const float gval = v[i] * (OS_R * INV_SQRT2);
+                if (col >= SKIP_H) { E.ge_s[(col - SKIP_H) * TM + E.r] = gval; v[i] = 0.f; }
+                else v[i] = gval * s[i];
+            }
+        }
+        E.publish(c, v);
+    }
+}
+
 template <bool GRAD, bool FEAT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_out, float* __restrict__ gx,
@@ -159,7 +307,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     uint64_t* a_ready = bars + 6;       // [4]
     uint64_t* acc_full = bars + 10;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    float* part = reinterpret_cast<float*>(bars + 16);          // [128]
+    float* part = reinterpret_cast<float*>(bars + 16);          // [3][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NG = num_gemms<GRAD, FEAT>();
@@ -234,15 +382,24 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         }
     } else {
         // ======================= epilogue warps =======================
-        const int q = warp & 3, g = (warp - 2) >> 2;
-        const int r = q * 32 + lane;                        // row of the tile == TMEM lane
+        Epi E;
+        E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready;
+        const int q = warp & 3;
+        E.gq = (warp - 2) >> 2;
+        E.r = q * 32 + lane;                                // row of the tile == TMEM lane
+        const int r = E.r, gq = E.gq;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        float* sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM);
-        float* pe_s = sig + (size_t)SDF_LAYERS * 256 * TM;            // [40][128] fp32 encoding (skip + final chain)
-        float* ge_s = pe_s + PE_PAD * TM;                             // [40][128] skip-path gradient (G_SCALE units)
-        constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);
-        constexpr float OS_R = 1.0f / W_SCALE;
+        E.sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM);
+        E.pe_s = E.sig + (size_t)SDF_LAYERS * 256 * TM;            // [40][128] fp32 encoding (skip + final chain)
+        E.ge_s = E.pe_s + PE_PAD * TM;                             // [40][128] skip-path gradient (G_SCALE units)
         uint32_t gc = 0;
+        auto wait_acc = [&]() -> uint32_t {
+            mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a = tmem_base + lane_base + (gc & 1) * 256;
+            ++gc;
+            return a;
+        };
 
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p = tile * TM + r;
@@ -255,7 +412,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 x[2] = valid ? pts.z[p * pts.stride] * SDF_SCALE : 0.f;
                 auto put = [&](int col, float v) {
                     put_split1(A_hi, A_lo, r, col, v * ACT_SCALE);
-                    pe_s[col * TM + r] = v;
+                    E.pe_s[col * TM + r] = v;
                 };
                 auto put_sin = [&](int d) {
                     float f = 1.0f;
@@ -269,13 +426,13 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                         put(3 + 3 * SDF_FREQ + d * SDF_FREQ + k, sinf(x[d] * f + 1.57079637050628662109375f)); f *= 2.0f;
                     }
                 };
-                if (g == 0) {
-                    put(0, x[0]); put(1, x[1]); put(2, x[2]);
-                    put_sin(0); put_cos(0); put_sin(1);
-                } else {
-                    put_cos(1); put_sin(2); put_cos(2);
+                if (gq == 0) { put(0, x[0]); put(1, x[1]); put(2, x[2]); put_sin(0); }
+                else if (gq == 1) { put_cos(0); put_sin(1); }
+                else if (gq == 2) { put_cos(1); put_sin(2); }
+                else {
+                    put_cos(2);
                     put_split1(A_hi, A_lo, r, 39, 0.f);
-                    pe_s[39 * TM + r] = 0.f;
+                    E.pe_s[39 * TM + r] = 0.f;
                     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int k8 = 40; k8 < 64; k8 += 8) {
@@ -288,120 +445,71 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 epi_bar_sync();                       // pe_s visible to every epilogue thread
             }
 
+            // ---------------- forward layers ----------------
             float dot = 0.f;
-            for (int gi = 0; gi < NG; ++gi, ++gc) {
-                mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
-                tc_fence_after();
-                const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256;
-                // ---- classify this gemm ----
-                int kind, l;                          // kind: 0 forward, 1 feature head, 2 reverse, 3 reverse layer 0
-                if (gi < SDF_LAYERS) { kind = 0; l = gi; }
-                else if (FEAT && gi == SDF_LAYERS) { kind = 1; l = 0; }
-                else { l = SDF_LAYERS - 1 - (gi - SDF_LAYERS - (FEAT ? 1 : 0)); kind = (l == 0) ? 3 : 2; }
-
-                if (kind == 3) {
-                    // ---- final: chain through the encoding (g == 0 warps; 39 columns) ----
-                    epi_bar_sync();                   // ge_s written by other threads in the R4 epilogue
-                    if (g == 0) {
-                        float v0[32], v1[32];
-                        tmem_ld32(acc, v0);
-                        tmem_ld32(acc + 32, v1);
-                        tmem_wait_ld();
-                        float gsum[3];
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) gsum[d] = v0[d] * OS_R + ge_s[d * TM + r];
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            const float x = pe_s[d * TM + r];
-                            float f = 1.0f;
-#pragma unroll
-                            for (int k = 0; k < SDF_FREQ; ++k) {
-                                const int js = 3 + d * SDF_FREQ + k, jc = 3 + 3 * SDF_FREQ + d * SDF_FREQ + k;
-                                const float gs = (js < 32 ? v0[js] : v1[js - 32]) * OS_R + ge_s[js * TM + r];
-                                const float gcv = (jc < 32 ? v0[jc] : v1[jc - 32]) * OS_R + ge_s[jc * TM + r];
-                                const float s = x * f;
-                                gsum[d] += gs * cosf(s) * f + gcv * cosf(s + 1.57079637050628662109375f) * f;
-                                f *= 2.0f;
-                            }
-                        }
-                        if (valid) {
-                            gx[p * gstride] = gsum[0] * (SDF_SCALE / G_SCALE);
-                            gy[p * gstride] = gsum[1] * (SDF_SCALE / G_SCALE);
-                            gz[p * gstride] = gsum[2] * (SDF_SCALE / G_SCALE);
-                        }
-                    }
-                    tc_fence_before();
-                    continue;
-                }
-
-                const bool next_exists = (gi + 1 < NG);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int col0 = c * 64 + g * 32;
-                    float v[32];
-                    tmem_ld32(acc + col0, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        float o[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int col = col0 + j8 * 8 + i;
-                            const float a = v[j8 * 8 + i];
-                            if (kind == 0) {
-                                float s;
-                                float h = softplus100(a * OS_F + __ldg(P.bias[l] + col), s);
-                                if (GRAD) sig[((size_t)l * 256 + col) * TM + r] = s;
-                                if (l == SDF_SKIP - 1) h = (col < SKIP_H) ? h / SQRT2F : pe_s[(col - SKIP_H) * TM + r] / SQRT2F;
-                                if (l == SDF_LAYERS - 1) {
-                                    const float w = __ldg(P.head_w + col);
-                                    dot = fmaf(h, w, dot);
-                                    o[i] = (FEAT || !GRAD) ? h * ACT_SCALE : (w / SDF_SCALE) * s * G_SCALE;
-                                } else {
-                                    o[i] = h * ACT_SCALE;
-                                }
-                            } else if (kind == 1) {
-                                o[i] = a * OS_F + __ldg(P.feat_b + col);          // feature value (written below)
-                            } else {
-                                float gval = a * OS_R;
-                                if (l == SDF_SKIP) {
-                                    gval = gval / SQRT2F;
-                                    if (col >= SKIP_H) { ge_s[(col - SKIP_H) * TM + r] = gval; gval = 0.f; }
-                                    else gval *= sig[((size_t)(l - 1) * 256 + col) * TM + r];
-                                } else {
-                                    gval *= sig[((size_t)(l - 1) * 256 + col) * TM + r];
-                                }
-                                o[i] = gval;
-                            }
-                        }
-                        if (kind == 1) {
-                            if (valid) {
-                                float* dst = feat_out + p * 256 + col0 + j8 * 8;
-                                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                            }
-                            if (GRAD) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int col = col0 + j8 * 8 + i;
-                                    o[i] = (__ldg(P.head_w + col) / SDF_SCALE) * sig[((size_t)(SDF_LAYERS - 1) * 256 + col) * TM + r] * G_SCALE;
-                                }
-                            }
-                        }
-                        if (next_exists) store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, g * 32 + j8 * 8), o);
-                    }
-                    if (next_exists) {
-                        fence_proxy_async_smem();
-                        tc_fence_before();
-                        mbar_arrive(&a_ready[c]);
-                    }
+            for (int l = 0; l < SDF_LAYERS - 1; ++l) {
+                const uint32_t acc = wait_acc();
+                if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, acc, l, P.bias[l], P.head_w, dot);
+                else epi_forward<GRAD, 0, 1>(E, acc, l, P.bias[l], P.head_w, dot);
+                tc_fence_before();
+            }
+            {
+                const uint32_t acc = wait_acc();
+                constexpr int OUT = FEAT ? 1 : (GRAD ? 2 : 0);
+                epi_forward<GRAD, 2, OUT>(E, acc, SDF_LAYERS - 1, P.bias[SDF_LAYERS - 1], P.head_w, dot);
+                tc_fence_before();
+                // sdf head: combine the four column quarters
+                if (gq > 0) part[(gq - 1) * TM + r] = dot;
+                epi_bar_sync();
+                if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) + __ldg(P.head_b)) / SDF_SCALE;
+            }
+            if (FEAT) {
+                const uint32_t acc = wait_acc();
+                epi_feat<GRAD>(E, acc, P.feat_b, P.head_w, feat_out + p * 256, valid);
+                tc_fence_before();
+            }
+            if (GRAD) {
+#pragma unroll 1
+                for (int l = SDF_LAYERS - 1; l >= 1; --l) {
+                    const uint32_t acc = wait_acc();
+                    if (l == SDF_SKIP) epi_reverse<true>(E, acc, l);
+                    else epi_reverse<false>(E, acc, l);
+                    tc_fence_before();
                 }
-                if (kind == 0 && l == SDF_LAYERS - 1) {
-                    // ---- sdf head: combine the two column halves ----
-                    if (g == 1) part[r] = dot;
-                    epi_bar_sync();
-                    if (g == 0 && valid) sdf_out[p] = (dot + part[r] + __ldg(P.head_b)) / SDF_SCALE;
-                    dot = 0.f;
+                // ---- reverse layer 0 + chain through the encoding (39 columns; quarter 0 warps) ----
+                const uint32_t acc = wait_acc();
+                epi_bar_sync();                       // ge_s written by other threads in the R4 epilogue
+                if (gq == 0) {
+                    float v0[16], v1[16], v2[16];
+                    tmem_ld16(acc, v0);
+                    tmem_ld16(acc + 16, v1);
+                    tmem_ld16(acc + 32, v2);
+                    tmem_wait_ld();
+                    auto gcol = [&](int j) -> float {
+                        const float a = j < 16 ? v0[j] : (j < 32 ? v1[j - 16] : v2[j - 32]);
+                        return fmaf(a, OS_R, E.ge_s[j * TM + r]);
+                    };
+                    float gsum[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float x = E.pe_s[d * TM + r];
+                        float acc_d = gcol(d);
+                        float f = 1.0f;
+#pragma unroll
+                        for (int k = 0; k < SDF_FREQ; ++k) {
+                            const float sarg = x * f;
+                            acc_d += gcol(3 + d * SDF_FREQ + k) * cosf(sarg) * f;
+                            acc_d += gcol(3 + 3 * SDF_FREQ + d * SDF_FREQ + k) * cosf(sarg + 1.57079637050628662109375f) * f;
+                            f *= 2.0f;
+                        }
+                        gsum[d] = acc_d;
+                    }
+                    if (valid) {
+                        gx[p * gstride] = gsum[0] * (SDF_SCALE / G_SCALE);
+                        gy[p * gstride] = gsum[1] * (SDF_SCALE / G_SCALE);
+                        gz[p * gstride] = gsum[2] * (SDF_SCALE / G_SCALE);
+                    }
                 }
                 tc_fence_before();
             }
@@ -435,7 +543,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
     uint64_t* a_ready = bars + 6;       // [6]
     uint64_t* acc_full = bars + 12;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* part = reinterpret_cast<float*>(bars + 16);          // [3][128]
+    float* part = reinterpret_cast<float*>(bars + 16);          // [3 channels][3 quarters][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TcLayout T = tc_layout();
@@ -491,19 +599,18 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 }
         }
     } else {
-        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int q = warp & 3, gq = (warp - 2) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        constexpr float OS = 1.0f / (W_SCALE * ACT_SCALE);
         uint32_t gc = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p = tile * TM + r;
             const bool valid = p < N;
             // ---- stage the inputs: features -> chunks 0..3, [pts | PE(view) | n | PE(light) | PE(vis) | PE(spec)] -> chunks 4,5 ----
             {
-                const float* frow = feat + p * 256 + g * 128;
-#pragma unroll 4
-                for (int k8 = 0; k8 < 128; k8 += 8) {
+                const float* frow = feat + p * 256 + gq * 64;
+#pragma unroll 2
+                for (int k8 = 0; k8 < 64; k8 += 8) {
                     float o[8];
                     if (valid) {
                         const float4 a = __ldg(reinterpret_cast<const float4*>(frow + k8));
@@ -515,15 +622,15 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] *= ACT_SCALE;
-                    const int kk = g * 128 + k8;                   // feature index 0..255
-                    store_half8(A + (kk >> 6) * A_CHUNK, sw128_offset(r, kk & 63), o);
+                    store_half8(A + gq * A_CHUNK, sw128_offset(r, k8), o);
                 }
                 const int64_t ray = valid ? (p % R) : 0;
-                for (int k8 = 0; k8 < 64; k8 += 8) {
+#pragma unroll 1
+                for (int k8 = 0; k8 < 32; k8 += 8) {
                     float o[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int j = g * 64 + k8 + i;                 // aux row 0..127
+                        const int j = gq * 32 + k8 + i;                 // aux row 0..127
                         float v = 0.f;
                         if (valid) {
                             if (j < 3) v = (j == 0 ? pts.x : (j == 1 ? pts.y : pts.z))[p * pts.stride];
@@ -533,13 +640,14 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                         }
                         o[i] = v * ACT_SCALE;
                     }
-                    store_half8(A + (4 + g) * A_CHUNK, sw128_offset(r, k8), o);
+                    store_half8(A + (4 + (gq >> 1)) * A_CHUNK, sw128_offset(r, (gq & 1) * 32 + k8), o);
                 }
                 fence_proxy_async_smem();
 #pragma unroll
                 for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
             }
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll 1
             for (int gi = 0; gi < 4; ++gi, ++gc) {
                 mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
                 tc_fence_after();
@@ -547,26 +655,24 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 const float* bias = gi == 0 ? P.b0 : P.b[gi - 1];
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    const int col0 = c * 64 + g * 32;
-                    float v[32];
-                    tmem_ld32(acc + col0, v);
+                    const int col0 = c * 64 + gq * 16;
+                    float v[16], b[16];
+                    tmem_ld16(acc + col0, v);
+                    ldg16(bias + col0, b);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        float o[8];
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], OS_F, b[i]), 0.f);
+                    if (gi == 3) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int col = col0 + j8 * 8 + i;
-                            const float h = fmaxf(v[j8 * 8 + i] * OS + __ldg(bias + col), 0.f);
-                            if (gi == 3) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + col * 4));
-                                d0 = fmaf(h, w.x, d0); d1 = fmaf(h, w.y, d1); d2 = fmaf(h, w.z, d2);
-                            }
-                            o[i] = h * ACT_SCALE;
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + (col0 + i) * 4));
+                            d0 = fmaf(v[i], w.x, d0); d1 = fmaf(v[i], w.y, d1); d2 = fmaf(v[i], w.z, d2);
                         }
-                        if (gi < 3) store_half8(A + c * A_CHUNK, sw128_offset(r, g * 32 + j8 * 8), o);
-                    }
-                    if (gi < 3) {
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] *= ACT_SCALE;
+                        store_half8(A + c * A_CHUNK, sw128_offset(r, gq * 16), v);
+                        store_half8(A + c * A_CHUNK, sw128_offset(r, gq * 16 + 8), v + 8);
                         fence_proxy_async_smem();
                         tc_fence_before();
                         mbar_arrive(&a_ready[c]);
@@ -574,10 +680,12 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 }
                 tc_fence_before();
             }
-            if (g == 1) { part[r] = d0; part[TM + r] = d1; part[2 * TM + r] = d2; }
+            if (gq > 0) { float* pp = part + (gq - 1) * TM + r; pp[0] = d0; pp[3 * TM] = d1; pp[6 * TM] = d2; }
             epi_bar_sync();
-            if (g == 0 && valid) {
-                const float s0 = d0 + part[r] + __ldg(P.b4 + 0), s1 = d1 + part[TM + r] + __ldg(P.b4 + 1), s2 = d2 + part[2 * TM + r] + __ldg(P.b4 + 2);
+            if (gq == 0 && valid) {
+                const float s0 = ((d0 + part[r]) + (part[TM + r] + part[2 * TM + r])) + __ldg(P.b4 + 0);
+                const float s1 = ((d1 + part[3 * TM + r]) + (part[4 * TM + r] + part[5 * TM + r])) + __ldg(P.b4 + 1);
+                const float s2 = ((d2 + part[6 * TM + r]) + (part[7 * TM + r] + part[8 * TM + r])) + __ldg(P.b4 + 2);
                 cr[p] = 1.0f / (1.0f + expf(-s0));
                 cg[p] = 1.0f / (1.0f + expf(-s1));
                 cb[p] = 1.0f / (1.0f + expf(-s2));
