@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "mlp_tc.cuh"
 #include "tc_primitives.cuh"
 
@@ -31,7 +32,9 @@ constexpr int TM = 128;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;     // 512
 constexpr int NTHREADS = 64 + EPI_THREADS;       // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue
-constexpr int NSTAGES = 3;
+constexpr int NSTAGES = 3;               // weight ring: 3 x 32 KB images (N < 256 per MMA does not pay: an SS-mode MMA costs
+                                         // ~115 clk whatever N is, measured; so a stage is a full [256 x 64] image)
+constexpr uint32_t STAGE = 32768;
 constexpr uint32_t IMG = 32768;            // one [256 x 64] fp16 weight image
 constexpr uint32_t IMG_SMALL = 8192;       // one [64 x 64] fp16 weight image (reverse layer 0)
 constexpr uint32_t A_CHUNK = 16384;        // one [128 x 64] fp16 activation chunk
@@ -48,6 +51,8 @@ struct TcLayout {
     uint32_t feat;                // 8 images
     uint32_t rev[SDF_LAYERS];     // l >= 1: 8 images of W_l^T; l = 0: 8 small images
     uint32_t col[4];              // reflectance hidden layers: 6 / 4 / 4 / 4 images (single pass)
+    uint32_t sdf_bias16;          // [8][256] fp32 biases * ACT_SCALE
+    uint32_t col_bias16;          // [4][256] fp32 biases * ACT_SCALE
     uint32_t total;
 };
 __host__ __device__ inline TcLayout tc_layout() {
@@ -57,13 +62,15 @@ __host__ __device__ inline TcLayout tc_layout() {
     t.feat = off; off += 8 * IMG;
     for (int l = 0; l < SDF_LAYERS; ++l) { t.rev[l] = off; off += (l == 0 ? 8 * IMG_SMALL : 8 * IMG); }
     for (int l = 0; l < 4; ++l) { t.col[l] = off; off += (l == 0 ? 6 : 4) * IMG; }
+    t.sdf_bias16 = off; off += SDF_LAYERS * 256 * 4;
+    t.col_bias16 = off; off += 4 * 256 * 4;
     t.total = off;
     return t;
 }
 
 // ---- shared memory map ---------------------------------------------------------------------------------------
-constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * IMG;    // sdf kernel
-constexpr uint32_t SMC_A = 0, SMC_B = 6 * A_CHUNK, SMC_MISC = SMC_B + NSTAGES * IMG;                 // color kernel
+constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * STAGE;    // sdf kernel
+constexpr uint32_t SMC_A = 0, SMC_B = 6 * A_CHUNK, SMC_MISC = SMC_B + NSTAGES * STAGE;                 // color kernel
 constexpr uint32_t SM_MISC_BYTES = 2048, SMC_MISC_BYTES = 8192;
 constexpr size_t SDF_SMEM = SM_MISC + SM_MISC_BYTES + 1024;     // + slack for manual 1024-B alignment
 constexpr size_t COL_SMEM = SMC_MISC + SMC_MISC_BYTES + 1024;
@@ -93,7 +100,33 @@ __device__ __forceinline__ float softplus100(float x, float& dsig) {
     return fmaf(lg2_approx(1.0f + e), 6.93147181e-3f, fmaxf(x, 0.0f));
 }
 
-// split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows (shared addresses)
+__device__ __forceinline__ void store_split8s(uint32_t s_hi, uint32_t s_lo, const float* x) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    sts128(s_hi, hw[0], hw[1], hw[2], hw[3]);
+    sts128(s_lo, lw[0], lw[1], lw[2], lw[3]);
+}
+__device__ __forceinline__ void store_half8s(uint32_t s_a, const float* x) {
+    uint32_t hw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    sts128(s_a, hw[0], hw[1], hw[2], hw[3]);
+}
+// (generic-pointer variants, used by the one-off staging code)
 __device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, const float* x) {
     uint32_t hw[4], lw[4];
 #pragma unroll
@@ -136,8 +169,10 @@ __device__ __forceinline__ void ldg16(const float* p, float (&b)[16]) {
 // ===============================================================================================================
 struct SdfTcParams {
     const uint8_t* tc;                 // tensor-core section (operand images)
-    const float* bias[SDF_LAYERS];     // fp32 section
+    const float* bias16;               // [8][256] biases * ACT_SCALE (tensor-core section)
     const float* head_w; const float* head_b; const float* feat_b;
+    long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
+    int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
 };
 
 struct Gemm { uint32_t b_off; int nchunks; int ksteps; int n; uint32_t img_bytes; };
@@ -166,129 +201,192 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
 // per-thread view of the epilogue: row r of the tile (== TMEM lane), column quarter gq of every 64-wide chunk
 struct Epi {
     uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;
-    float* sig; float* pe_s; float* ge_s;
-    int r, gq;
-    __device__ __forceinline__ void publish(int c, const float* o) const {        // 16 values -> A chunk c, then signal
-        const uint32_t k0 = gq * 16;
-        store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, k0), o);
-        store_split8(A_hi + c * A_CHUNK, A_lo + c * A_CHUNK, sw128_offset(r, k0 + 8), o + 8);
+    float* sig;      // [8][256][128] softplus' / W_SCALE of every forward layer (reverse sweep)
+    float* pe_s;     // [40][128] fp32 Fourier encoding (final chain)
+    float* pk_s;     // [40][128] encoding * ACT_SCALE / sqrt2 (skip concat operand)
+    float* ge_s;     // [40][128] skip-path gradient (G_SCALE units)
+    int r, gq, lane;
+    uint32_t off0, off1;                   // swizzled byte offsets of this thread's two 8-column groups inside a chunk
+    uint32_t s_hi, s_lo;                   // shared-space addresses of A_hi / A_lo
+    long long* tl;                         // timeline slot of the current gemm (nullptr = off)
+    // 16 values -> A chunk c (hi/lo split), then signal the MMA issuer (one arrival per warp).
+    // NOTE: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it drains every outstanding memory
+    // operation of the thread, so callers issue their global loads / stores right AFTER publish(), never before.
+    __device__ __forceinline__ void publish(int c, const float* o) const {
+        store_split8s(s_hi + c * A_CHUNK + off0, s_lo + c * A_CHUNK + off0, o);
+        store_split8s(s_hi + c * A_CHUNK + off1, s_lo + c * A_CHUNK + off1, o + 8);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&a_ready[c]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[c]);
     }
 };
 
+// precise trig kept out of line: the range-reduction slow paths are large and would be inlined dozens of times
+__device__ __noinline__ float sin_precise(float x) { return sinf(x); }
+__device__ __noinline__ float cos_precise(float x) { return cosf(x); }
+
+// forward arithmetic happens in "x16" units (everything pre-multiplied by ACT_SCALE = 16, biases included):
+//   x16 = acc / W_SCALE + 16 b ;  softplus16(x16) = max(x16,0) + 16 ln2/100 * lg2(1 + 2^(-100 log2e/16 |x16|))
+constexpr float OS_F16 = 1.0f / W_SCALE;
+constexpr float SP_K = -144.269504f / ACT_SCALE;
+constexpr float SP_L = 6.93147181e-3f * ACT_SCALE;
+
+// All epilogues are software-pipelined over the four 64-column chunks with two alternating register sets: the
+// TMEM load and the L2 loads of chunk c+1 are in flight while chunk c is processed.  `wait_acc` blocks until the
+// accumulator of this gemm is complete and returns its TMEM address (lane base included); loads that do not
+// depend on it (bias, softplus') are issued before it.
+
 // forward layer epilogue.  LT: 0 = plain, 1 = lin3 (skip concat + 1/sqrt2), 2 = lin7 (sdf head dot).
 // OUT: 0 = no operand for a next gemm, 1 = activations, 2 = reverse seed (w_s/3 * softplus' * G_SCALE)
-template <bool GRAD, int LT, int OUT>
-__device__ __forceinline__ void epi_forward(const Epi& E, uint32_t acc, int l, const float* __restrict__ bias,
-                                            const float* __restrict__ head_w, float& dot) {
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        const int col0 = c * 64 + E.gq * 16;
-        float v[16], b[16];
-        tmem_ld16(acc + col0, v);
-        ldg16(bias + col0, b);
-        float w[16];
-        if (LT == 2) ldg16(head_w + col0, w);
+template <bool GRAD, int LT, int OUT, class WaitAcc>
+__device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, int l, const float* __restrict__ bias16,
+                                            const float* __restrict__ head_w, float& dot16) {
+    float vA[16], bA[16], vB[16], bB[16];
+    const int cq = E.gq * 16;
+    ldg16(bias16 + cq, bA);
+    ldg16(bias16 + cq + 64, bB);
+    if (E.tl) E.tl[0] = clock64();
+    const uint32_t acc = wait_acc() + cq;
+    if (E.tl) E.tl[1] = clock64();
+    tmem_ld16(acc, vA);
+    float* const sig_l = E.sig + ((size_t)l * 256 + cq) * TM + E.r;
+    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], const int c) {
         tmem_wait_ld();
+        if (E.tl) E.tl[2 + c * 3] = clock64();
+        if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
+        float w[16];
+        if (LT == 2) ldg16(head_w + cq + c * 64, w);
         float s[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = softplus100<GRAD>(fmaf(v[i], OS_F, b[i]), s[i]);
-        if (GRAD) {
-            float* sp = E.sig + ((size_t)l * 256 + col0) * TM + E.r;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sp[i * TM] = s[i];
+        for (int i = 0; i < 16; ++i) {
+            const float x = fmaf(v[i], OS_F16, b[i]);
+            const float e = ex2_approx(SP_K * fabsf(x));
+            const float t = 1.0f + e;
+            if (GRAD) { const float rr = rcp_approx(t); s[i] = (x > 0.0f ? rr : e * rr) * OS_R; }
+            v[i] = fmaf(lg2_approx(t), SP_L, fmaxf(x, 0.0f));
         }
         if (LT == 1) {
-            if (col0 + 16 <= SKIP_H) {
+            if (c * 64 + cq + 16 <= SKIP_H) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] *= INV_SQRT2;
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int col = col0 + i;
-                    v[i] = (col < SKIP_H ? v[i] : E.pe_s[(col < SKIP_H ? 0 : col - SKIP_H) * TM + E.r]) * INV_SQRT2;
+                    const int col = c * 64 + cq + i;
+                    v[i] = col < SKIP_H ? v[i] * INV_SQRT2 : E.pk_s[(col < SKIP_H ? 0 : col - SKIP_H) * TM + E.r];
                 }
             }
         }
         if (LT == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dot = fmaf(v[i], w[i], dot);
+            for (int i = 0; i < 16; ++i) dot16 = fmaf(v[i], w[i], dot16);
         }
+        if (E.tl) E.tl[3 + c * 3] = clock64();
         if (OUT == 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= ACT_SCALE;
             E.publish(c, v);
         } else if (OUT == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (G_SCALE / SDF_SCALE);
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (W_SCALE * G_SCALE / SDF_SCALE);
             E.publish(c, v);
         }
-    }
+        if (E.tl) E.tl[4 + c * 3] = clock64();
+        // global traffic goes after the fence inside publish(): softplus' stores, bias of the chunk after next
+        if (GRAD) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sig_l[(size_t)(c * 64 + i) * TM] = s[i];
+        }
+        if (c < 2) ldg16(bias16 + cq + (c + 2) * 64, b);
+    };
+    step(vA, bA, vB, 0);
+    step(vB, bB, vA, 1);
+    step(vA, bA, vB, 2);
+    step(vB, bB, vA, 3);
 }
 
 // feature head epilogue: write feat (fp32, row-major) and, with GRAD, seed the reverse sweep
-template <bool GRAD>
-__device__ __forceinline__ void epi_feat(const Epi& E, uint32_t acc, const float* __restrict__ bias, const float* __restrict__ head_w,
+template <bool GRAD, class WaitAcc>
+__device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
                                          float* __restrict__ feat_row, bool valid) {
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        const int col0 = c * 64 + E.gq * 16;
-        float v[16], b[16];
-        tmem_ld16(acc + col0, v);
-        ldg16(bias + col0, b);
+    float vA[16], bA[16], vB[16], bB[16];
+    const int cq = E.gq * 16;
+    ldg16(bias + cq, bA);
+    const uint32_t acc = wait_acc() + cq;
+    tmem_ld16(acc, vA);
+    const float* const sig_l = E.sig + ((size_t)(SDF_LAYERS - 1) * 256 + cq) * TM + E.r;
+    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], float (&nb)[16], const int c) {
+        tmem_wait_ld();
+        if (c < 3) { tmem_ld16(acc + (c + 1) * 64, nv); ldg16(bias + cq + (c + 1) * 64, nb); }
         float w[16], s[16];
         if (GRAD) {
-            ldg16(head_w + col0, w);
-            const float* sp = E.sig + ((size_t)(SDF_LAYERS - 1) * 256 + col0) * TM + E.r;
+            ldg16(head_w + cq + c * 64, w);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = sp[i * TM];
+            for (int i = 0; i < 16; ++i) s[i] = sig_l[(size_t)(c * 64 + i) * TM];
         }
-        tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(feat_row + col0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                *reinterpret_cast<float4*>(feat_row + cq + c * 64 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (G_SCALE / SDF_SCALE);
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (W_SCALE * G_SCALE / SDF_SCALE);
             E.publish(c, v);
         }
-    }
+    };
+    step(vA, bA, vB, bB, 0);
+    step(vB, bB, vA, bA, 1);
+    step(vA, bA, vB, bB, 2);
+    step(vB, bB, vA, bA, 3);
 }
 
-// reverse layer epilogue (l = 7..1): g_pre_{l-1} = (W_l^T g_pre_l) * softplus'_{l-1}; SKIP = (l == 4)
-template <bool SKIP>
-__device__ __forceinline__ void epi_reverse(const Epi& E, uint32_t acc, int l) {
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        const int col0 = c * 64 + E.gq * 16;
-        float v[16], s[16];
-        tmem_ld16(acc + col0, v);
-        const float* sp = E.sig + ((size_t)(l - 1) * 256 + col0) * TM + E.r;
-        if (!SKIP || col0 < SKIP_H) {
+// reverse layer epilogue (l = 7..1): g_pre_{l-1} = (W_l^T g_pre_l) * softplus'_{l-1}; SKIP = (l == 4).
+// sig holds softplus' / W_SCALE, so acc * sig is already in G_SCALE units.
+template <bool SKIP, class WaitAcc>
+__device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, int l) {
+    const int cq = E.gq * 16;
+    const float* const sig_l = E.sig + ((size_t)(l - 1) * 256 + cq) * TM + E.r;
+    float vA[16], sA[16], vB[16], sB[16];
+    auto load_sig = [&](float (&sg)[16], const int c) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = (!SKIP || col0 + i < SKIP_H) ? sp[i * TM] : 0.f;
-        }
+        for (int i = 0; i < 16; ++i)
+            sg[i] = (!SKIP || c * 64 + cq + i < SKIP_H) ? sig_l[(size_t)(c * 64 + i) * TM] : 0.f;
+    };
+    load_sig(sA, 0);
+    load_sig(sB, 1);
+    const uint32_t acc = wait_acc() + cq;
+    tmem_ld16(acc, vA);
+    auto step = [&](float (&v)[16], float (&sg)[16], float (&nv)[16], const int c) {
         tmem_wait_ld();
+        if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
+        float ge[16];
         if (!SKIP) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i] * OS_R * s[i];
+            for (int i = 0; i < 16; ++i) v[i] *= sg[i];
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const int col = col0 + i;
-                const float gval = v[i] * (OS_R * INV_SQRT2);
-                if (col >= SKIP_H) { E.ge_s[(col - SKIP_H) * TM + E.r] = gval; v[i] = 0.f; }
-                else v[i] = gval * s[i];
+                const int col = c * 64 + cq + i;
+                if (col >= SKIP_H) { ge[i] = v[i] * (OS_R * INV_SQRT2); v[i] = 0.f; }
+                else v[i] = v[i] * INV_SQRT2 * sg[i];
             }
         }
         E.publish(c, v);
-    }
+        if (SKIP) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int col = c * 64 + cq + i;
+                if (col >= SKIP_H) E.ge_s[(col - SKIP_H) * TM + E.r] = ge[i];
+            }
+        }
+        if (c < 2) load_sig(sg, c + 2);
+    };
+    step(vA, sA, vB, 0);
+    step(vB, sB, vA, 1);
+    step(vA, sA, vB, 2);
+    step(vB, sB, vA, 3);
 }
 
 template <bool GRAD, bool FEAT>
@@ -302,12 +400,12 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     uint8_t* A_lo = smem + SM_A_LO;
     uint8_t* Bst = smem + SM_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC);
-    uint64_t* b_full = bars;            // [3]
-    uint64_t* b_empty = bars + 3;       // [3]
-    uint64_t* a_ready = bars + 6;       // [4]
-    uint64_t* acc_full = bars + 10;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    float* part = reinterpret_cast<float*>(bars + 16);          // [3][128]
+    uint64_t* b_full = bars;                  // [12]
+    uint64_t* b_empty = bars + NSTAGES;       // [12]
+    uint64_t* a_ready = bars + 2 * NSTAGES;   // [4]
+    uint64_t* acc_full = a_ready + 4;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    float* part = reinterpret_cast<float*>(bars + 32);          // [3][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NG = num_gemms<GRAD, FEAT>();
@@ -316,7 +414,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], EPI_THREADS);
+        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], EPI_WARPS);
         for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
         fence_mbar_init();
     }
@@ -336,8 +434,9 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     for (int img = 0; img < G.nchunks * 2; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
+                        if (P.dbg >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic
                         mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
-                        bulk_g2s(Bst + s * IMG, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
+                        bulk_g2s(Bst + s * STAGE, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
                     }
                 }
         }
@@ -345,53 +444,72 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         // ======================= MMA issuer =======================
         if (lane == 0) {
             uint32_t it = 0, a_par = 0, gc = 0;
-            const uint32_t a_hi_addr = smem_u32(A_hi), a_lo_addr = smem_u32(A_lo), b_addr = smem_u32(Bst);
+            const uint32_t a_hi_lo = desc_lo(smem_u32(A_hi)), a_lo_lo = desc_lo(smem_u32(A_lo)), b_lo0 = desc_lo(smem_u32(Bst));
+            const bool mma_on = (P.dbg != 2 && P.dbg != 4);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int gi = 0; gi < NG; ++gi, ++gc) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
+                    const bool lg = P.tlog && blockIdx.x == 0 && tile == 2 * (int64_t)gridDim.x && gi < 8;
                     for (int c = 0; c < G.nchunks; ++c) {
+                        if (lg) P.tlog[gi * 16 + c * 3 + 0] = clock64();
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
+                        if (lg) P.tlog[gi * 16 + c * 3 + 1] = clock64();
                         a_par ^= (1u << c);
                         tc_fence_after();
-                        {   // W_hi image: A_hi * W_hi + A_lo * W_hi
+                        const uint32_t ah = a_hi_lo + c * (A_CHUNK >> 4), al = a_lo_lo + c * (A_CHUNK >> 4);
+                        // W_hi image: A_hi * W_hi + A_lo * W_hi
+                        {
                             const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
                             mbar_wait(&b_full[s], u & 1);
                             tc_fence_after();
-                            for (int ks = 0; ks < G.ksteps; ++ks)
-                                umma_f16(acc, make_desc_sw128(a_hi_addr + c * A_CHUNK + ks * 32),
-                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, (c | ks) != 0);
-                            for (int ks = 0; ks < G.ksteps; ++ks)
-                                umma_f16(acc, make_desc_sw128(a_lo_addr + c * A_CHUNK + ks * 32),
-                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, true);
+                            if (mma_on) {
+                                const uint32_t bl = b_lo0 + s * (STAGE >> 4), d = acc;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    if (ks < G.ksteps) umma_f16_lo(d, ah + ks * 2, bl + ks * 2, idesc, (uint32_t)((c | ks) != 0));
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    if (ks < G.ksteps) umma_f16_lo(d, al + ks * 2, bl + ks * 2, idesc, 1u);
+                            }
                             umma_commit(&b_empty[s]);
                         }
-                        {   // W_lo image: A_hi * W_lo
+                        // W_lo image: A_hi * W_lo
+                        {
                             const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
                             mbar_wait(&b_full[s], u & 1);
                             tc_fence_after();
-                            for (int ks = 0; ks < G.ksteps; ++ks)
-                                umma_f16(acc, make_desc_sw128(a_hi_addr + c * A_CHUNK + ks * 32),
-                                         make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, true);
+                            if (mma_on) {
+                                const uint32_t bl = b_lo0 + s * (STAGE >> 4), d = acc;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    if (ks < G.ksteps) umma_f16_lo(d, ah + ks * 2, bl + ks * 2, idesc, 1u);
+                            }
                             umma_commit(&b_empty[s]);
                         }
+                        if (lg) P.tlog[gi * 16 + c * 3 + 2] = clock64();
                     }
                     umma_commit(&acc_full[gc & 1]);
+                    if (lg) P.tlog[gi * 16 + 12] = clock64();
                 }
         }
     } else {
         // ======================= epilogue warps =======================
         Epi E;
-        E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready;
+        E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
         const int q = warp & 3;
         E.gq = (warp - 2) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
         const int r = E.r, gq = E.gq;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        E.sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM);
-        E.pe_s = E.sig + (size_t)SDF_LAYERS * 256 * TM;            // [40][128] fp32 encoding (skip + final chain)
-        E.ge_s = E.pe_s + PE_PAD * TM;                             // [40][128] skip-path gradient (G_SCALE units)
+        E.sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 3 * PE_PAD) * TM);
+        E.pe_s = E.sig + (size_t)SDF_LAYERS * 256 * TM;
+        E.pk_s = E.pe_s + PE_PAD * TM;
+        E.ge_s = E.pk_s + PE_PAD * TM;
+        E.off0 = sw128_offset(E.r, E.gq * 16);
+        E.off1 = sw128_offset(E.r, E.gq * 16 + 8);
+        E.s_hi = smem_u32(A_hi); E.s_lo = smem_u32(A_lo);
         uint32_t gc = 0;
         auto wait_acc = [&]() -> uint32_t {
             mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
@@ -413,17 +531,18 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 auto put = [&](int col, float v) {
                     put_split1(A_hi, A_lo, r, col, v * ACT_SCALE);
                     E.pe_s[col * TM + r] = v;
+                    E.pk_s[col * TM + r] = v * (ACT_SCALE * INV_SQRT2);
                 };
                 auto put_sin = [&](int d) {
                     float f = 1.0f;
 #pragma unroll
-                    for (int k = 0; k < SDF_FREQ; ++k) { put(3 + d * SDF_FREQ + k, sinf(x[d] * f)); f *= 2.0f; }
+                    for (int k = 0; k < SDF_FREQ; ++k) { put(3 + d * SDF_FREQ + k, sin_precise(x[d] * f)); f *= 2.0f; }
                 };
                 auto put_cos = [&](int d) {
                     float f = 1.0f;
 #pragma unroll
                     for (int k = 0; k < SDF_FREQ; ++k) {
-                        put(3 + 3 * SDF_FREQ + d * SDF_FREQ + k, sinf(x[d] * f + 1.57079637050628662109375f)); f *= 2.0f;
+                        put(3 + 3 * SDF_FREQ + d * SDF_FREQ + k, sin_precise(x[d] * f + 1.57079637050628662109375f)); f *= 2.0f;
                     }
                 };
                 if (gq == 0) { put(0, x[0]); put(1, x[1]); put(2, x[2]); put_sin(0); }
@@ -433,6 +552,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     put_cos(2);
                     put_split1(A_hi, A_lo, r, 39, 0.f);
                     E.pe_s[39 * TM + r] = 0.f;
+                    E.pk_s[39 * TM + r] = 0.f;
                     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int k8 = 40; k8 < 64; k8 += 8) {
@@ -441,7 +561,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     }
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&a_ready[0]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[0]);
                 epi_bar_sync();                       // pe_s visible to every epilogue thread
             }
 
@@ -449,32 +570,30 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             float dot = 0.f;
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
-                const uint32_t acc = wait_acc();
-                if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, acc, l, P.bias[l], P.head_w, dot);
-                else epi_forward<GRAD, 0, 1>(E, acc, l, P.bias[l], P.head_w, dot);
+                E.tl = (P.tlog && blockIdx.x == 0 && tile == 2 * (int64_t)gridDim.x && warp == 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
+                if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
+                else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 tc_fence_before();
             }
             {
-                const uint32_t acc = wait_acc();
                 constexpr int OUT = FEAT ? 1 : (GRAD ? 2 : 0);
-                epi_forward<GRAD, 2, OUT>(E, acc, SDF_LAYERS - 1, P.bias[SDF_LAYERS - 1], P.head_w, dot);
+                E.tl = nullptr;
+                epi_forward<GRAD, 2, OUT>(E, wait_acc, SDF_LAYERS - 1, P.bias16 + (SDF_LAYERS - 1) * 256, P.head_w, dot);
                 tc_fence_before();
                 // sdf head: combine the four column quarters
                 if (gq > 0) part[(gq - 1) * TM + r] = dot;
                 epi_bar_sync();
-                if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) + __ldg(P.head_b)) / SDF_SCALE;
+                if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) * (1.0f / ACT_SCALE) + __ldg(P.head_b)) / SDF_SCALE;
             }
             if (FEAT) {
-                const uint32_t acc = wait_acc();
-                epi_feat<GRAD>(E, acc, P.feat_b, P.head_w, feat_out + p * 256, valid);
+                epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + p * 256, valid);
                 tc_fence_before();
             }
             if (GRAD) {
 #pragma unroll 1
                 for (int l = SDF_LAYERS - 1; l >= 1; --l) {
-                    const uint32_t acc = wait_acc();
-                    if (l == SDF_SKIP) epi_reverse<true>(E, acc, l);
-                    else epi_reverse<false>(E, acc, l);
+                    if (l == SDF_SKIP) epi_reverse<true>(E, wait_acc, l);
+                    else epi_reverse<false>(E, wait_acc, l);
                     tc_fence_before();
                 }
                 // ---- reverse layer 0 + chain through the encoding (39 columns; quarter 0 warps) ----
@@ -499,8 +618,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
 #pragma unroll
                         for (int k = 0; k < SDF_FREQ; ++k) {
                             const float sarg = x * f;
-                            acc_d += gcol(3 + d * SDF_FREQ + k) * cosf(sarg) * f;
-                            acc_d += gcol(3 + 3 * SDF_FREQ + d * SDF_FREQ + k) * cosf(sarg + 1.57079637050628662109375f) * f;
+                            acc_d += gcol(3 + d * SDF_FREQ + k) * cos_precise(sarg) * f;
+                            acc_d += gcol(3 + 3 * SDF_FREQ + d * SDF_FREQ + k) * cos_precise(sarg + 1.57079637050628662109375f) * f;
                             f *= 2.0f;
                         }
                         gsum[d] = acc_d;
@@ -527,7 +646,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
 // ===============================================================================================================
 struct ColTcParams {
     const uint8_t* tc;
-    const float* b0; const float* b[3]; const float* w4t; const float* b4;
+    const float* bias16;               // [4][256] hidden-layer biases * ACT_SCALE
+    const float* w4t; const float* b4;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -538,19 +658,19 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
     uint8_t* A = smem + SMC_A;
     uint8_t* Bst = smem + SMC_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMC_MISC);
-    uint64_t* b_full = bars;            // [3]
-    uint64_t* b_empty = bars + 3;       // [3]
-    uint64_t* a_ready = bars + 6;       // [6]
-    uint64_t* acc_full = bars + 12;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* part = reinterpret_cast<float*>(bars + 16);          // [3 channels][3 quarters][128]
+    uint64_t* b_full = bars;                  // [12]
+    uint64_t* b_empty = bars + NSTAGES;       // [12]
+    uint64_t* a_ready = bars + 2 * NSTAGES;   // [6]
+    uint64_t* acc_full = a_ready + 6;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    float* part = reinterpret_cast<float*>(bars + 40);          // [3 channels][3 quarters][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TcLayout T = tc_layout();
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 6; ++i) mbar_init(&a_ready[i], EPI_THREADS);
+        for (int i = 0; i < 6; ++i) mbar_init(&a_ready[i], EPI_WARPS);
         for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
         fence_mbar_init();
     }
@@ -569,15 +689,15 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     for (int img = 0; img < nimg; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[s], IMG);
-                        bulk_g2s(Bst + s * IMG, P.tc + T.col[gi] + (size_t)img * IMG, IMG, &b_full[s]);
+                        mbar_arrive_expect_tx(&b_full[s], STAGE);
+                        bulk_g2s(Bst + s * STAGE, P.tc + T.col[gi] + (size_t)img * IMG, STAGE, &b_full[s]);
                     }
                 }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             uint32_t it = 0, a_par = 0, gc = 0;
-            const uint32_t a_addr = smem_u32(A), b_addr = smem_u32(Bst);
+            const uint32_t a_lo0 = desc_lo(smem_u32(A)), b_lo0 = desc_lo(smem_u32(Bst));
             const uint32_t idesc = make_idesc_f16(TM, 256);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int gi = 0; gi < 4; ++gi, ++gc) {
@@ -587,13 +707,16 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
                         a_par ^= (1u << c);
                         tc_fence_after();
-                        const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
-                        mbar_wait(&b_full[s], u & 1);
-                        tc_fence_after();
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_f16(acc, make_desc_sw128(a_addr + c * A_CHUNK + ks * 32),
-                                     make_desc_sw128(b_addr + s * IMG + ks * 32), idesc, (c | ks) != 0);
-                        umma_commit(&b_empty[s]);
+                        const uint32_t al = a_lo0 + c * (A_CHUNK >> 4);
+                        {
+                            const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
+                            mbar_wait(&b_full[s], u & 1);
+                            tc_fence_after();
+                            const uint32_t bl = b_lo0 + s * (STAGE >> 4), d = acc;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_lo(d, al + ks * 2, bl + ks * 2, idesc, (uint32_t)((c | ks) != 0));
+                            umma_commit(&b_empty[s]);
+                        }
                     }
                     umma_commit(&acc_full[gc & 1]);
                 }
@@ -602,6 +725,8 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
         const int q = warp & 3, gq = (warp - 2) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t off0 = sw128_offset(r, gq * 16), off1 = sw128_offset(r, gq * 16 + 8);
+        const uint32_t a_s = smem_u32(A);
         uint32_t gc = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p = tile * TM + r;
@@ -643,43 +768,52 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     store_half8(A + (4 + (gq >> 1)) * A_CHUNK, sw128_offset(r, (gq & 1) * 32 + k8), o);
                 }
                 fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
 #pragma unroll
-                for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
+                    for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
+                }
             }
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
             for (int gi = 0; gi < 4; ++gi, ++gc) {
+                const float* bias16 = P.bias16 + gi * 256 + gq * 16;
+                float vA[16], bA[16], vB[16], bB[16];
+                ldg16(bias16, bA);
+                ldg16(bias16 + 64, bB);
                 mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256;
-                const float* bias = gi == 0 ? P.b0 : P.b[gi - 1];
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int col0 = c * 64 + gq * 16;
-                    float v[16], b[16];
-                    tmem_ld16(acc + col0, v);
-                    ldg16(bias + col0, b);
+                const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256 + gq * 16;
+                tmem_ld16(acc, vA);
+                const bool last = gi == 3;
+                auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], const int c) {
                     tmem_wait_ld();
+                    if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], OS_F, b[i]), 0.f);
-                    if (gi == 3) {
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], OS_F16, b[i]), 0.f);      // ReLU, x16 units
+                    if (last) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + (col0 + i) * 4));
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + (c * 64 + gq * 16 + i) * 4));
                             d0 = fmaf(v[i], w.x, d0); d1 = fmaf(v[i], w.y, d1); d2 = fmaf(v[i], w.z, d2);
                         }
                     } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] *= ACT_SCALE;
-                        store_half8(A + c * A_CHUNK, sw128_offset(r, gq * 16), v);
-                        store_half8(A + c * A_CHUNK, sw128_offset(r, gq * 16 + 8), v + 8);
+                        store_half8s(a_s + c * A_CHUNK + off0, v);
+                        store_half8s(a_s + c * A_CHUNK + off1, v + 8);
                         fence_proxy_async_smem();
                         tc_fence_before();
-                        mbar_arrive(&a_ready[c]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&a_ready[c]);
                     }
-                }
+                    if (c < 2) ldg16(bias16 + (c + 2) * 64, b);      // after the fence (it drains outstanding loads)
+                };
+                step(vA, bA, vB, 0);
+                step(vB, bB, vA, 1);
+                step(vA, bA, vB, 2);
+                step(vB, bB, vA, 3);
                 tc_fence_before();
             }
+            d0 *= (1.0f / ACT_SCALE); d1 *= (1.0f / ACT_SCALE); d2 *= (1.0f / ACT_SCALE);
             if (gq > 0) { float* pp = part + (gq - 1) * TM + r; pp[0] = d0; pp[3 * TM] = d1; pp[6 * TM] = d2; }
             epi_bar_sync();
             if (gq == 0 && valid) {
@@ -727,6 +861,10 @@ __global__ void k_build_image(ImgJob J) {
     }
 }
 
+__global__ void k_scale_copy(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i] * scale;
+}
+
 int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
                 uint8_t* dst, cudaStream_t st) {
     ImgJob J; J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
@@ -758,7 +896,7 @@ int build_matrix(const float* src, int src_ld, int nrows_valid, int nrows_img, i
 
 bool tc_available() { return true; }
 size_t tc_packed_bytes(const NrhConfig&) { return tc_layout().total; }
-size_t tc_scratch_bytes(int num_sms) { return (size_t)num_sms * ((SDF_LAYERS * 256 + 2 * PE_PAD) * TM) * sizeof(float); }
+size_t tc_scratch_bytes(int num_sms) { return (size_t)num_sms * ((SDF_LAYERS * 256 + 3 * PE_PAD) * TM) * sizeof(float); }
 
 int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& raw, void* packed, cudaStream_t st) {
     uint8_t* tcb = reinterpret_cast<uint8_t*>(packed) + L.tc_offset_bytes;
@@ -794,6 +932,16 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     }
     for (int l = 1; l < 4; ++l)
         if ((rc = build_matrix(raw.col_W[l], 256, 256, 256, 256, 4, false, tcb + T.col[l], IMG, st))) return rc;
+    // biases pre-multiplied by ACT_SCALE (the forward epilogues work in x16 units)
+    for (int l = 0; l < SDF_LAYERS; ++l) {
+        const int out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
+        k_scale_copy<<<1, 256, 0, st>>>(raw.sdf_b[l], reinterpret_cast<float*>(tcb + T.sdf_bias16) + l * 256, out, ACT_SCALE);
+        NRH_LAUNCH_CHECK();
+    }
+    for (int l = 0; l < 4; ++l) {
+        k_scale_copy<<<1, 256, 0, st>>>(raw.col_b[l], reinterpret_cast<float*>(tcb + T.col_bias16) + l * 256, 256, ACT_SCALE);
+        NRH_LAUNCH_CHECK();
+    }
     return NRH_OK;
 }
 
@@ -804,8 +952,10 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     const float* Pf = reinterpret_cast<const float*>(packed);
     SdfTcParams P;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
-    for (int l = 0; l < SDF_LAYERS; ++l) P.bias[l] = Pf + L.sdf_b[l];
+    P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
+    { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
@@ -832,8 +982,7 @@ int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Stride
     const float* Pf = reinterpret_cast<const float*>(packed);
     ColTcParams P;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
-    P.b0 = Pf + L.col_b0;
-    for (int l = 0; l < 3; ++l) P.b[l] = Pf + L.col_b[l];
+    P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().col_bias16);
     P.w4t = Pf + L.col_w4t; P.b4 = Pf + L.col_b4;
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
