@@ -43,7 +43,7 @@ def test_forward_matches_oracle_and_fixture(name, impl):
     got = T.to_np(out)
     for k, v in got.items():
         assert np.isfinite(v).all(), k
-    tol = T.TOL[case["weights"]]
+    tol = (T.TOL if impl == "fp32" else T.TOL_TC)[case["weights"]]
     want = T.to_np(T.run_oracle(case))
     s1 = T.compare_outputs(got, want, label=f"cuda[{impl}]-vs-oracle[{name}]", **tol)
     fx = np.load(T.GOLDEN_DIR / f"{name}.npz")
@@ -73,7 +73,7 @@ def test_training_mode_forward(impl):
         want = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
                                   rays["fars"], is_training=True, background_rgb=bg, cos_anneal=0.5,
                                   jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
-    T.compare_outputs(T.to_np(out), T.to_np(want), label=f"cuda[{impl}]-train", **T.TOL["init"])
+    T.compare_outputs(T.to_np(out), T.to_np(want), label=f"cuda[{impl}]-train", **(T.TOL if impl == "fp32" else T.TOL_TC)["init"])
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -106,8 +106,9 @@ def test_sdf_query_matches_oracle(kind, impl):
     sdf = m.sdf_network.sdf(pts.cuda())
     assert full.shape == (1077, 257) and grad.shape == (1077, 1, 3) and sdf.shape == (1077, 1)
     # fp32 noise grows with |x| (Fourier arguments up to 430 rad at the light distance)
-    assert (sdf.cpu() - want["sdf"]).abs().max() < 2e-5
-    assert (full[:, 1:].cpu() - want["feat"]).abs().max() < 2e-4
+    k = 1.0 if impl == "fp32" else 4.0            # the split-fp16 tensor-core engine carries ~2e-5 absolute noise
+    assert (sdf.cpu() - want["sdf"]).abs().max() < 2e-5 * k
+    assert (full[:, 1:].cpu() - want["feat"]).abs().max() < 2e-4 * k
     assert (grad[:, 0].cpu() - want["grad"]).abs().max() < (2e-3 if kind == "sharp" else 3e-4)
     w64 = orc.sdf_mlp(orc.effective_weights(sd, torch.float64), pts.double(), ocfg, want_grad=True)
     print(kind, impl, "sdf err vs fp64:", float((sdf.cpu().double() - w64["sdf"]).abs().max()),
