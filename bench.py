@@ -89,12 +89,31 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_leg(n_rays: int, repeats: int):
-    """The reference algorithm (oracle port) on the host cores, all threads, on `n_rays` rays of the workload."""
+_BEST_THREADS = None
+
+
+def _pick_threads():
+    """The reference runs PyTorch with min(8, cpus/gpus) threads (trainer/launcher.py:43); on a many-core host more
+    threads help only up to a point and over-subscription hurts, so calibrate once on a small sample and keep the best."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    cores = os.cpu_count() or 1
+    best, best_t = None, None
+    for th in sorted({min(cores, t) for t in (8, 16, 32, 64, cores)}):
+        _, med = cpu_reference_leg(32, 0, threads=th)
+        if best_t is None or med < best_t:
+            best, best_t = th, med
+    _BEST_THREADS = best
+    return best
+
+
+def cpu_reference_leg(n_rays: int, repeats: int, threads: int = None):
+    """The reference algorithm (oracle port) on the host cores on `n_rays` rays of the workload."""
     from oracle import nrh_oracle as orc
     import nrhints_b200 as nb
     from nrhints_b200.workload import synthetic_rays
-    cores = os.cpu_count() or 1
+    cores = threads if threads is not None else _pick_threads()
     torch.set_num_threads(cores)
     cfg = nb.NeuSModelConfig()
     torch.manual_seed(3407)
@@ -111,9 +130,10 @@ def cpu_reference_leg(n_rays: int, repeats: int):
         times.append(time.perf_counter() - t0)
     times = sorted(times[1:]) if repeats > 0 else times
     med = times[len(times) // 2]
-    return {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": "port",
+    return {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
             "sample": f"{n_rays} rays x 128 samples of the same workload, 1 warm-up + median of {max(repeats, 1)} passes, "
-                      f"torch {torch.get_num_threads()} threads (oracle port of the reference PyTorch path)"}, med
+                      f"torch {torch.get_num_threads()} threads = best of {{8,16,32,64,all}} on this host "
+                      f"(oracle port of the reference PyTorch path)"}, med
 
 
 def run_reference_arm(args):
@@ -224,14 +244,14 @@ def main():
     e2e_steps = max(3, min(K, 5))
     out_host = None
     for _ in range(2):
-        out_host = model(host_rays.to(dev, non_blocking=True), background_rgb=bg).to("cpu")
+        out_host = model.to_host(model(host_rays.to(dev, non_blocking=True), background_rgb=bg))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         o = model(host_rays.to(dev, non_blocking=True), is_training=False, background_rgb=bg)
-        out_host = o.to("cpu")
+        out_host = model.to_host(o)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -266,7 +286,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": f"cuBLAS bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); the fp16x3 split issues 3 MMAs per "
                              "logical product, the fp32-simt engine runs on FFMA (75 TFLOP/s nominal)",
-                "kernel_ms": k_ms, "flop_per_launch": FLOP_PER_FINE_POINT * R * 128, "traffic": None,
+                "kernel_ms": k_ms, "flop_per_launch": FLOP_PER_FINE_POINT * R * 128, "traffic": _ncu_traffic(engine),
                 "whole_step": {"achieved_tflops": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12,
                                "frac_of_tensor_peak": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12 / peak,
                                "hbm_algorithmic_gbs": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9,
@@ -286,13 +306,23 @@ def main():
                        "rays_per_gpu": R, "samples_per_ray": 128, "mlp_engine": engine, "parallelism": f"rays sharded x{world}, no data-path collective",
                        "l2": "256 MiB buffer rewritten between timed steps (L2 flush); per-step working set ~0.9 GB > 126 MB L2"},
             "e2e": {"value": world * R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "pinned host RayBundle -> device, forward, full RenderOutput -> host (pipelines/base_pipeline.py:114-120 pattern)"},
+                    "what": "pinned host RayBundle -> device, forward, full RenderOutput -> pinned host buffers (pipelines/base_pipeline.py:114-120 pattern)"},
             "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _ncu_traffic(engine):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json, written by hand from profiles/*.txt); None if there is no capture for this engine."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text()).get(engine)
+    return d
 
 
 def _engine_is_tc(lib, ccfg):

@@ -395,6 +395,31 @@ class NeuSHintRenderer(nn.Module):
             specular_cue=out["specular_cue"] if self.has_specular_hint else None,
             z_vals=out["z_vals"], z_shadow=out["z_shadow"], sampled_color=out["sampled_color"])
 
+    # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
+    #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy
+    #    per field on the current stream, one sync) -------------------------------------------------------------------
+    def to_host(self, out: RenderOutput) -> RenderOutput:
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        host = {}
+        for k, v in out.as_dict().items():
+            if v is None:
+                host[k] = None
+                continue
+            if k == "relax_inside_sphere":
+                continue
+            v = v.detach()
+            key = (k, tuple(v.shape), v.dtype)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                self._pinned[key] = buf
+            buf.copy_(v, non_blocking=True)
+            host[k] = buf
+        host["relax_inside_sphere"] = host["inside_sphere"]
+        torch.cuda.current_stream(out.rgb.device).synchronize()
+        return RenderOutput(**host)
+
     # -- meshing helpers (models/neus_hint_model.py:68-93,753-758) -------------------------------------------
     @torch.no_grad()
     def extract_fields(self, bound_min, bound_max, resolution: int, chunk: int = 1 << 22) -> np.ndarray:

@@ -36,3 +36,13 @@ def synthetic_rays(R: int, seed: int = 3407, crop: int = 800):
     mid = 0.5 * (-b) / a
     return {"origins": o32, "directions": d32, "pl_positions": torch.tensor(pl, dtype=torch.float32),
             "nears": mid - 1.0, "fars": mid + 1.0}
+
+
+def shard_rays(rays: dict, rank: int, world: int) -> dict:
+    """Contiguous ray slice of one rank (the reference's per-rank batch = batch_size // world_size,
+    /root/reference/trainer/trainer.py:118).  Rays are independent: no data-path collective is needed."""
+    R = rays["origins"].shape[0]
+    per = R // world
+    lo = rank * per
+    hi = R if rank == world - 1 else lo + per
+    return {k: v[lo:hi] for k, v in rays.items()}

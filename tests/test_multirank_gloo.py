@@ -1,0 +1,62 @@
+"""The N>1 path of bench.py on CPU with 2 gloo ranks: ray sharding bookkeeping (each rank renders its own slice, no
+data-path collective), max-over-ranks timing reduction and whole-job throughput aggregation.  The compute itself is
+replaced by the oracle on a handful of rays (the CUDA library needs a GPU); what is tested is the host logic."""
+import os
+import socket
+import sys
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import nrh_testlib as T
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(T.ROOT))
+    from nrhints_b200.workload import synthetic_rays, shard_rays
+    from oracle import nrh_oracle as orc
+    import nrhints_b200 as nb
+    torch.set_num_threads(2)
+    R_total = 8
+    rays = synthetic_rays(R_total, seed=11, crop=300)
+    mine = shard_rays(rays, rank, world)                      # contiguous slice, trainer/trainer.py:118 semantics
+    cfg = nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_samples=8, n_importance_samples=8, n_shadow_samples=8,
+                                                            n_shadow_importance_samples=8))
+    sd = T.make_state("init", cfg)
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    with torch.no_grad():
+        out = orc.render_forward(sd, ocfg, mine["origins"], mine["directions"], mine["pl_positions"], mine["nears"], mine["fars"],
+                                 background_rgb=torch.ones(1, 3))
+    # gather the slices on rank 0 and compare with the unsharded render
+    parts = [torch.zeros_like(out["rgb"]) for _ in range(world)]
+    dist.all_gather(parts, out["rgb"])
+    t = torch.tensor([1.0 + rank], dtype=torch.float64)       # fake per-rank elapsed ms: the slowest rank defines the step
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        with torch.no_grad():
+            full = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"], rays["fars"],
+                                      background_rgb=torch.ones(1, 3))
+        q.put((torch.allclose(torch.cat(parts), full["rgb"], atol=1e-6), float(t.item()), world * mine["origins"].shape[0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ray_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, tmax, total = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, "sharded render != unsharded render"
+    assert tmax == 2.0 and total == 8
