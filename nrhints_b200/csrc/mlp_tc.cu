@@ -171,6 +171,7 @@ struct SdfTcParams {
     const uint8_t* tc;                 // tensor-core section (operand images)
     const float* bias16;               // [8][256] biases * ACT_SCALE (tensor-core section)
     const float* head_w; const float* head_b; const float* feat_b;
+    int ncta;                          // CTAs per cluster sharing one weight stream (1 or 2, multicast loads)
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
 };
@@ -411,32 +412,46 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     constexpr int NG = num_gemms<GRAD, FEAT>();
     const TcLayout T = tc_layout();
 
+    // A cluster of `ncta` CTAs shares one weight stream: every CTA loads 1/ncta of each stage and multicasts it, a
+    // stage is recycled when the MMAs of every CTA that read it have completed (multicast commit -> b_empty).
+    // All CTAs of a cluster run the same number of tile iterations (a CTA without a real tile computes on zeros).
+    const int ncta = P.ncta;
+    const uint32_t crank = ncta > 1 ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << ncta) - 1);
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
-        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], ncta); }
         for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], EPI_WARPS);
         for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
         fence_mbar_init();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t ntiles = (N + TM - 1) / TM;
+    const int64_t tile0 = (int64_t)(blockIdx.x / ncta) * ncta + crank;      // == blockIdx.x
+    const int64_t tstride = gridDim.x;
+    const int64_t tiles_padded = (ntiles + ncta - 1) / ncta * ncta;          // clusters iterate in lock step
 
     if (warp == 0) {
         // ======================= weight producer =======================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
                 for (int gi = 0; gi < NG; ++gi) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     for (int img = 0; img < G.nchunks * 2; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                        if (P.dbg >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic
+                        if (P.dbg >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
                         mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
-                        bulk_g2s(Bst + s * STAGE, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
+                        const uint8_t* src = P.tc + G.b_off + (size_t)img * G.img_bytes;
+                        if (ncta == 1) bulk_g2s(Bst + s * STAGE, src, G.img_bytes, &b_full[s]);
+                        else {
+                            const uint32_t part = G.img_bytes / ncta;
+                            bulk_g2s_multicast(Bst + s * STAGE + crank * part, src + crank * part, part, &b_full[s], cmask);
+                        }
                     }
                 }
         }
@@ -446,12 +461,12 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             uint32_t it = 0, a_par = 0, gc = 0;
             const uint32_t a_hi_lo = desc_lo(smem_u32(A_hi)), a_lo_lo = desc_lo(smem_u32(A_lo)), b_lo0 = desc_lo(smem_u32(Bst));
             const bool mma_on = (P.dbg != 2 && P.dbg != 4);
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
                 for (int gi = 0; gi < NG; ++gi, ++gc) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
-                    const bool lg = P.tlog && blockIdx.x == 0 && tile == 2 * (int64_t)gridDim.x && gi < 8;
+                    const bool lg = P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && gi < 8;
                     for (int c = 0; c < G.nchunks; ++c) {
                         if (lg) P.tlog[gi * 16 + c * 3 + 0] = clock64();
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
@@ -473,7 +488,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                                 for (int ks = 0; ks < 4; ++ks)
                                     if (ks < G.ksteps) umma_f16_lo(d, al + ks * 2, bl + ks * 2, idesc, 1u);
                             }
-                            umma_commit(&b_empty[s]);
+                            if (ncta == 1) umma_commit(&b_empty[s]); else umma_commit_multicast(&b_empty[s], cmask);
                         }
                         // W_lo image: A_hi * W_lo
                         {
@@ -486,7 +501,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                                 for (int ks = 0; ks < 4; ++ks)
                                     if (ks < G.ksteps) umma_f16_lo(d, ah + ks * 2, bl + ks * 2, idesc, 1u);
                             }
-                            umma_commit(&b_empty[s]);
+                            if (ncta == 1) umma_commit(&b_empty[s]); else umma_commit_multicast(&b_empty[s], cmask);
                         }
                         if (lg) P.tlog[gi * 16 + c * 3 + 2] = clock64();
                     }
@@ -519,7 +534,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             return a;
         };
 
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int64_t tile = tile0; tile < tiles_padded; tile += tstride) {
             const int64_t p = tile * TM + r;
             const bool valid = p < N;
             // ---------------- Fourier encoding -> A chunk 0 (hi/lo) + fp32 copy ----------------
@@ -570,7 +585,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             float dot = 0.f;
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
-                E.tl = (P.tlog && blockIdx.x == 0 && tile == 2 * (int64_t)gridDim.x && warp == 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
+                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 tc_fence_before();
@@ -586,7 +601,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) * (1.0f / ACT_SCALE) + __ldg(P.head_b)) / SDF_SCALE;
             }
             if (FEAT) {
-                epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + p * 256, valid);
+                epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + (valid ? p : 0) * 256, valid);
                 tc_fence_before();
             }
             if (GRAD) {
@@ -637,7 +652,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();            // no CTA may exit while its peer can still multicast into it / arrive on its barriers
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -957,13 +972,21 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int64_t ntiles = (N + TM - 1) / TM;
-    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    { const char* e = getenv("NRH_TC_CLUSTER"); P.ncta = e ? atoi(e) : 2; if (P.ncta != 2 || P.dbg >= 3) P.ncta = 1; }
+    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    if (P.ncta == 2) grid = (grid + 1) / 2 * 2 > num_sms ? num_sms / 2 * 2 : (grid + 1) / 2 * 2;
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
     const bool grad = gx != nullptr, wfeat = feat != nullptr;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = SDF_SMEM; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
 #define NRH_LAUNCH_TC(G, F)                                                                                        \
     do {                                                                                                           \
         NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM)); \
-        sdf_tc_kernel<G, F><<<grid, NTHREADS, SDF_SMEM, st>>>(P, pts, N, sdf, gx, gy, gz, grad_stride, feat, scratch);          \
+        NRH_CUDA_CHECK(cudaLaunchKernelEx(&lc, sdf_tc_kernel<G, F>, P, pts, N, sdf, gx, gy, gz, grad_stride, feat, scratch));   \
     } while (0)
     if (grad && wfeat) NRH_LAUNCH_TC(true, true);
     else if (grad) NRH_LAUNCH_TC(true, false);
