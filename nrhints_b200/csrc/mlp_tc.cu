@@ -11,8 +11,8 @@
 // accumulate); operands are pre-scaled by powers of two so the lo parts stay normal.  The reflectance network
 // enters the pixel through a sigmoid and is safe in a single fp16 pass.
 //
-// Warp roles (576 threads): warp 0 = weight producer (TMA), warp 1 = MMA issuer (one elected thread),
-// warps 2..17 = epilogue (TMEM -> registers -> bias/activation/split -> swizzled smem operand for the next layer).
+// Warp roles (640 threads): warp 0 = weight producer (TMA), warp 1 = MMA issuer (one elected thread), warps 2-3
+// idle (keeps the epilogue on whole warpgroups), warps 4..19 = epilogue (TMEM -> registers -> bias/activation/split -> swizzled smem operand for the next layer).
 //
 // Reference semantics: /root/reference/fields/sdf_field.py:106-148, fields/reflectance_network.py:68-96,
 // fields/encodings.py:168-176.
@@ -31,7 +31,9 @@ using namespace tc;
 constexpr int TM = 128;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;     // 512
-constexpr int NTHREADS = 64 + EPI_THREADS;       // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue
+constexpr int NTHREADS = 128 + EPI_THREADS;      // warpgroup 0: warp 0 producer, warp 1 MMA issuer, warps 2-3 idle;
+                                                 // warps 4..19 epilogue.
+constexpr int EPI_WARP0 = 4;
 constexpr int NSTAGES = 3;               // weight ring: 3 x 32 KB images (N < 256 per MMA does not pay: an SS-mode MMA costs
                                          // ~115 clk whatever N is, measured; so a stage is a full [256 x 64] image)
 constexpr uint32_t STAGE = 32768;
@@ -79,6 +81,8 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// (setmaxnreg re-balancing between the control warpgroup and the epilogue was tried: nvcc 12.9 segfaults on this
+//  kernel with it, so every thread keeps the 96 registers ptxas grants a 640-thread block.)
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -102,6 +106,20 @@ __device__ __forceinline__ float softplus100(float x, float& dsig) {
 
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// The reverse sweep needs softplus'(x) = sigmoid(100 x) of every forward pre-activation.  The forward epilogue is
+// MUFU-bound (ex2 + lg2 per element on 16 SFU lanes/SM), the reverse epilogue has no transcendental at all, so the
+// forward parks only e = exp(-100|x|) with the sign of x (one LOP3) and the reverse epilogue finishes the job:
+// sigmoid = x > 0 ? 1/(1+e) : e/(1+e)  (one MUFU.RCP there).  Result is pre-divided by W_SCALE.
+__device__ __forceinline__ uint32_t pack_sig2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_sig2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ float dsig_from_packed(float pk) {
+    const float e = fabsf(pk);
+    const float rr = rcp_approx(1.0f + e);
+    return (__float_as_int(pk) >= 0 ? rr : e * rr) * OS_R;      // sign BIT: e underflows to +-0 for |100 x| > 87
 }
 // split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows (shared addresses)
 __device__ __forceinline__ void store_split8s(uint32_t s_hi, uint32_t s_lo, const float* x) {
@@ -202,7 +220,7 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
 // per-thread view of the epilogue: row r of the tile (== TMEM lane), column quarter gq of every 64-wide chunk
 struct Epi {
     uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;
-    float* sig;      // [8][256][128] softplus' / W_SCALE of every forward layer (reverse sweep)
+    uint32_t* sig;   // [8][128 column pairs][128 rows] packed softplus' of every forward layer: half2 of copysign(exp(-100|x|), x)
     float* pe_s;     // [40][128] fp32 Fourier encoding (final chain)
     float* pk_s;     // [40][128] encoding * ACT_SCALE / sqrt2 (skip concat operand)
     float* ge_s;     // [40][128] skip-path gradient (G_SCALE units)
@@ -244,27 +262,31 @@ template <bool GRAD, int LT, int OUT, class WaitAcc>
 __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, int l, const float* __restrict__ bias16,
                                             const float* __restrict__ head_w, float& dot16) {
     float vA[16], bA[16], vB[16], bB[16];
+    float wA[LT == 2 ? 16 : 1], wB[LT == 2 ? 16 : 1], pk[LT == 1 ? 16 : 1];
     const int cq = E.gq * 16;
     ldg16(bias16 + cq, bA);
     ldg16(bias16 + cq + 64, bB);
+    if (LT == 2) { ldg16(head_w + cq, reinterpret_cast<float (&)[16]>(wA)); ldg16(head_w + cq + 64, reinterpret_cast<float (&)[16]>(wB)); }
+    if (LT == 1) {                                     // skip-concat operand of the last chunk (columns >= 217)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int col = 192 + cq + i; pk[LT == 1 ? i : 0] = col >= SKIP_H ? E.pk_s[(col - SKIP_H) * TM + E.r] : 0.f; }
+    }
     if (E.tl) E.tl[0] = clock64();
     const uint32_t acc = wait_acc() + cq;
     if (E.tl) E.tl[1] = clock64();
     tmem_ld16(acc, vA);
-    float* const sig_l = E.sig + ((size_t)l * 256 + cq) * TM + E.r;
-    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], const int c) {
+    uint32_t* const sig_l = E.sig + ((size_t)l * 128 + cq / 2) * TM + E.r;
+    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], float* w, const int c) {
         tmem_wait_ld();
         if (E.tl) E.tl[2 + c * 3] = clock64();
         if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
-        float w[16];
-        if (LT == 2) ldg16(head_w + cq + c * 64, w);
         float s[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float x = fmaf(v[i], OS_F16, b[i]);
             const float e = ex2_approx(SP_K * fabsf(x));
             const float t = 1.0f + e;
-            if (GRAD) { const float rr = rcp_approx(t); s[i] = (x > 0.0f ? rr : e * rr) * OS_R; }
+            if (GRAD) s[i] = copysignf(e, x);                     // packed softplus' (see dsig_from_packed)
             v[i] = fmaf(lg2_approx(t), SP_L, fmaxf(x, 0.0f));
         }
         if (LT == 1) {
@@ -275,7 +297,7 @@ __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, in
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int col = c * 64 + cq + i;
-                    v[i] = col < SKIP_H ? v[i] * INV_SQRT2 : E.pk_s[(col < SKIP_H ? 0 : col - SKIP_H) * TM + E.r];
+                    v[i] = col < SKIP_H ? v[i] * INV_SQRT2 : pk[LT == 1 ? i : 0];
                 }
             }
         }
@@ -288,21 +310,24 @@ __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, in
             E.publish(c, v);
         } else if (OUT == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (W_SCALE * G_SCALE / SDF_SCALE);
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
             E.publish(c, v);
         }
         if (E.tl) E.tl[4 + c * 3] = clock64();
         // global traffic goes after the fence inside publish(): softplus' stores, bias of the chunk after next
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sig_l[(size_t)(c * 64 + i) * TM] = s[i];
+            for (int i = 0; i < 8; ++i) sig_l[(size_t)(c * 32 + i) * TM] = pack_sig2(s[2 * i], s[2 * i + 1]);
         }
-        if (c < 2) ldg16(bias16 + cq + (c + 2) * 64, b);
+        if (c < 2) {
+            ldg16(bias16 + cq + (c + 2) * 64, b);
+            if (LT == 2) ldg16(head_w + cq + (c + 2) * 64, *reinterpret_cast<float (*)[16]>(w));
+        }
     };
-    step(vA, bA, vB, 0);
-    step(vB, bB, vA, 1);
-    step(vA, bA, vB, 2);
-    step(vB, bB, vA, 3);
+    step(vA, bA, vB, wA, 0);
+    step(vB, bB, vA, wB, 1);
+    step(vA, bA, vB, wA, 2);
+    step(vB, bB, vA, wB, 3);
 }
 
 // feature head epilogue: write feat (fp32, row-major) and, with GRAD, seed the reverse sweep
@@ -314,7 +339,7 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
     ldg16(bias + cq, bA);
     const uint32_t acc = wait_acc() + cq;
     tmem_ld16(acc, vA);
-    const float* const sig_l = E.sig + ((size_t)(SDF_LAYERS - 1) * 256 + cq) * TM + E.r;
+    const uint32_t* const sig_l = E.sig + ((size_t)(SDF_LAYERS - 1) * 128 + cq / 2) * TM + E.r;
     auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], float (&nb)[16], const int c) {
         tmem_wait_ld();
         if (c < 3) { tmem_ld16(acc + (c + 1) * 64, nv); ldg16(bias + cq + (c + 1) * 64, nb); }
@@ -322,7 +347,7 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
         if (GRAD) {
             ldg16(head_w + cq + c * 64, w);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = sig_l[(size_t)(c * 64 + i) * TM];
+            for (int i = 0; i < 8; ++i) { const float2 t2 = unpack_sig2(sig_l[(size_t)(c * 32 + i) * TM]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
@@ -333,7 +358,7 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
         }
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * s[i] * (W_SCALE * G_SCALE / SDF_SCALE);
+            for (int i = 0; i < 16; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
             E.publish(c, v);
         }
     };
@@ -348,30 +373,32 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
 template <bool SKIP, class WaitAcc>
 __device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, int l) {
     const int cq = E.gq * 16;
-    const float* const sig_l = E.sig + ((size_t)(l - 1) * 256 + cq) * TM + E.r;
-    float vA[16], sA[16], vB[16], sB[16];
-    auto load_sig = [&](float (&sg)[16], const int c) {
+    const uint32_t* const sig_l = E.sig + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
+    float vA[16], vB[16];
+    uint32_t sA[8], sB[8];
+    auto load_sig = [&](uint32_t (&sg)[8], const int c) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            sg[i] = (!SKIP || c * 64 + cq + i < SKIP_H) ? sig_l[(size_t)(c * 64 + i) * TM] : 0.f;
+        for (int i = 0; i < 8; ++i)
+            sg[i] = (!SKIP || c * 64 + cq + 2 * i < SKIP_H) ? sig_l[(size_t)(c * 32 + i) * TM] : 0u;
     };
     load_sig(sA, 0);
     load_sig(sB, 1);
     const uint32_t acc = wait_acc() + cq;
     tmem_ld16(acc, vA);
-    auto step = [&](float (&v)[16], float (&sg)[16], float (&nv)[16], const int c) {
+    auto step = [&](float (&v)[16], uint32_t (&sg)[8], float (&nv)[16], const int c) {
         tmem_wait_ld();
         if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
         float ge[16];
-        if (!SKIP) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= sg[i];
-        } else {
+        for (int i = 0; i < 8; ++i) {
+            const float2 pk = unpack_sig2(sg[i]);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int col = c * 64 + cq + i;
-                if (col >= SKIP_H) { ge[i] = v[i] * (OS_R * INV_SQRT2); v[i] = 0.f; }
-                else v[i] = v[i] * INV_SQRT2 * sg[i];
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * i + h, col = c * 64 + cq + j;
+                const float p1 = h ? pk.y : pk.x;
+                if (!SKIP) v[j] *= dsig_from_packed(p1);
+                else if (col >= SKIP_H) { ge[j] = v[j] * (OS_R * INV_SQRT2); v[j] = 0.f; }
+                else v[j] = v[j] * INV_SQRT2 * dsig_from_packed(p1);
             }
         }
         E.publish(c, v);
@@ -466,11 +493,12 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
-                    const bool lg = P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && gi < 8;
+                    const int lgi = (P.dbg == 9) ? gi - 8 : gi;
+                    const bool lg = P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
                     for (int c = 0; c < G.nchunks; ++c) {
-                        if (lg) P.tlog[gi * 16 + c * 3 + 0] = clock64();
+                        if (lg) P.tlog[lgi * 16 + c * 3 + 0] = clock64();
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
-                        if (lg) P.tlog[gi * 16 + c * 3 + 1] = clock64();
+                        if (lg) P.tlog[lgi * 16 + c * 3 + 1] = clock64();
                         a_par ^= (1u << c);
                         tc_fence_after();
                         const uint32_t ah = a_hi_lo + c * (A_CHUNK >> 4), al = a_lo_lo + c * (A_CHUNK >> 4);
@@ -503,23 +531,24 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                             }
                             if (ncta == 1) umma_commit(&b_empty[s]); else umma_commit_multicast(&b_empty[s], cmask);
                         }
-                        if (lg) P.tlog[gi * 16 + c * 3 + 2] = clock64();
+                        if (lg) P.tlog[lgi * 16 + c * 3 + 2] = clock64();
                     }
                     umma_commit(&acc_full[gc & 1]);
-                    if (lg) P.tlog[gi * 16 + 12] = clock64();
+                    if (lg) P.tlog[lgi * 16 + 12] = clock64();
                 }
         }
-    } else {
+    } else if (warp >= EPI_WARP0) {
         // ======================= epilogue warps =======================
         Epi E;
         E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
         const int q = warp & 3;
-        E.gq = (warp - 2) >> 2;
+        E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
         const int r = E.r, gq = E.gq;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        E.sig = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 256 + 3 * PE_PAD) * TM);
-        E.pe_s = E.sig + (size_t)SDF_LAYERS * 256 * TM;
+        float* const scr = scratch + (size_t)blockIdx.x * ((SDF_LAYERS * 128 + 3 * PE_PAD) * TM);
+        E.sig = reinterpret_cast<uint32_t*>(scr);
+        E.pe_s = scr + (size_t)SDF_LAYERS * 128 * TM;
         E.pk_s = E.pe_s + PE_PAD * TM;
         E.ge_s = E.pk_s + PE_PAD * TM;
         E.off0 = sw128_offset(E.r, E.gq * 16);
@@ -585,7 +614,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             float dot = 0.f;
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
-                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
+                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 tc_fence_before();
@@ -736,8 +765,8 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     umma_commit(&acc_full[gc & 1]);
                 }
         }
-    } else {
-        const int q = warp & 3, gq = (warp - 2) >> 2;
+    } else if (warp >= EPI_WARP0) {
+        const int q = warp & 3, gq = (warp - EPI_WARP0) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t off0 = sw128_offset(r, gq * 16), off1 = sw128_offset(r, gq * 16 + 8);
@@ -911,7 +940,7 @@ int build_matrix(const float* src, int src_ld, int nrows_valid, int nrows_img, i
 
 bool tc_available() { return true; }
 size_t tc_packed_bytes(const NrhConfig&) { return tc_layout().total; }
-size_t tc_scratch_bytes(int num_sms) { return (size_t)num_sms * ((SDF_LAYERS * 256 + 3 * PE_PAD) * TM) * sizeof(float); }
+size_t tc_scratch_bytes(int num_sms) { return (size_t)num_sms * ((SDF_LAYERS * 128 + 3 * PE_PAD) * TM) * sizeof(float); }
 
 int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& raw, void* packed, cudaStream_t st) {
     uint8_t* tcb = reinterpret_cast<uint8_t*>(packed) + L.tc_offset_bytes;

@@ -159,6 +159,25 @@ NRH_HD void merge_sorted(int k, CSoA z_old, CSoA s_old, int n, CSoA z_new, CSoA 
     }
 }
 
+// The same merge, in place and from the back: z/s hold the k old entries in slots [0,k) and have room for
+// k+n; the n new entries come from z_new/s_new.  Ties keep old before new, exactly like merge_sorted.
+NRH_HD void merge_sorted_backward(int k, SoA z, SoA s, int n, CSoA z_new, CSoA s_new, bool with_sdf) {
+    int a = k - 1, b = n - 1;
+    for (int i = k + n - 1; i >= 0 && b >= 0; --i) {
+        const float zb = z_new[b];
+        const bool take_new = (a < 0) || (zb >= z[a]);
+        if (take_new) {
+            z[i] = zb;
+            if (with_sdf) s[i] = s_new[b];
+            --b;
+        } else {
+            z[i] = z[a];
+            if (with_sdf) s[i] = s[a];
+            --a;
+        }
+    }
+}
+
 // section length / mid-point of sample j (render_core :491-493, get_visibility :416-418)
 NRH_HD void section(CSoA z, int j, int S, float last_dist, float& dist, float& mid) {
     const float zj = z[j];

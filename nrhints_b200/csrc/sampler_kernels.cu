@@ -35,31 +35,53 @@ __global__ void k_coarse_primary(NrhRays rays, int64_t R, int n, const float* __
 
 // ---- one importance step (merge previous new samples, draw new ones, emit their points; on the
 //      last step also merge them and emit the section mid-points of the final sample set) ---------
-__global__ void k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool merge_first,
-                                  float inv_s, bool last, float last_dist_const, const float* last_dist_ray) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// The per-ray algorithm is a chain of short dependent steps over <= 128 samples, so each thread first stages its
+// ray's arrays in shared memory (coalesced, fully overlapped global loads), runs ray_math.cuh on them, and writes
+// the results back: the dependent chain then pays shared-memory latency instead of L2 latency per step.
+constexpr int IS_TPB = 64;
+constexpr int IS_NEW = 32;                                   // max samples drawn per step
+constexpr int IS_ROWS = 3 * NRH_MAX_SAMPLES + 2 * IS_NEW;   // z[128] s[128] w[128] z_new[32] s_new[32]
+constexpr size_t IS_SMEM = (size_t)IS_ROWS * IS_TPB * sizeof(float);
+
+__global__ void __launch_bounds__(IS_TPB)
+k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool merge_first,
+                  float inv_s, bool last, float last_dist_const, const float* last_dist_ray) {
+    extern __shared__ float sm[];
+    const int t = threadIdx.x;
+    const int64_t r = blockIdx.x * (int64_t)IS_TPB + t;
     if (r >= R) return;
+    float* sz = sm + t;                                      // element j at sz[j * IS_TPB]
+    float* ss = sz + NRH_MAX_SAMPLES * IS_TPB;
+    float* sw = ss + NRH_MAX_SAMPLES * IS_TPB;
+    float* szn = sw + NRH_MAX_SAMPLES * IS_TPB;
+    float* ssn = szn + IS_NEW * IS_TPB;
     float o[3], d[3];
     for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
+    for (int j = 0; j < k_old; ++j) { sz[j * IS_TPB] = m.z[cur][(int64_t)j * R + r]; ss[j * IS_TPB] = m.s[cur][(int64_t)j * R + r]; }
     int k = k_old;
     if (merge_first) {
-        merge_sorted(k_old, CSoA{m.z[cur] + r, R}, CSoA{m.s[cur] + r, R}, n_new, CSoA{m.znew + r, R},
-                     CSoA{m.snew + r, R}, SoA{m.z[cur ^ 1] + r, R}, SoA{m.s[cur ^ 1] + r, R}, true);
-        cur ^= 1; k = k_old + n_new;
+        for (int j = 0; j < n_new; ++j) { szn[j * IS_TPB] = m.znew[(int64_t)j * R + r]; ssn[j * IS_TPB] = m.snew[(int64_t)j * R + r]; }
+        merge_sorted_backward(k_old, SoA{sz, IS_TPB}, SoA{ss, IS_TPB}, n_new, CSoA{szn, IS_TPB}, CSoA{ssn, IS_TPB}, true);
+        k = k_old + n_new;
+        cur ^= 1;
+        if (!last)
+            for (int j = 0; j < k; ++j) { m.z[cur][(int64_t)j * R + r] = sz[j * IS_TPB]; m.s[cur][(int64_t)j * R + r] = ss[j * IS_TPB]; }
     }
-    upsample_new_z(o, d, k, CSoA{m.z[cur] + r, R}, CSoA{m.s[cur] + r, R}, inv_s, n_new,
-                   SoA{m.wbuf + r, R}, SoA{m.znew + r, R});
+    upsample_new_z(o, d, k, CSoA{sz, IS_TPB}, CSoA{ss, IS_TPB}, inv_s, n_new, SoA{sw, IS_TPB}, SoA{szn, IS_TPB});
     if (!last) {
-        for (int t = 0; t < n_new; ++t) write_points(o, d, m.znew[(int64_t)t * R + r], (int64_t)t * R + r, m.px, m.py, m.pz);
+        for (int j = 0; j < n_new; ++j) {
+            const float zv = szn[j * IS_TPB];
+            m.znew[(int64_t)j * R + r] = zv;
+            write_points(o, d, zv, (int64_t)j * R + r, m.px, m.py, m.pz);
+        }
     } else {
-        merge_sorted(k, CSoA{m.z[cur] + r, R}, CSoA{nullptr, 0}, n_new, CSoA{m.znew + r, R}, CSoA{nullptr, 0},
-                     SoA{m.z[cur ^ 1] + r, R}, SoA{nullptr, 0}, false);
+        merge_sorted_backward(k, SoA{sz, IS_TPB}, SoA{ss, IS_TPB}, n_new, CSoA{szn, IS_TPB}, CSoA{nullptr, 0}, false);
         cur ^= 1;
         const int S = k + n_new;
         const float last_dist = last_dist_ray ? last_dist_ray[r] : last_dist_const;
-        CSoA z{m.z[cur] + r, R};
         for (int j = 0; j < S; ++j) {
-            float dist, mid; section(z, j, S, last_dist, dist, mid);
+            float dist, mid; section(CSoA{sz, IS_TPB}, j, S, last_dist, dist, mid);
+            m.z[cur][(int64_t)j * R + r] = sz[j * IS_TPB];
             write_points(o, d, mid, (int64_t)j * R + r, m.px, m.py, m.pz);
         }
     }
@@ -198,7 +220,9 @@ int launch_coarse_primary(const NrhRays& rays, int64_t R, int n, const float* ji
 
 int launch_importance_step(int64_t R, const MarchState& m, int cur, int k_old, int n_new, bool merge_first, float inv_s,
                            bool last, float last_dist_const, const float* last_dist_ray, cudaStream_t st) {
-    k_importance_step<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
+    if (n_new > IS_NEW) { set_error("importance step draws at most %d samples per step", IS_NEW); return NRH_ERR_UNSUPPORTED; }
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(k_importance_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_SMEM));
+    k_importance_step<<<(unsigned)((R + IS_TPB - 1) / IS_TPB), IS_TPB, IS_SMEM, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -26,6 +26,10 @@ void h_merge(int k, const float* z_old, const float* s_old, int n, const float* 
     merge_sorted(k, CSoA{z_old, 1}, CSoA{s_old, 1}, n, CSoA{z_new, 1}, CSoA{s_new, 1}, SoA{z_out, 1}, SoA{s_out, 1}, with_sdf != 0);
 }
 
+void h_merge_backward(int k, float* z, float* s, int n, const float* z_new, const float* s_new, int with_sdf) {
+    merge_sorted_backward(k, SoA{z, 1}, SoA{s, 1}, n, CSoA{z_new, 1}, CSoA{s_new, 1}, with_sdf != 0);
+}
+
 void h_sections(const float* z, int S, float last_dist, float* dist, float* mid) {
     for (int j = 0; j < S; ++j) section(CSoA{z, 1}, j, S, last_dist, dist[j], mid[j]);
 }

@@ -9,6 +9,7 @@ cfg = nb.NeuSModelConfig(); sd = T.make_state("init", cfg)
 m = nb.NeuSHintRenderer(cfg, mlp_impl="tcgen05"); m.load_state_dict(sd); m.cuda()
 pts = (torch.rand(4096 * 128, 3, device="cuda") - 0.5) * 2
 grad = len(sys.argv) > 1 and sys.argv[1] == "grad"
+if len(sys.argv) > 2: os.environ["NRH_TC_DEBUG"] = sys.argv[2]
 m.sdf_query(pts, want_grad=grad); torch.cuda.synchronize()
 buf.zero_(); m.sdf_query(pts, want_grad=grad); torch.cuda.synchronize()
 t = buf.cpu().numpy()

@@ -101,6 +101,25 @@ def test_merge(hlib):
     np.testing.assert_array_equal(so, torch.cat([sdf[0], sn])[idx].numpy())
 
 
+def test_merge_backward_equals_forward(hlib):
+    """the in-place backward merge used by the shared-memory importance kernel == the forward merge, ties included"""
+    g = torch.Generator().manual_seed(12)
+    for trial in range(20):
+        k, n = 64 + 16 * (trial % 4), 16
+        zo, _ = torch.sort(torch.rand(k, generator=g))
+        zn, _ = torch.sort(torch.rand(n, generator=g))
+        if trial % 2:                       # force ties
+            zn[3] = zo[10]; zn[4] = zo[10]; zn[-1] = zo[-1]; zn[0] = zo[0]
+            zn, _ = torch.sort(zn)
+        so, sn = torch.randn(k, generator=g), torch.randn(n, generator=g)
+        zf, sf = np.empty(k + n, np.float32), np.empty(k + n, np.float32)
+        hlib.h_merge(k, _p(f32(zo)), _p(f32(so)), n, _p(f32(zn)), _p(f32(sn)), _p(zf), _p(sf), 1)
+        zb = np.concatenate([f32(zo), np.zeros(n, np.float32)]); sb = np.concatenate([f32(so), np.zeros(n, np.float32)])
+        hlib.h_merge_backward(k, _p(zb), _p(sb), n, _p(f32(zn)), _p(f32(sn)), 1)
+        np.testing.assert_array_equal(zb, zf)
+        np.testing.assert_array_equal(sb, sf)
+
+
 @pytest.mark.parametrize("cos_anneal", [1.0, 0.5])
 def test_composite_primary(hlib, cos_anneal):
     S = 128
