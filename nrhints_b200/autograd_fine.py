@@ -1,0 +1,114 @@
+"""Differentiable fine pass (training / camera registration) -- interim autograd backend.
+
+The CUDA library implements the forward of the whole hot path.  Its backward (recompute-in-backward with the
+second-order terms of the analytic normals) is the next milestone; until it lands, a call that needs
+gradients is split exactly where the reference puts its `torch.no_grad()` fences:
+
+  * everything the reference computes WITHOUT gradients -- the hierarchical sampler on both rays (7 + 6 SDF
+    passes), the shadow visibility, depth / hit point and the specular cue
+    (/root/reference/models/neus_hint_model.py:697-713, :379, :531-533, :589) -- runs in the CUDA kernels;
+  * the differentiable remainder -- SDF + feature at the 128 section mid-points, d sdf/dx with create_graph
+    (fields/sdf_field.py:136-148), NeuS alpha, weights, reflectance MLP, compositing (:504-525, :583-637) --
+    is expressed here with torch ops on the same device, so autograd produces the reference's gradients
+    (parameters, ray origins / directions / light positions, and near/far through the coarse samples).
+
+This module only uses torch; it never touches the oracle and never runs on the CPU in the product path
+(the renderer rejects CPU tensors).  The CPU test-suite exercises it against the oracle.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+def _fourier(x: Tensor, n_freq: int) -> Tensor:
+    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, device=x.device, dtype=x.dtype)
+    s = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
+    return torch.cat([x, torch.sin(torch.cat([s, s + torch.pi / 2.0], dim=-1))], dim=-1)
+
+
+def sdf_forward(sdf_w: List[Tensor], sdf_b: List[Tensor], head: Dict[str, Tensor], pts: Tensor, scale: float = 3.0,
+                skip: int = 4, n_freq: int = 6) -> Tensor:
+    """[N,3] -> [N,257] (sdf | feature), fields/sdf_field.py:106-123."""
+    e = _fourier(pts * scale, n_freq)
+    h = e
+    for l, (w, b) in enumerate(zip(sdf_w, sdf_b)):
+        if l == skip:
+            h = torch.cat([h, e], dim=1) / math.sqrt(2.0)
+        h = F.softplus(F.linear(h, w, b), beta=100.0)
+    sdf = F.linear(h, head["sdf_w"], head["sdf_b"]) / scale
+    feat = F.linear(h, head["feat_w"], head["feat_b"])
+    return torch.cat([sdf, feat], dim=-1)
+
+
+def attach_coarse_gradient(z_final: Tensor, z_coarse: Tensor) -> Tensor:
+    """The reference's final z_vals are a sort of [coarse (differentiable in near/far), importance (detached)]
+    (models/neus_hint_model.py:321-322): give the coarse entries of the kernel's (detached) z their gradient path."""
+    if not z_coarse.requires_grad:
+        return z_final
+    zc = z_coarse.detach()
+    idx = torch.searchsorted(z_final.contiguous(), zc.contiguous()).clamp(max=z_final.shape[1] - 1)
+    lo = (idx - 1).clamp(min=0)
+    pick_lo = (z_final.gather(1, lo) - zc).abs() < (z_final.gather(1, idx) - zc).abs()
+    idx = torch.where(pick_lo, lo, idx)
+    return z_final + torch.zeros_like(z_final).scatter_add(1, idx, z_coarse - zc)
+
+
+def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
+                sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
+                background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
+                refl_freq: int = 4) -> Dict[str, Tensor]:
+    """render_core's differentiable part (models/neus_hint_model.py:475-651) given the sample positions and hints.
+
+    weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b; col_w, col_b: lists of 5).
+    visibilities [R,1] / specular_cue [R,n_rough]: per-ray hint values (no gradient, as in the reference)."""
+    R, S = z_vals.shape
+    dev, dt = z_vals.device, z_vals.dtype
+    dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), sample_dist, device=dev, dtype=dt)], -1)
+    mid_z = z_vals + dists * 0.5
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., None]).reshape(-1, 3)
+    dirs = rays_d[:, None, :].expand(R, S, 3).reshape(-1, 3)
+    pls = rays_pl[:, None, :].expand(R, S, 3).reshape(-1, 3)
+    head = {"sdf_w": weights["sdf_w_head"], "sdf_b": weights["sdf_b_head"], "feat_w": weights["feat_w"], "feat_b": weights["feat_b"]}
+
+    out = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, pts)
+    feat = out[:, 1:]
+    # get_alpha re-evaluates the SDF and differentiates it w.r.t. the points (:335-336)
+    with torch.enable_grad():
+        x = pts if pts.requires_grad else pts.detach().requires_grad_(True)
+        sdf = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, x)[:, :1]
+        grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
+    true_cos = (dirs * grad).sum(-1, keepdim=True)
+    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
+    half = iter_cos * dists.reshape(-1, 1) * 0.5
+    prev_cdf = torch.sigmoid((sdf - half) * inv_s)
+    next_cdf = torch.sigmoid((sdf + half) * inv_s)
+    alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1).reshape(R, S)
+    trans = torch.cumprod(torch.cat([torch.ones((R, 1), device=dev, dtype=dt), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = alpha * trans
+    wsum = w.sum(-1, keepdim=True)
+
+    n_hat = F.normalize(grad, dim=-1, p=2)
+    parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
+    if visibilities is not None:
+        parts.append(_fourier(visibilities[:, None, :].expand(R, S, 1).reshape(-1, 1), refl_freq))
+    if specular_cue is not None:
+        nr = specular_cue.shape[-1]
+        parts.append(_fourier(specular_cue[:, None, :].expand(R, S, nr).reshape(-1, nr), refl_freq))
+    hcol = torch.cat(parts, dim=-1)
+    n_col = len(weights["col_w"])
+    for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
+        hcol = F.linear(hcol, cw, cb)
+        if l < n_col - 1:
+            hcol = torch.relu(hcol)
+    color = torch.sigmoid(hcol).reshape(R, S, 3)
+    rgb = (color * w[..., None]).sum(1)
+    if background_rgb is not None:
+        rgb = rgb + background_rgb * (1.0 - wsum)
+    return {"rgb": rgb, "weights": w, "analytic_normals": grad.reshape(R, S, 3),
+            "normalized_analytic_normals": n_hat.reshape(R, S, 3), "sampled_color": color}

@@ -27,6 +27,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import autograd_fine
 from .config import (DepthComputationType, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig, SDFNetConfig)
 
 
@@ -344,6 +345,12 @@ class NeuSHintRenderer(nn.Module):
         Ss = r.n_shadow_samples + r.n_shadow_importance_samples
         f32 = dict(dtype=torch.float32, device=device)
 
+        # Gradients requested?  (training, or camera registration at eval time, pipelines/base_pipeline.py:71-91)
+        ray_fields = (rays_o, ray_bundle.directions, ray_bundle.pl_positions, ray_bundle.nears, ray_bundle.fars)
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                  or any(t.requires_grad for t in ray_fields))
+        want_z = return_extras or needs_grad
+
         def prep(t):
             return t.detach().to(**f32).contiguous()
         o, d, pl = prep(rays_o), prep(ray_bundle.directions), prep(ray_bundle.pl_positions)
@@ -368,7 +375,7 @@ class NeuSHintRenderer(nn.Module):
             visibilities=torch.empty(R, 1, **f32) if r.shadow_hint else None,
             specular_cue=torch.empty(R, S, len(r.specular_roughness), **f32) if r.specular_hint else None,
             inv_s=torch.empty(1, **f32),
-            z_vals=torch.empty(R, S, **f32) if return_extras else None,
+            z_vals=torch.empty(R, S, **f32) if want_z else None,
             z_shadow=torch.zeros(R, Ss, **f32) if (return_extras and r.shadow_hint) else None,
             sampled_color=torch.empty(R, S, 3, **f32) if return_extras else None)
         c_rays = _lib.NrhRays(o.data_ptr(), d.data_ptr(), pl.data_ptr(), near.data_ptr(), far.data_ptr())
@@ -387,6 +394,14 @@ class NeuSHintRenderer(nn.Module):
 
         inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6).to(device)
         s_val = (1.0 / inv_s).reshape(1, 1).expand(R, S)
+        if needs_grad and R > 0:
+            # interim autograd backend (nrhints_b200/autograd_fine.py): the no_grad parts of the reference ran in the
+            # CUDA kernels above; the differentiable fine pass is re-expressed with torch ops on the same device
+            fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32)
+            out["rgb"], out["weights"] = fine["rgb"], fine["weights"]
+            out["analytic_normals"], out["normalized_normals"] = fine["analytic_normals"], fine["normalized_analytic_normals"]
+            if out["sampled_color"] is not None:
+                out["sampled_color"] = fine["sampled_color"]
         return RenderOutput(
             rgb=out["rgb"], depth=out["depth"], weights=out["weights"], s_val=s_val,
             inside_sphere=out["inside_sphere"], relax_inside_sphere=out["inside_sphere"],      # reference quirk (:746)
@@ -394,6 +409,32 @@ class NeuSHintRenderer(nn.Module):
             visibilities=out["visibilities"] if self.has_shadow_hint else None,
             specular_cue=out["specular_cue"] if self.has_specular_hint else None,
             z_vals=out["z_vals"], z_shadow=out["z_shadow"], sampled_color=out["sampled_color"])
+
+    def _autograd_weights(self) -> Dict[str, object]:
+        sn, cn = self.sdf_network, self.color_network
+        return {
+            "sdf_w": [getattr(sn, f"lin{l}").effective_weight() for l in range(8)],
+            "sdf_b": [getattr(sn, f"lin{l}").bias for l in range(8)],
+            "sdf_w_head": sn.out_sdf.effective_weight(), "sdf_b_head": sn.out_sdf.bias,
+            "feat_w": sn.out_feat.effective_weight(), "feat_b": sn.out_feat.bias,
+            "col_w": [getattr(cn, f"lin{l}").effective_weight() for l in range(5)],
+            "col_b": [getattr(cn, f"lin{l}").bias for l in range(5)],
+        }
+
+    def _differentiable_fine(self, ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32):
+        r = self.config.renderer
+        rays_o, rays_d, rays_pl, nears, fars = (t.to(**f32) for t in ray_fields)
+        n = r.n_samples
+        z_coarse = nears + (fars - nears) * torch.linspace(0.0, 1.0, n, **f32)[None, :]
+        if jit_p is not None:
+            z_coarse = z_coarse + (jit_p - 0.5) * 2.0 / n
+        z = autograd_fine.attach_coarse_gradient(out["z_vals"], z_coarse)
+        vis = out["visibilities"] if r.shadow_hint else None
+        spec = out["specular_cue"][:, 0, :] if r.specular_hint else None
+        bg = background_rgb.to(**f32) if background_rgb is not None else None
+        normalized = getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value
+        return autograd_fine.render_fine(self._autograd_weights(), rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
+                                         float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy

@@ -135,9 +135,10 @@ def _softplus100(x: Tensor) -> Tensor:
 
 
 def _softplus100_grad(x: Tensor) -> Tensor:
-    """d softplus(beta=100)/dx = z/(z+1), z = exp(100 x); 1 beyond the linear threshold."""
-    z = torch.exp(x * 100.0)
-    return torch.where(x * 100.0 > 20.0, torch.ones_like(x), z / (z + 1.0))
+    """d softplus(beta=100)/dx = z/(z+1), z = exp(100 x), i.e. sigmoid(100 x); 1 beyond the linear threshold.
+    Written with sigmoid so that autograd THROUGH this expression (second-order terms of the training loss) stays
+    finite: exp(100 x) overflows for x > 0.887 and would poison the where() with inf/inf."""
+    return torch.where(x * 100.0 > 20.0, torch.ones_like(x), torch.sigmoid(x * 100.0))
 
 
 def sdf_mlp(W: Dict[str, Tensor], pts: Tensor, cfg: OracleConfig, want_feat=False, want_grad=False):

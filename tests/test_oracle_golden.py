@@ -64,3 +64,32 @@ def test_oracle_edge_cases():
     assert out["weights"][1].sum() < 1e-2          # passes far outside
     assert torch.allclose(out["rgb"][1], torch.ones(3), atol=2e-2)
     assert torch.isfinite(out["rgb"]).all() and torch.isfinite(out["analytic_normals"]).all()
+
+
+def test_oracle_autograd_gradients_match_reference_fixture():
+    """Gradients of the training loss w.r.t. all 46 parameter tensors: oracle autograd (through its explicit reverse
+    sweep, i.e. including the second-order terms) vs the reference's own loss.backward(), committed as a fixture."""
+    from oracle import nrh_oracle as orc
+    fx = np.load(T.GOLDEN_DIR / "train_16x128_grads.npz")
+    case = T.CASES["train_16x128"]
+    cfg = T.make_config(case)
+    sd = {k: v.clone().requires_grad_(True) for k, v in T.make_state(case["weights"], cfg).items()}
+    rays, bg = T.case_inputs(case)
+    jp, js = T.case_jitters(case, cfg)
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    out = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"], rays["fars"],
+                             is_training=True, background_rgb=bg, cos_anneal=0.5, jitter_primary=jp, jitter_shadow=js)
+    loss = orc.training_loss(out, torch.tensor(fx["gt"]))
+    assert abs(float(loss) - float(fx["loss"])) < 2e-5
+    keys = sorted(sd)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [sd[k] for k in keys])))
+    n = 0
+    for k in keys:
+        want = float(fx["norm::" + k])
+        got = float(grads[k].norm())
+        assert abs(got - want) <= 2e-3 * max(want, 1e-6) + 1e-7, (k, got, want)
+        if "full::" + k in fx.files:
+            g = torch.tensor(fx["full::" + k])
+            assert (grads[k] - g).abs().max() <= 3e-3 * g.abs().max().clamp_min(1e-7) + 1e-8, k
+        n += 1
+    assert n == 46
