@@ -48,6 +48,11 @@ extern "C" {
 #define NRH_MLP_FP32_SIMT 1      /* fp32 FFMA register-tiled fused MLP (always-correct path)   */
 #define NRH_MLP_TCGEN05 2        /* tcgen05 tensor-core fused MLP, fp16 hi/lo split operands   */
 
+/* depth / hit-point estimators (models/neus_hint_model.py:528-538) */
+#define NRH_DEPTH_ALPHA_BLEND 0  /* sum_j mid_z_j w_j (default)                                 */
+#define NRH_DEPTH_MAX_WEIGHT 1   /* mid_z of the sample with the largest weight                 */
+#define NRH_DEPTH_SPHERE_TRACE 2 /* hit point supplied by the caller from nrh_sphere_trace      */
+
 /* Knobs of NeuSRendererConfig (models/neus_hint_model.py:133-174) the path honours. */
 typedef struct NrhConfig {
     int32_t n_samples;            /* coarse samples per primary ray (64)                      */
@@ -62,6 +67,7 @@ typedef struct NrhConfig {
     float shadow_ray_offset;      /* 1e-2                                                     */
     int32_t normalized_normals;   /* 1: NormalizedAnalytic feeds the reflectance net, 0: Analytic */
     int32_t mlp_impl;             /* NRH_MLP_*                                                */
+    int32_t depth_type;           /* NRH_DEPTH_* (DepthComputationType, models/neus_hint_model.py:113-121) */
 } NrhConfig;
 
 /* Effective (weight-norm already applied) weights, torch layout W[out][in], b[out]. */
@@ -83,6 +89,8 @@ typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-2
     const float* pl_positions;    /* [R,3] */
     const float* nears;           /* [R,1] */
     const float* fars;            /* [R,1] */
+    const float* hit_points;      /* [R,3] nullable: required when depth_type == NRH_DEPTH_SPHERE_TRACE */
+    const float* hit_depths;      /* [R,1] nullable: required when depth_type == NRH_DEPTH_SPHERE_TRACE */
 } NrhRays;
 
 typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance */
@@ -128,6 +136,15 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
  * sdf [N] (required), grad [N,3] (nullable), feat [N,256] (nullable). */
 int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N,
                   float* sdf, float* grad, float* feat, void* workspace, size_t workspace_bytes, void* stream);
+
+/* sphere_trace (models/neus_hint_model.py:359-371): p <- p + sdf(p) d from the ray origin until |sdf| < threshold or
+ * depth > far_limit, at most max_iterations times.  Converged points are fixed points of the update, so the result does
+ * not depend on when the loop stops; like the reference (`converged.all()` is a host sync there) this call checks for
+ * completion on the host every `check_every` iterations and therefore SYNCHRONISES the stream (the only entry point
+ * that does).  Outputs: hit_points [R,3], hit_depths [R,1].  Workspace: nrh_query_workspace_bytes(cfg, R) + 32*R bytes. */
+int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
+                     int max_iterations, float threshold, float far_limit, int check_every,
+                     float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
 int nrh_last_launch_count(void);

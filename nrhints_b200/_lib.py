@@ -19,6 +19,7 @@ _HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh
 
 NRH_MAX_ROUGHNESS = 4
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
+DEPTH_TYPES = {"alpha_blending": 0, "maximum_point": 1, "sphere_tracing": 2}
 MLP_IMPLS = {"auto": NRH_MLP_AUTO, "fp32": NRH_MLP_FP32_SIMT, "tcgen05": NRH_MLP_TCGEN05}
 
 
@@ -28,7 +29,7 @@ class NrhConfig(C.Structure):
         ("n_shadow_samples", C.c_int32), ("n_shadow_importance", C.c_int32),
         ("shadow_hint", C.c_int32), ("specular_hint", C.c_int32), ("n_roughness", C.c_int32),
         ("roughness", C.c_float * NRH_MAX_ROUGHNESS), ("shadow_ray_offset", C.c_float),
-        ("normalized_normals", C.c_int32), ("mlp_impl", C.c_int32),
+        ("normalized_normals", C.c_int32), ("mlp_impl", C.c_int32), ("depth_type", C.c_int32),
     ]
 
 
@@ -43,7 +44,7 @@ class NrhRawWeights(C.Structure):
 
 
 class NrhRays(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("origins", "directions", "pl_positions", "nears", "fars")]
+    _fields_ = [(n, C.c_void_p) for n in ("origins", "directions", "pl_positions", "nears", "fars", "hit_points", "hit_depths")]
 
 
 class NrhOutputs(C.Structure):
@@ -65,6 +66,8 @@ EXPORTS = {
                                      C.POINTER(NrhOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_sdf_query": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_sphere_trace": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

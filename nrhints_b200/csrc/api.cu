@@ -226,6 +226,7 @@ int nrh_check_config(const NrhConfig* c) {
         if (c->n_shadow_importance % 4) { set_error("n_shadow_importance must be a multiple of 4 (get_visibility uses 4 steps)"); return NRH_ERR_UNSUPPORTED; }
     }
     if (c->specular_hint && (c->n_roughness < 1 || c->n_roughness > NRH_MAX_ROUGHNESS)) { set_error("n_roughness must be in [1,%d]", NRH_MAX_ROUGHNESS); return NRH_ERR_UNSUPPORTED; }
+    if (c->depth_type < NRH_DEPTH_ALPHA_BLEND || c->depth_type > NRH_DEPTH_SPHERE_TRACE) { set_error("unknown depth_type %d", c->depth_type); return NRH_ERR_INVALID; }
     if (c->mlp_impl < NRH_MLP_AUTO || c->mlp_impl > NRH_MLP_TCGEN05) { set_error("unknown mlp_impl %d", c->mlp_impl); return NRH_ERR_INVALID; }
     if (c->mlp_impl == NRH_MLP_TCGEN05 && !tc_available()) { set_error("tcgen05 engine not built"); return NRH_ERR_UNSUPPORTED; }
     return NRH_OK;
@@ -301,6 +302,41 @@ int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, in
                    reinterpret_cast<float*>(workspace), workspace_bytes, sms, (cudaStream_t)stream);
 }
 
+int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
+                     int max_iterations, float threshold, float far_limit, int check_every,
+                     float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = nrh_check_config(cfg); if (rc) return rc;
+    if (!packed || !origins || !directions || !hit_points || !hit_depths || !workspace || R < 0) { set_error("null argument"); return NRH_ERR_INVALID; }
+    if (R == 0) return NRH_OK;
+    int sms; if ((rc = device_sms(&sms))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mlp_bytes = nrh_query_workspace_bytes(cfg, R);
+    if (workspace_bytes < mlp_bytes + 32 * (size_t)R) { set_error("workspace too small"); return NRH_ERR_WORKSPACE; }
+    char* base = reinterpret_cast<char*>(workspace);
+    float* scratch = reinterpret_cast<float*>(base);
+    float* sdf = reinterpret_cast<float*>(base + mlp_bytes);                  // [R]
+    int* moving = reinterpret_cast<int*>(base + mlp_bytes + 4 * (size_t)R + 16);
+    const PackedLayout L = make_layout(*cfg);
+    NRH_CUDA_CHECK(cudaMemcpyAsync(hit_points, origins, sizeof(float) * 3 * R, cudaMemcpyDeviceToDevice, st));
+    NRH_CUDA_CHECK(cudaMemsetAsync(hit_depths, 0, sizeof(float) * R, st));
+    if (check_every < 1) check_every = 1;
+    for (int it = 0; it < max_iterations; ++it) {
+        const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iterations);
+        if (it % check_every == 0) NRH_CUDA_CHECK(cudaMemsetAsync(moving, 0, sizeof(int), st));
+        Strided3 P{hit_points, hit_points + 1, hit_points + 2, 3};
+        if ((rc = run_sdf(*cfg, packed, L, P, R, sdf, nullptr, nullptr, nullptr, 1, nullptr, scratch, mlp_bytes, sms, st))) return rc;
+        if ((rc = launch_sphere_step(R, directions, sdf, hit_points, hit_depths, threshold, far_limit, moving, st))) return rc;
+        if (check) {
+            int h = 0;
+            NRH_CUDA_CHECK(cudaMemcpyAsync(&h, moving, sizeof(int), cudaMemcpyDeviceToHost, st));
+            NRH_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (h == 0) break;                     // nothing moved during the last `check_every` updates: every ray converged
+        }
+    }
+    return NRH_OK;
+}
+
 int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* rays, int64_t R,
                        const float* bg_rgb, const float* jitter_primary, const float* jitter_shadow,
                        float cos_anneal, int warmup, const NrhOutputs* out,
@@ -313,6 +349,9 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     if (cfg->shadow_hint && !out->visibilities) { set_error("visibilities output required with shadow_hint"); return NRH_ERR_INVALID; }
     if (cfg->specular_hint && !out->specular_cue) { set_error("specular_cue output required with specular_hint"); return NRH_ERR_INVALID; }
     if (R < 0) { set_error("negative ray count"); return NRH_ERR_INVALID; }
+    if (cfg->depth_type == NRH_DEPTH_SPHERE_TRACE && (!rays->hit_points || !rays->hit_depths)) {
+        set_error("depth_type == sphere tracing needs hit_points / hit_depths from nrh_sphere_trace"); return NRH_ERR_INVALID;
+    }
     if (R == 0) return NRH_OK;
     int sms; if ((rc = device_sms(&sms))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -335,7 +374,8 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
                       w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
     const bool do_shadow = cfg->shadow_hint && !warmup;
     if ((rc = launch_composite_primary(R, w.prim, cur, S, sample_dist, inv_s, cos_anneal, w.fine, w.rs, rays->pl_positions,
-                                       do_shadow, w.shad, ns, cfg->shadow_ray_offset, jitter_shadow, st))) return rc;
+                                       do_shadow, w.shad, ns, cfg->shadow_ray_offset, jitter_shadow,
+                                       cfg->depth_type, rays->hit_points, rays->hit_depths, st))) return rc;
     // ---- shadow march -------------------------------------------------------------------------------------
     int scur = 0;
     if (do_shadow) {

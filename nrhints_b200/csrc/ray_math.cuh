@@ -199,6 +199,7 @@ NRH_HD float neus_alpha(float sdf, float gx, float gy, float gz, const float d[3
 
 struct PrimaryComposite {
     float wsum, depth, nsum[3];
+    float max_w, max_mid;          // largest weight and its section mid-point (first maximum, like torch.argmax)
 };
 
 // weights, inside mask, normals, depth (render_core :508-533, :583-587).
@@ -207,6 +208,7 @@ NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], in
                                           CSoA sdf, CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal,
                                           SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz) {
     PrimaryComposite r; r.wsum = 0.f; r.depth = 0.f; r.nsum[0] = r.nsum[1] = r.nsum[2] = 0.f;
+    r.max_w = -1.f; r.max_mid = 0.f;
     float T = 1.0f;
     for (int j = 0; j < S; ++j) {
         float dist, mid; section(z, j, S, last_dist, dist, mid);
@@ -220,6 +222,7 @@ NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], in
         const float gn = fmaxf(norm3(g0, g1, g2), 1e-12f);       // F.normalize eps
         const float n0 = g0 / gn, n1 = g1 / gn, n2 = g2 / gn;
         nx[j] = n0; ny[j] = n1; nz[j] = n2;
+        if (w > r.max_w) { r.max_w = w; r.max_mid = mid; }
         r.wsum += w; r.depth += mid * w;
         r.nsum[0] += n0 * w; r.nsum[1] += n1 * w; r.nsum[2] += n2 * w;
     }

@@ -105,7 +105,8 @@ __global__ void k_sections_only(int64_t R, MarchState m, int cur, int S, float l
 __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, float last_dist,
                                     const float* __restrict__ inv_s_ptr, float cos_anneal, FineBuffers f,
                                     RayState rs, const float* __restrict__ pl, bool do_shadow, MarchState sh,
-                                    int n_shadow, float shadow_offset, const float* __restrict__ jitter_shadow) {
+                                    int n_shadow, float shadow_offset, const float* __restrict__ jitter_shadow,
+                                    int depth_type, const float* __restrict__ hit_pts, const float* __restrict__ hit_depth) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= R) return;
     float o[3], d[3];
@@ -114,9 +115,16 @@ __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, flo
     PrimaryComposite pc = composite_primary(o, d, S, CSoA{m.z[cur] + r, R}, last_dist, CSoA{f.sdf + r, R},
                                             CSoA{f.gx + r, R}, CSoA{f.gy + r, R}, CSoA{f.gz + r, R}, inv_s, cos_anneal,
                                             SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R});
-    rs.depth[r] = pc.depth; rs.wsum[r] = pc.wsum;
     float hit[3], hn[3];
-    for (int c = 0; c < 3; ++c) hit[c] = o[c] + d[c] * pc.depth;
+    float depth = pc.depth;                                              // AlphaBlend (:530-533)
+    if (depth_type == NRH_DEPTH_MAX_WEIGHT) depth = pc.max_mid;           // MaximalWeightPoint (:534-538)
+    if (depth_type == NRH_DEPTH_SPHERE_TRACE) {                           // SphereTracing (:528-529), traced by the caller
+        depth = hit_depth[r];
+        for (int c = 0; c < 3; ++c) hit[c] = hit_pts[r * 3 + c];
+    } else {
+        for (int c = 0; c < 3; ++c) hit[c] = o[c] + d[c] * depth;
+    }
+    rs.depth[r] = depth; rs.wsum[r] = pc.wsum;
     normalize3(pc.nsum, hn);
     for (int c = 0; c < 3; ++c) { rs.hit[c][r] = hit[c]; rs.hitn[c][r] = hn[c]; }
     if (do_shadow) {
@@ -208,6 +216,20 @@ __global__ void k_to_ray_major(TransposeArgs a, int64_t R, int S, float* __restr
     }
 }
 
+// one sphere-tracing update (models/neus_hint_model.py:365-368); counts the rays that are still moving
+__global__ void k_sphere_step(int64_t R, const float* __restrict__ dirs, const float* __restrict__ sdf, float* __restrict__ pts,
+                              float* __restrict__ depth, float threshold, float far_limit, int* __restrict__ moving) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float s = sdf[r], dep = depth[r];
+    const bool converged = (fabsf(s) < threshold) || (dep > far_limit);
+    if (!converged) {
+        for (int c = 0; c < 3; ++c) pts[r * 3 + c] = pts[r * 3 + c] + s * dirs[r * 3 + c];
+        depth[r] = dep + s;
+        atomicAdd(moving, 1);
+    }
+}
+
 inline int blocks_for(int64_t R) { return (int)((R + TPB - 1) / TPB); }
 
 }  // namespace
@@ -235,9 +257,17 @@ int launch_sections_only(int64_t R, const MarchState& m, int cur, int S, float l
 
 int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, float last_dist, const float* inv_s,
                              float cos_anneal, const FineBuffers& f, const RayState& rs, const float* pl, bool do_shadow,
-                             const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow, cudaStream_t st) {
+                             const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow,
+                             int depth_type, const float* hit_pts, const float* hit_depth, cudaStream_t st) {
     k_composite_primary<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, last_dist, inv_s, cos_anneal, f, rs, pl, do_shadow, sh,
-                                                       n_shadow, shadow_offset, jitter_shadow);
+                                                       n_shadow, shadow_offset, jitter_shadow, depth_type, hit_pts, hit_depth);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pts, float* depth, float threshold, float far_limit,
+                       int* moving, cudaStream_t st) {
+    k_sphere_step<<<blocks_for(R), TPB, 0, st>>>(R, dirs, sdf, pts, depth, threshold, far_limit, moving);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

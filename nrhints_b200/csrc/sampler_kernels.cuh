@@ -29,7 +29,10 @@ int launch_importance_step(int64_t R, const MarchState& m, int cur, int k_old, i
 int launch_sections_only(int64_t R, const MarchState& m, int cur, int S, float last_dist_const, const float* last_dist_ray, cudaStream_t st);
 int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, float last_dist, const float* inv_s,
                              float cos_anneal, const FineBuffers& f, const RayState& rs, const float* pl, bool do_shadow,
-                             const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow, cudaStream_t st);
+                             const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow,
+                             int depth_type, const float* hit_pts, const float* hit_depth, cudaStream_t st);
+int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pts, float* depth, float threshold, float far_limit,
+                       int* moving, cudaStream_t st);
 int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int cur, int S_shadow, const float* inv_s,
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,

@@ -216,8 +216,6 @@ class NeuSHintRenderer(nn.Module):
         r = config.renderer
         if r.use_outside_nerf:
             raise NotImplementedError("use_outside_nerf=True is outside the B200 hot path (SURVEY.md section 8a row A15)")
-        if getattr(r.depth_type, "value", r.depth_type) != DepthComputationType.AlphaBlend.value:
-            raise NotImplementedError("only depth_type=AlphaBlend is implemented (reference default)")
         if r.n_shadow_importance_clip != -1:
             raise NotImplementedError("n_shadow_importance_clip != -1 is not implemented (reference default is -1)")
         if r.shadow_hint_gradient or r.specular_hint_gradient:
@@ -260,6 +258,7 @@ class NeuSHintRenderer(nn.Module):
         c.shadow_ray_offset = float(r.shadow_ray_offset)
         c.normalized_normals = int(getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value)
         c.mlp_impl = _lib.MLP_IMPLS[self.mlp_impl]
+        c.depth_type = _lib.DEPTH_TYPES[getattr(r.depth_type, "value", r.depth_type)]
         return c
 
     def _weight_tensors(self) -> List[torch.Tensor]:
@@ -331,6 +330,28 @@ class NeuSHintRenderer(nn.Module):
         self.last_launch_count = lib.nrh_last_launch_count()
         return sdf, grad, feat
 
+    @torch.no_grad()
+    def sphere_trace(self, rays_o: torch.Tensor, rays_d: torch.Tensor, num_iterations: int, convergence_threshold: float,
+                     far: float, check_every: int = 16):
+        """NeuSHintRenderer.sphere_trace (models/neus_hint_model.py:359-371) on the SDF kernel -> (points [R,3], depths [R,1])."""
+        lib = _lib.load()
+        device = rays_o.device
+        packed = self._ensure_packed(device)
+        cfg = self._c_config()
+        o = rays_o.detach().to(torch.float32).contiguous()
+        d = rays_d.detach().to(torch.float32).contiguous()
+        R = o.shape[0]
+        pts = torch.empty(R, 3, dtype=torch.float32, device=device)
+        dep = torch.empty(R, 1, dtype=torch.float32, device=device)
+        wsb = lib.nrh_query_workspace_bytes(C.byref(cfg), R) + 32 * R
+        ws = self._ensure_workspace(wsb, device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.nrh_sphere_trace(C.byref(cfg), packed.data_ptr(), o.data_ptr(), d.data_ptr(), R, int(num_iterations),
+                                            float(convergence_threshold), float(far), int(check_every), pts.data_ptr(),
+                                            dep.data_ptr(), ws.data_ptr(), ws.numel(), stream), "nrh_sphere_trace")
+        return pts, dep
+
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
                 global_step: int = 0, return_extras: bool = False) -> RenderOutput:
@@ -378,7 +399,12 @@ class NeuSHintRenderer(nn.Module):
             z_vals=torch.empty(R, S, **f32) if want_z else None,
             z_shadow=torch.zeros(R, Ss, **f32) if (return_extras and r.shadow_hint) else None,
             sampled_color=torch.empty(R, S, 3, **f32) if return_extras else None)
-        c_rays = _lib.NrhRays(o.data_ptr(), d.data_ptr(), pl.data_ptr(), near.data_ptr(), far.data_ptr())
+        hit_pts = hit_dep = None
+        if cfg.depth_type == _lib.DEPTH_TYPES["sphere_tracing"] and R > 0:
+            hit_pts, hit_dep = self.sphere_trace(o, d, 2000, 1e-4, 100.0)        # models/neus_hint_model.py:529
+        c_rays = _lib.NrhRays(o.data_ptr(), d.data_ptr(), pl.data_ptr(), near.data_ptr(), far.data_ptr(),
+                              hit_pts.data_ptr() if hit_pts is not None else None,
+                              hit_dep.data_ptr() if hit_dep is not None else None)
         c_out = _lib.NrhOutputs(**{k: (v.data_ptr() if v is not None else None) for k, v in out.items()})
         wsb = lib.nrh_workspace_bytes(C.byref(cfg), R)
         ws = self._ensure_workspace(wsb, device)

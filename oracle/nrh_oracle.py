@@ -57,6 +57,7 @@ class OracleConfig:
     shadow_ray_offset: float = 1e-2
     specular_roughness: List[float] = field(default_factory=lambda: [0.02, 0.05, 0.13, 0.34])
     normalized_normals: bool = True      # NormalComputationType.NormalizedAnalytic
+    depth_type: str = "alpha_blending"   # DepthComputationType value: alpha_blending | maximum_point | sphere_tracing
     # SDF network
     sdf_n_layers: int = 8
     sdf_hidden: int = 256
@@ -79,6 +80,7 @@ class OracleConfig:
             shadow_hint=r.shadow_hint, specular_hint=r.specular_hint,
             shadow_ray_offset=r.shadow_ray_offset, specular_roughness=list(r.specular_roughness),
             normalized_normals=(getattr(r.normal_type, "value", r.normal_type) == "normalized_analytic"),
+            depth_type=getattr(r.depth_type, "value", r.depth_type),
             sdf_n_layers=s.n_layers, sdf_hidden=s.d_hidden, sdf_skip_in=tuple(s.skip_in),
             sdf_multires=s.multi_res, sdf_scale=s.scale, sdf_feat=s.d_out_feat,
             refl_n_layers=c.n_layers, refl_multires=c.multi_res, refl_squeeze_out=c.squeeze_out)
@@ -304,6 +306,20 @@ def shadow_visibility(W, cfg: OracleConfig, lights, targets, cos_anneal=1.0, jit
     return taus[..., -1:], z
 
 
+def sphere_trace(W, cfg: OracleConfig, o, d, num_iterations=2000, threshold=1e-4, far=100.0):
+    """sphere_trace (models/neus_hint_model.py:359-371): march p += sdf * d until |sdf| < threshold or depth > far."""
+    pts = o
+    depths = torch.zeros((o.shape[0], 1), dtype=o.dtype)
+    for _ in range(num_iterations):
+        sdf = sdf_mlp(W, pts, cfg)["sdf"]
+        converged = (torch.abs(sdf) < threshold) | (depths > far)
+        pts = torch.where(converged, pts, pts + sdf * d)
+        depths = torch.where(converged, depths, depths + sdf)
+        if converged.all():
+            break
+    return pts, depths
+
+
 def specular_cue(cfg: OracleConfig, hit_normal, lights, hits, d):
     """4-lobe Cook-Torrance cue (models/neus_hint_model.py:588-616)."""
     l = F.normalize(lights - hits, dim=-1, p=2)
@@ -345,8 +361,14 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
     weights = alpha * _excl_cumprod(1.0 - alpha + 1e-7)
     wsum = weights.sum(-1, keepdim=True)
     with torch.no_grad():
-        depth = (mid_z[..., None] * weights[..., None]).sum(1)
-        hits = o + d * depth
+        if cfg.depth_type == "sphere_tracing":                      # :528-529
+            hits, depth = sphere_trace(W, cfg, o, d, 2000, 1e-4, 100.0)
+        elif cfg.depth_type == "maximum_point":                     # :534-538
+            depth = torch.gather(mid_z, 1, torch.argmax(weights, dim=1, keepdim=True))
+            hits = o + d * depth
+        else:                                                       # :530-533
+            depth = (mid_z[..., None] * weights[..., None]).sum(1)
+            hits = o + d * depth
 
     vis_map = None
     vis = None

@@ -33,6 +33,8 @@ def ref_config(M, case):
     kw = dict(case.get("renderer", {}))
     if "normal_type" in kw:
         kw["normal_type"] = M.NormalComputationType(kw["normal_type"].value)
+    if "depth_type" in kw:
+        kw["depth_type"] = M.DepthComputationType(kw["depth_type"].value)
     return M.NeuSModelConfig(renderer=M.NeuSRendererConfig(**kw))
 
 

@@ -37,6 +37,13 @@ CASES = {
                                                  n_shadow_importance_samples=32, specular_hint=False,
                                                  normal_type=nb.NormalComputationType.Analytic),
                              weights="sharp", ray_seed=9, bg=0.0),
+    # non-default depth estimators (DepthComputationType, models/neus_hint_model.py:113-121, :528-538)
+    "maxpoint_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, n_shadow_samples=32,
+                                               n_shadow_importance_samples=32, depth_type=nb.DepthComputationType.MaximalWeightPoint),
+                           weights="init", ray_seed=21),
+    "sphere_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, n_shadow_samples=32,
+                                             n_shadow_importance_samples=32, depth_type=nb.DepthComputationType.SphereTracing),
+                         weights="init", ray_seed=22),
 }
 
 

@@ -44,9 +44,9 @@ def test_version_and_config_validation_without_gpu():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 2 * 4
+    assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 3 * 4
     assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1) * 8
-    assert C.sizeof(_lib.NrhRays) == 5 * 8
+    assert C.sizeof(_lib.NrhRays) == 7 * 8
     assert C.sizeof(_lib.NrhOutputs) == 12 * 8
     fields = re.findall(r"float\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
     assert fields == [n for n, _ in _lib.NrhOutputs._fields_]
@@ -69,7 +69,7 @@ def test_unsupported_configs_raise():
     with pytest.raises(NotImplementedError):
         nb.NeuSHintRenderer(nb.NeuSModelConfig(sdf_network=nb.SDFNetConfig(d_hidden=128)))
     with pytest.raises(NotImplementedError):
-        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(depth_type=nb.DepthComputationType.SphereTracing)))
+        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_shadow_importance_clip=4)))
 
 
 def test_state_dict_layout_matches_reference_inventory():
