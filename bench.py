@@ -201,6 +201,9 @@ def main():
     bg = torch.ones(1, 3, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                       # > 126 MB L2
 
+    torch.set_grad_enabled(False)          # config #2 is the inference render (the reference evaluates under @torch.no_grad(),
+                                           # pipelines/base_pipeline.py:93); with grad enabled the module would add its autograd backend
+
     def step():
         return model(dev_rays, is_training=False, background_rgb=bg)
 

@@ -87,36 +87,41 @@ NRH_HD void coarse_z(float near, float far, int n, bool has_jitter, float jitter
 }
 
 // ------------------------------------------------------------------------------------------
-// one importance step: (z sorted[k], sdf[k]) -> n_new new z (non-decreasing).
-// wbuf: scratch for k-1 interval weights (+1e-5).
+// one importance step: (z sorted[k], sdf[k]) -> n_new new z (non-decreasing), in two parts so that the expensive,
+// independent per-interval part can be spread over many threads:
+//   interval_alpha(j)     : NeuS alpha of interval [z_j, z_{j+1}] with the fixed sharpness inv_s (up_sample :276-310)
+//   sample_from_alphas()  : weights = alpha * exclusive cumprod, pdf/cdf, inverse-CDF at linspace(0,1,n) (:311-314, :21-65)
+// upsample_new_z() = both, sequentially (host harness / reference order of operations).
 // ------------------------------------------------------------------------------------------
-NRH_HD void upsample_new_z(const float o[3], const float d[3], int k, CSoA z, CSoA sdf,
-                           float inv_s, int n_new, SoA wbuf, SoA z_new) {
-    // pass 1: interval weights
-    float zj = z[0], sj = sdf[0];
-    float rj = norm3(o[0] + d[0] * zj, o[1] + d[1] * zj, o[2] + d[2] * zj);
-    float prev_cos = 0.0f, T = 1.0f, wsum = 0.0f;
+NRH_HD float interval_alpha(const float o[3], const float d[3], int j, CSoA z, CSoA sdf, float inv_s) {
+    const float zj = z[j], zn = z[j + 1], sj = sdf[j], sn = sdf[j + 1];
+    const float rj = norm3(o[0] + d[0] * zj, o[1] + d[1] * zj, o[2] + d[2] * zj);
+    const float rn = norm3(o[0] + d[0] * zn, o[1] + d[1] * zn, o[2] + d[2] * zn);
+    const float inside = (rj < 1.0f || rn < 1.0f) ? 1.0f : 0.0f;
+    const float mid_sdf = (sj + sn) * 0.5f;
+    const float dist = zn - zj;
+    const float cos_raw = (sn - sj) / (dist + 1e-5f);
+    float prev_cos = 0.0f;
+    if (j > 0) { const float zp = z[j - 1]; prev_cos = (sj - sdf[j - 1]) / (zj - zp + 1e-5f); }
+    float c = fminf(prev_cos, cos_raw);
+    c = fminf(fmaxf(c, -1e3f), 0.0f) * inside;
+    const float half = c * dist * 0.5f;
+    const float prev_cdf = sigmoidf_((mid_sdf - half) * inv_s);
+    const float next_cdf = sigmoidf_((mid_sdf + half) * inv_s);
+    return (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
+}
+
+// wbuf holds the k-1 alphas on entry and is overwritten with the weights (+1e-5).
+NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
+    float T = 1.0f, wsum = 0.0f;
     for (int j = 0; j + 1 < k; ++j) {
-        const float zn = z[j + 1], sn = sdf[j + 1];
-        const float rn = norm3(o[0] + d[0] * zn, o[1] + d[1] * zn, o[2] + d[2] * zn);
-        const float inside = (rj < 1.0f || rn < 1.0f) ? 1.0f : 0.0f;
-        const float mid_sdf = (sj + sn) * 0.5f;
-        const float dist = zn - zj;
-        const float cos_raw = (sn - sj) / (dist + 1e-5f);
-        float c = fminf(prev_cos, cos_raw);
-        c = fminf(fmaxf(c, -1e3f), 0.0f) * inside;
-        prev_cos = cos_raw;
-        const float half = c * dist * 0.5f;
-        const float prev_cdf = sigmoidf_((mid_sdf - half) * inv_s);
-        const float next_cdf = sigmoidf_((mid_sdf + half) * inv_s);
-        const float alpha = (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
+        const float alpha = wbuf[j];
         const float w = alpha * T + 1e-5f;
         T = T * (1.0f - alpha + 1e-7f);
         wbuf[j] = w;
         wsum += w;
-        zj = zn; sj = sn; rj = rn;
     }
-    // pass 2: inverse CDF at u = linspace(0,1,n_new); cdf has k entries, cdf[0]=0.
+    // inverse CDF at u = linspace(0,1,n_new); cdf has k entries, cdf[0]=0.
     int m = 0;                 // running searchsorted(right=True) result
     float c_m = 0.0f;          // cdf[m]
     float c_below = 0.0f;      // cdf[m-1]
@@ -136,6 +141,12 @@ NRH_HD void upsample_new_z(const float o[3], const float d[3], int k, CSoA z, CS
         const float zb = z[below], za = z[above];
         z_new[t] = zb + tt * (za - zb);
     }
+}
+
+NRH_HD void upsample_new_z(const float o[3], const float d[3], int k, CSoA z, CSoA sdf,
+                           float inv_s, int n_new, SoA wbuf, SoA z_new) {
+    for (int j = 0; j + 1 < k; ++j) wbuf[j] = interval_alpha(o, d, j, z, sdf, inv_s);
+    sample_from_alphas(k, z, n_new, wbuf, z_new);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -38,51 +38,96 @@ __global__ void k_coarse_primary(NrhRays rays, int64_t R, int n, const float* __
 // The per-ray algorithm is a chain of short dependent steps over <= 128 samples, so each thread first stages its
 // ray's arrays in shared memory (coalesced, fully overlapped global loads), runs ray_math.cuh on them, and writes
 // the results back: the dependent chain then pays shared-memory latency instead of L2 latency per step.
-constexpr int IS_TPB = 64;
+constexpr int IS_RAYS = 64;                                 // rays per CTA
+constexpr int IS_THREADS = 512;                             // 8 threads per ray for the parallel phases
 constexpr int IS_NEW = 32;                                   // max samples drawn per step
 constexpr int IS_ROWS = 3 * NRH_MAX_SAMPLES + 2 * IS_NEW;   // z[128] s[128] w[128] z_new[32] s_new[32]
-constexpr size_t IS_SMEM = (size_t)IS_ROWS * IS_TPB * sizeof(float);
+constexpr size_t IS_SMEM = (size_t)IS_ROWS * IS_RAYS * sizeof(float);
 
-__global__ void __launch_bounds__(IS_TPB)
+// A CTA owns 64 rays.  Data movement and the per-interval alphas (two precise sigmoids + three divisions each, the bulk
+// of the arithmetic) are spread over all 512 threads; the short sequential parts (merge, prefix products, cdf walk)
+// run one thread per ray on the shared-memory copies.  Arithmetic and its order are exactly those of ray_math.cuh.
+__global__ void __launch_bounds__(IS_THREADS)
 k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool merge_first,
                   float inv_s, bool last, float last_dist_const, const float* last_dist_ray) {
     extern __shared__ float sm[];
-    const int t = threadIdx.x;
-    const int64_t r = blockIdx.x * (int64_t)IS_TPB + t;
-    if (r >= R) return;
-    float* sz = sm + t;                                      // element j at sz[j * IS_TPB]
-    float* ss = sz + NRH_MAX_SAMPLES * IS_TPB;
-    float* sw = ss + NRH_MAX_SAMPLES * IS_TPB;
-    float* szn = sw + NRH_MAX_SAMPLES * IS_TPB;
-    float* ssn = szn + IS_NEW * IS_TPB;
-    float o[3], d[3];
-    for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
-    for (int j = 0; j < k_old; ++j) { sz[j * IS_TPB] = m.z[cur][(int64_t)j * R + r]; ss[j * IS_TPB] = m.s[cur][(int64_t)j * R + r]; }
+    const int tid = threadIdx.x;
+    const int64_t r0 = blockIdx.x * (int64_t)IS_RAYS;
+    const int nr = (int)((R - r0) < IS_RAYS ? (R - r0) : IS_RAYS);          // rays of this CTA
+    float* sz = sm;                                                       // element j of local ray t at [j * IS_RAYS + t]
+    float* ss = sz + NRH_MAX_SAMPLES * IS_RAYS;
+    float* sw = ss + NRH_MAX_SAMPLES * IS_RAYS;
+    float* szn = sw + NRH_MAX_SAMPLES * IS_RAYS;
+    float* ssn = szn + IS_NEW * IS_RAYS;
+    // ---- phase 0: stage (coalesced: consecutive threads = consecutive rays) ----
+    for (int idx = tid; idx < k_old * IS_RAYS; idx += IS_THREADS) {
+        const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+        if (t < nr) { sz[idx] = m.z[cur][(int64_t)j * R + r0 + t]; ss[idx] = m.s[cur][(int64_t)j * R + r0 + t]; }
+    }
+    if (merge_first)
+        for (int idx = tid; idx < n_new * IS_RAYS; idx += IS_THREADS) {
+            const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+            if (t < nr) { szn[idx] = m.znew[(int64_t)j * R + r0 + t]; ssn[idx] = m.snew[(int64_t)j * R + r0 + t]; }
+        }
+    __syncthreads();
     int k = k_old;
+    // ---- phase 1: merge the samples drawn by the previous step (one thread per ray) ----
     if (merge_first) {
-        for (int j = 0; j < n_new; ++j) { szn[j * IS_TPB] = m.znew[(int64_t)j * R + r]; ssn[j * IS_TPB] = m.snew[(int64_t)j * R + r]; }
-        merge_sorted_backward(k_old, SoA{sz, IS_TPB}, SoA{ss, IS_TPB}, n_new, CSoA{szn, IS_TPB}, CSoA{ssn, IS_TPB}, true);
+        if (tid < nr)
+            merge_sorted_backward(k_old, SoA{sz + tid, IS_RAYS}, SoA{ss + tid, IS_RAYS}, n_new, CSoA{szn + tid, IS_RAYS},
+                                  CSoA{ssn + tid, IS_RAYS}, true);
         k = k_old + n_new;
         cur ^= 1;
+        __syncthreads();
         if (!last)
-            for (int j = 0; j < k; ++j) { m.z[cur][(int64_t)j * R + r] = sz[j * IS_TPB]; m.s[cur][(int64_t)j * R + r] = ss[j * IS_TPB]; }
+            for (int idx = tid; idx < k * IS_RAYS; idx += IS_THREADS) {
+                const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+                if (t < nr) { m.z[cur][(int64_t)j * R + r0 + t] = sz[idx]; m.s[cur][(int64_t)j * R + r0 + t] = ss[idx]; }
+            }
     }
-    upsample_new_z(o, d, k, CSoA{sz, IS_TPB}, CSoA{ss, IS_TPB}, inv_s, n_new, SoA{sw, IS_TPB}, SoA{szn, IS_TPB});
+    // ---- phase 2: per-interval alphas, all threads ----
+    for (int idx = tid; idx < (k - 1) * IS_RAYS; idx += IS_THREADS) {
+        const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+        if (t < nr) {
+            const int64_t r = r0 + t;
+            const float o[3] = {m.o[0][r], m.o[1][r], m.o[2][r]}, d[3] = {m.d[0][r], m.d[1][r], m.d[2][r]};
+            sw[idx] = interval_alpha(o, d, j, CSoA{sz + t, IS_RAYS}, CSoA{ss + t, IS_RAYS}, inv_s);
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: weights, cdf, inverse-CDF samples (one thread per ray); last step: final merge ----
+    if (tid < nr) {
+        sample_from_alphas(k, CSoA{sz + tid, IS_RAYS}, n_new, SoA{sw + tid, IS_RAYS}, SoA{szn + tid, IS_RAYS});
+        if (last)
+            merge_sorted_backward(k, SoA{sz + tid, IS_RAYS}, SoA{ss + tid, IS_RAYS}, n_new, CSoA{szn + tid, IS_RAYS},
+                                  CSoA{nullptr, 0}, false);
+    }
+    __syncthreads();
+    // ---- phase 4: write back (all threads) ----
     if (!last) {
-        for (int j = 0; j < n_new; ++j) {
-            const float zv = szn[j * IS_TPB];
-            m.znew[(int64_t)j * R + r] = zv;
-            write_points(o, d, zv, (int64_t)j * R + r, m.px, m.py, m.pz);
+        for (int idx = tid; idx < n_new * IS_RAYS; idx += IS_THREADS) {
+            const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+            if (t < nr) {
+                const int64_t r = r0 + t;
+                const float o[3] = {m.o[0][r], m.o[1][r], m.o[2][r]}, d[3] = {m.d[0][r], m.d[1][r], m.d[2][r]};
+                const float zv = szn[idx];
+                m.znew[(int64_t)j * R + r] = zv;
+                write_points(o, d, zv, (int64_t)j * R + r, m.px, m.py, m.pz);
+            }
         }
     } else {
-        merge_sorted_backward(k, SoA{sz, IS_TPB}, SoA{ss, IS_TPB}, n_new, CSoA{szn, IS_TPB}, CSoA{nullptr, 0}, false);
         cur ^= 1;
         const int S = k + n_new;
-        const float last_dist = last_dist_ray ? last_dist_ray[r] : last_dist_const;
-        for (int j = 0; j < S; ++j) {
-            float dist, mid; section(CSoA{sz, IS_TPB}, j, S, last_dist, dist, mid);
-            m.z[cur][(int64_t)j * R + r] = sz[j * IS_TPB];
-            write_points(o, d, mid, (int64_t)j * R + r, m.px, m.py, m.pz);
+        for (int idx = tid; idx < S * IS_RAYS; idx += IS_THREADS) {
+            const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+            if (t < nr) {
+                const int64_t r = r0 + t;
+                const float o[3] = {m.o[0][r], m.o[1][r], m.o[2][r]}, d[3] = {m.d[0][r], m.d[1][r], m.d[2][r]};
+                const float last_dist = last_dist_ray ? last_dist_ray[r] : last_dist_const;
+                float dist, mid; section(CSoA{sz + t, IS_RAYS}, j, S, last_dist, dist, mid);
+                m.z[cur][(int64_t)j * R + r] = sz[idx];
+                write_points(o, d, mid, (int64_t)j * R + r, m.px, m.py, m.pz);
+            }
         }
     }
 }
@@ -244,7 +289,7 @@ int launch_importance_step(int64_t R, const MarchState& m, int cur, int k_old, i
                            bool last, float last_dist_const, const float* last_dist_ray, cudaStream_t st) {
     if (n_new > IS_NEW) { set_error("importance step draws at most %d samples per step", IS_NEW); return NRH_ERR_UNSUPPORTED; }
     NRH_CUDA_CHECK(cudaFuncSetAttribute(k_importance_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_SMEM));
-    k_importance_step<<<(unsigned)((R + IS_TPB - 1) / IS_TPB), IS_TPB, IS_SMEM, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
+    k_importance_step<<<(unsigned)((R + IS_RAYS - 1) / IS_RAYS), IS_THREADS, IS_SMEM, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -1,6 +1,7 @@
 """Developer check of the tcgen05 engine against the fp32 engine and the oracle (run on the GPU box)."""
 import sys, time
 import torch
+torch.set_grad_enabled(False)
 sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
 import nrh_testlib as T
 import nrhints_b200 as nb

@@ -28,8 +28,9 @@ def run_cuda(case, impl):
     if training:
         torch.manual_seed(case["rng_seed"])
         torch.cuda.manual_seed(case["rng_seed"])
-    out = m(bundle, is_training=training, background_rgb=bg.cuda(), global_step=case.get("global_step", 0),
-            return_extras=True)
+    with torch.no_grad():                 # pure CUDA path (with grad enabled the autograd backend would take over the fine pass)
+        out = m(bundle, is_training=training, background_rgb=bg.cuda(), global_step=case.get("global_step", 0),
+                return_extras=True)
     torch.cuda.synchronize()
     assert m.last_launch_count > 10
     return out, m
@@ -74,8 +75,9 @@ def test_training_mode_forward(impl):
     jp = torch.rand([R, 1], device="cuda")
     js = torch.rand([R, cfg.renderer.n_shadow_samples], device="cuda")
     torch.manual_seed(7)
-    out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"],
-            return_extras=True)
+    with torch.no_grad():
+        out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"],
+                return_extras=True)
     ocfg = orc.OracleConfig.from_model_config(cfg)
     with torch.no_grad():
         want = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
@@ -91,7 +93,8 @@ def test_warmup_zeroes_hints(impl):
     m = nb.NeuSHintRenderer(cfg, mlp_impl=impl)
     m.load_state_dict(T.make_state("init", cfg)); m.cuda()
     rays, bg = T.case_inputs(case)
-    out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=10)
+    with torch.no_grad():
+        out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=10)
     assert float(out.visibilities.abs().max()) == 0.0 and float(out.specular_cue.abs().max()) == 0.0
     assert torch.isfinite(out.rgb).all()
 
@@ -123,6 +126,7 @@ def test_sdf_query_matches_oracle(kind, impl):
           "grad err vs fp64:", float((grad[:, 0].cpu().double() - w64["grad"]).abs().max()))
 
 
+@torch.no_grad()
 def test_edge_cases():
     """R = 1, R not a multiple of anything, rays that miss the sphere, R = 0."""
     cfg = nb.NeuSModelConfig()
@@ -136,6 +140,7 @@ def test_edge_cases():
     assert torch.equal(full.relax_inside_sphere, full.inside_sphere)     # reference quirk Q1
 
 
+@torch.no_grad()
 def test_full_size_properties():
     """BASELINE.json config #2 size (4096 x 128): size-independent properties."""
     cfg = nb.NeuSModelConfig()
