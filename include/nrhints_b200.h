@@ -96,16 +96,22 @@ typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-2
 typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance */
     float* rgb;                   /* [R,3]   */
     float* depth;                 /* [R,1]   */
-    float* weights;               /* [R,S]   */
-    float* inside_sphere;         /* [R,S]   (relax_inside_sphere aliases it, reference quirk :746) */
-    float* analytic_normals;      /* [R,S,3] */
-    float* normalized_normals;    /* [R,S,3] */
-    float* visibilities;          /* [R,1]   nullable when !shadow_hint                        */
-    float* specular_cue;          /* [R,S,n_roughness] nullable when !specular_hint            */
+    float* weights;               /* [R,S]   nullable (see the per-ray maps below)                          */
+    float* inside_sphere;         /* [R,S]   nullable; relax_inside_sphere aliases it (reference quirk :746)  */
+    float* analytic_normals;      /* [R,S,3] nullable */
+    float* normalized_normals;    /* [R,S,3] nullable */
+    float* visibilities;          /* [R,1]   nullable                                          */
+    float* specular_cue;          /* [R,S,n_roughness] nullable                                */
     float* inv_s;                 /* [1]     exp(10*variance) clipped to [1e-6,1e6]; s_val = 1/inv_s broadcast by the caller */
     float* z_vals;                /* [R,S]   nullable; final primary sample positions (debug / backward) */
     float* z_shadow;              /* [R,Ss]  nullable; final shadow-ray sample positions                   */
     float* sampled_color;         /* [R,S,3] nullable; per-sample reflectance output                       */
+    /* per-ray maps for full-image evaluation (pipelines/base_pipeline.py:126-148 computes them on the host from the
+     * per-sample tensors): with these, the per-sample fields above (weights ... specular_cue) may all be NULL and only
+     * 60 B/ray instead of 7 KB/ray leave the device. */
+    float* normal_map;            /* [R,3] nullable: sum_j analytic_normal_j * w_j * inside_j               */
+    float* normalized_normal_map; /* [R,3] nullable: sum_j normalized_normal_j * w_j * inside_j             */
+    float* specular_cue_ray;      /* [R,n_roughness] nullable: the per-ray cue (before broadcast)           */
 } NrhOutputs;
 
 int nrh_version(void);

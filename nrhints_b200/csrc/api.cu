@@ -93,6 +93,7 @@ struct Workspace {
     float* feat;                 // [S*R][256]
     float* ssdf; float* sgx; float* sgy; float* sgz;   // shadow fine pass outputs
     float* rayfeat;              // [RAYFEAT][R]
+    float* aux_img;              // [R/128] operand images of the per-ray reflectance inputs (streamed tcgen05 path)
     float* cr; float* cg; float* cb;
     float* mlp_scratch; size_t mlp_scratch_bytes;
     size_t total_bytes;
@@ -131,6 +132,7 @@ Workspace carve(const NrhConfig& cfg, int64_t R, char* base, int num_sms) {
     w.feat = take((size_t)S * R * 256);
     w.ssdf = take((size_t)Ss * R); w.sgx = take((size_t)Ss * R); w.sgy = take((size_t)Ss * R); w.sgz = take((size_t)Ss * R);
     w.rayfeat = take((size_t)RAYFEAT * R);
+    w.aux_img = take((size_t)((R + 127) / 128) * (TC_TILE_AUX_BYTES / sizeof(float)));
     w.cr = take((size_t)S * R); w.cg = take((size_t)S * R); w.cb = take((size_t)S * R);
     size_t sb = sdf_mlp_simt_scratch_bytes(num_sms);
     size_t tb = tc_scratch_bytes(num_sms);
@@ -163,17 +165,17 @@ int resolve_impl(const NrhConfig& cfg) {
 // engine dispatch ------------------------------------------------------------------------------------
 int run_sdf(const NrhConfig& cfg, const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf,
             float* gx, float* gy, float* gz, int64_t gstride, float* feat, float* scratch, size_t scratch_bytes,
-            int num_sms, cudaStream_t st) {
+            int num_sms, cudaStream_t st, bool feat_as_image = false) {
     if (resolve_impl(cfg) == NRH_MLP_TCGEN05)
-        return sdf_mlp_tc(packed, L, pts, N, sdf, gx, gy, gz, gstride, feat, scratch, scratch_bytes, num_sms, st);
+        return sdf_mlp_tc(packed, L, pts, N, sdf, gx, gy, gz, gstride, feat, feat_as_image, scratch, scratch_bytes, num_sms, st);
     return sdf_mlp_simt(reinterpret_cast<const float*>(packed), L, pts, N, sdf, gx, gy, gz, gstride, feat, scratch,
                         scratch_bytes, num_sms, st);
 }
 int run_color(const NrhConfig& cfg, const void* packed, const PackedLayout& L, Strided3 pts, Strided3 nrm, const float* feat,
-              const float* rayfeat, int64_t R, int64_t N, float* cr, float* cg, float* cb, float* scratch, size_t scratch_bytes,
-              int num_sms, cudaStream_t st) {
+              const float* rayfeat, const void* aux_img, int64_t R, int64_t N, float* cr, float* cg, float* cb, float* scratch,
+              size_t scratch_bytes, int num_sms, cudaStream_t st) {
     if (resolve_impl(cfg) == NRH_MLP_TCGEN05)
-        return color_mlp_tc(packed, L, pts, nrm, feat, rayfeat, R, N, cr, cg, cb, scratch, scratch_bytes, num_sms, st);
+        return color_mlp_tc(packed, L, pts, nrm, feat, rayfeat, aux_img, R, N, cr, cg, cb, scratch, scratch_bytes, num_sms, st);
     return color_mlp_simt(reinterpret_cast<const float*>(packed), L, pts, nrm, feat, rayfeat, R, N, cr, cg, cb, num_sms, st);
 }
 
@@ -345,9 +347,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     int rc = nrh_check_config(cfg); if (rc) return rc;
     if (!packed || !rays || !out || !workspace) { set_error("null argument"); return NRH_ERR_INVALID; }
     if (!rays->origins || !rays->directions || !rays->pl_positions || !rays->nears || !rays->fars) { set_error("null ray field"); return NRH_ERR_INVALID; }
-    if (!out->rgb || !out->depth || !out->weights || !out->inside_sphere || !out->analytic_normals || !out->normalized_normals) { set_error("null output field"); return NRH_ERR_INVALID; }
-    if (cfg->shadow_hint && !out->visibilities) { set_error("visibilities output required with shadow_hint"); return NRH_ERR_INVALID; }
-    if (cfg->specular_hint && !out->specular_cue) { set_error("specular_cue output required with specular_hint"); return NRH_ERR_INVALID; }
+    if (!out->rgb || !out->depth) { set_error("null output field (rgb / depth are mandatory)"); return NRH_ERR_INVALID; }
     if (R < 0) { set_error("negative ray count"); return NRH_ERR_INVALID; }
     if (cfg->depth_type == NRH_DEPTH_SPHERE_TRACE && (!rays->hit_points || !rays->hit_depths)) {
         set_error("depth_type == sphere tracing needs hit_points / hit_depths from nrh_sphere_trace"); return NRH_ERR_INVALID;
@@ -370,8 +370,11 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     if ((rc = run_hierarchical(*cfg, packed, L, R, w.prim, n, cfg->n_importance, cfg->up_sample_steps, sample_dist, nullptr,
                                w.mlp_scratch, w.mlp_scratch_bytes, sms, st, &cur))) return rc;
     Strided3 P{w.prim.px, w.prim.py, w.prim.pz, 1};
+    // tcgen05 engine with whole 128-ray blocks: features and per-ray inputs travel as fp16 operand images that the
+    // reflectance kernel streams straight into its A operand (no conversion pass, half the feature bytes)
+    const bool streamed = resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
     if ((rc = run_sdf(*cfg, packed, L, P, (int64_t)S * R, w.fine.sdf, w.fine.gx, w.fine.gy, w.fine.gz, 1, w.feat,
-                      w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
+                      w.mlp_scratch, w.mlp_scratch_bytes, sms, st, streamed))) return rc;
     const bool do_shadow = cfg->shadow_hint && !warmup;
     if ((rc = launch_composite_primary(R, w.prim, cur, S, sample_dist, inv_s, cos_anneal, w.fine, w.rs, rays->pl_positions,
                                        do_shadow, w.shad, ns, cfg->shadow_ray_offset, jitter_shadow,
@@ -386,24 +389,26 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
                           w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
     }
     if ((rc = launch_shade_prep(R, *cfg, w.shad, scur, Ss, inv_s, cos_anneal, w.ssdf, w.sgx, w.sgy, w.sgz, w.rs,
-                                rays->pl_positions, rays->directions, warmup, do_shadow, w.rayfeat, st))) return rc;
+                                rays->pl_positions, rays->directions, warmup, do_shadow, w.rayfeat,
+                                streamed ? reinterpret_cast<unsigned char*>(w.aux_img) : nullptr, st))) return rc;
     // ---- reflectance + composite ----------------------------------------------------------------------------
     Strided3 Nrm = cfg->normalized_normals ? Strided3{w.fine.nx, w.fine.ny, w.fine.nz, 1} : Strided3{w.fine.gx, w.fine.gy, w.fine.gz, 1};
-    if ((rc = run_color(*cfg, packed, L, P, Nrm, w.feat, w.rayfeat, R, (int64_t)S * R, w.cr, w.cg, w.cb,
+    if ((rc = run_color(*cfg, packed, L, P, Nrm, w.feat, w.rayfeat, streamed ? w.aux_img : nullptr, R, (int64_t)S * R, w.cr, w.cg, w.cb,
                         w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
     if ((rc = launch_final_rgb(R, S, w.fine, w.rs, w.cr, w.cg, w.cb, bg_rgb, out->rgb, out->depth,
-                               cfg->shadow_hint ? out->visibilities : nullptr, st))) return rc;
+                               cfg->shadow_hint ? out->visibilities : nullptr, out->normal_map, out->normalized_normal_map,
+                               cfg->specular_hint ? out->specular_cue_ray : nullptr, cfg->n_roughness, st))) return rc;
     // ---- ray-major RenderOutput fields -------------------------------------------------------------------------
     {
         const float* s1[4] = {w.fine.w, nullptr, nullptr, nullptr};
-        if ((rc = launch_to_ray_major(s1, 1, false, R, S, out->weights, st))) return rc;
+        if (out->weights && (rc = launch_to_ray_major(s1, 1, false, R, S, out->weights, st))) return rc;
         const float* s2[4] = {w.fine.inside, nullptr, nullptr, nullptr};
-        if ((rc = launch_to_ray_major(s2, 1, false, R, S, out->inside_sphere, st))) return rc;
+        if (out->inside_sphere && (rc = launch_to_ray_major(s2, 1, false, R, S, out->inside_sphere, st))) return rc;
         const float* s3[4] = {w.fine.gx, w.fine.gy, w.fine.gz, nullptr};
-        if ((rc = launch_to_ray_major(s3, 3, false, R, S, out->analytic_normals, st))) return rc;
+        if (out->analytic_normals && (rc = launch_to_ray_major(s3, 3, false, R, S, out->analytic_normals, st))) return rc;
         const float* s4[4] = {w.fine.nx, w.fine.ny, w.fine.nz, nullptr};
-        if ((rc = launch_to_ray_major(s4, 3, false, R, S, out->normalized_normals, st))) return rc;
-        if (cfg->specular_hint) {
+        if (out->normalized_normals && (rc = launch_to_ray_major(s4, 3, false, R, S, out->normalized_normals, st))) return rc;
+        if (cfg->specular_hint && out->specular_cue) {
             const float* s5[4] = {w.rs.spec[0], w.rs.spec[1], w.rs.spec[2], w.rs.spec[3]};
             if ((rc = launch_to_ray_major(s5, cfg->n_roughness, true, R, S, out->specular_cue, st))) return rc;
         }

@@ -40,8 +40,8 @@ constexpr uint32_t STAGE = 32768;
 constexpr uint32_t IMG = 32768;            // one [256 x 64] fp16 weight image
 constexpr uint32_t IMG_SMALL = 8192;       // one [64 x 64] fp16 weight image (reverse layer 0)
 constexpr uint32_t A_CHUNK = 16384;        // one [128 x 64] fp16 activation chunk
-constexpr float W_SCALE = 64.0f;           // weights are stored * 2^6
-constexpr float ACT_SCALE = 16.0f;         // forward activations are stored * 2^4
+constexpr float W_SCALE = TC_W_SCALE;
+constexpr float ACT_SCALE = TC_ACT_SCALE;
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
 constexpr float INV_SQRT2 = 0.70710678f;
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
@@ -73,7 +73,7 @@ __host__ __device__ inline TcLayout tc_layout() {
 // ---- shared memory map ---------------------------------------------------------------------------------------
 constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * STAGE;    // sdf kernel
 constexpr uint32_t SMC_A = 0, SMC_B = 6 * A_CHUNK, SMC_MISC = SMC_B + NSTAGES * STAGE;                 // color kernel
-constexpr uint32_t SM_MISC_BYTES = 2048, SMC_MISC_BYTES = 8192;
+constexpr uint32_t SM_MISC_BYTES = 2048, SMC_MISC_BYTES = 12288;
 constexpr size_t SDF_SMEM = SM_MISC + SM_MISC_BYTES + 1024;     // + slack for manual 1024-B alignment
 constexpr size_t COL_SMEM = SMC_MISC + SMC_MISC_BYTES + 1024;
 
@@ -189,6 +189,7 @@ struct SdfTcParams {
     const uint8_t* tc;                 // tensor-core section (operand images)
     const float* bias16;               // [8][256] biases * ACT_SCALE (tensor-core section)
     const float* head_w; const float* head_b; const float* feat_b;
+    int feat_image;                    // 1: features leave as fp16 operand images (TC_TILE_FEAT_BYTES per tile)
     int ncta;                          // CTAs per cluster sharing one weight stream (1 or 2, multicast loads)
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
@@ -333,7 +334,7 @@ __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, in
 // feature head epilogue: write feat (fp32, row-major) and, with GRAD, seed the reverse sweep
 template <bool GRAD, class WaitAcc>
 __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
-                                         float* __restrict__ feat_row, bool valid) {
+                                         float* __restrict__ feat_row, uint8_t* __restrict__ feat_tile_img, bool valid) {
     float vA[16], bA[16], vB[16], bB[16];
     const int cq = E.gq * 16;
     ldg16(bias + cq, bA);
@@ -351,7 +352,13 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
-        if (valid) {
+        if (feat_tile_img) {                           // fp16 operand image of this tile (every row is written)
+            float t16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = valid ? v[i] * ACT_SCALE : 0.f;
+            store_half8(feat_tile_img + c * A_CHUNK, E.off0, t16);
+            store_half8(feat_tile_img + c * A_CHUNK, E.off1, t16 + 8);
+        } else if (valid) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 *reinterpret_cast<float4*>(feat_row + cq + c * 64 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -630,7 +637,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) * (1.0f / ACT_SCALE) + __ldg(P.head_b)) / SDF_SCALE;
             }
             if (FEAT) {
-                epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + (valid ? p : 0) * 256, valid);
+                epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + (valid ? p : 0) * 256,
+                               P.feat_image ? reinterpret_cast<uint8_t*>(feat_out) + (size_t)tile * TC_TILE_FEAT_BYTES : nullptr, valid);
                 tc_fence_before();
             }
             if (GRAD) {
@@ -692,6 +700,9 @@ struct ColTcParams {
     const uint8_t* tc;
     const float* bias16;               // [4][256] hidden-layer biases * ACT_SCALE
     const float* w4t; const float* b4;
+    const uint8_t* feat_img;           // streamed-input path: per-tile feature operand images (else nullptr)
+    const uint8_t* aux_img;            //                      per-ray-block operand images of the per-ray inputs
+    long long* tlog;                   // developer timeline (NRH_TC_TLOG)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -707,7 +718,11 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
     uint64_t* a_ready = bars + 2 * NSTAGES;   // [6]
     uint64_t* acc_full = a_ready + 6;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    uint64_t* in_full = acc_full + 4;         // streamed inputs of a tile have landed (TMA complete_tx)
+    uint64_t* a_free = acc_full + 5;          // the MMAs of the tile's last layer are done: A may be refilled
     float* part = reinterpret_cast<float*>(bars + 40);          // [3 channels][3 quarters][128]
+    float* w4s = part + 9 * TM;                                 // [256][4] output layer weights, [4] bias
+    const bool streamed = P.aux_img != nullptr;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TcLayout T = tc_layout();
@@ -716,8 +731,10 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
         for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 6; ++i) mbar_init(&a_ready[i], EPI_WARPS);
         for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
+        mbar_init(in_full, 1); mbar_init(a_free, 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < 1024 + 4; i += NTHREADS) w4s[i] = i < 1024 ? __ldg(P.w4t + i) : __ldg(P.b4 + (i - 1024));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -726,8 +743,16 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            uint32_t it = 0, ti = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+                if (streamed) {                    // the tile's A operand for layer 0 comes straight from HBM / L2
+                    mbar_wait(a_free, (ti & 1) ^ 1);
+                    mbar_arrive_expect_tx(in_full, 6 * A_CHUNK);
+                    const uint8_t* fsrc = P.feat_img + (size_t)tile * TC_TILE_FEAT_BYTES;
+                    const uint8_t* asrc = P.aux_img + (size_t)(((tile * TM) % R) / TM) * TC_TILE_AUX_BYTES;
+                    for (int c = 0; c < 4; ++c) bulk_g2s(A + c * A_CHUNK, fsrc + c * A_CHUNK, A_CHUNK, in_full);
+                    for (int c = 0; c < 2; ++c) bulk_g2s(A + (4 + c) * A_CHUNK, asrc + c * A_CHUNK, A_CHUNK, in_full);
+                }
                 for (int gi = 0; gi < 4; ++gi) {
                     const int nimg = gi == 0 ? 6 : 4;
                     for (int img = 0; img < nimg; ++img, ++it) {
@@ -737,6 +762,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                         bulk_g2s(Bst + s * STAGE, P.tc + T.col[gi] + (size_t)img * IMG, STAGE, &b_full[s]);
                     }
                 }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -747,8 +773,11 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 for (int gi = 0; gi < 4; ++gi, ++gc) {
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const int nch = gi == 0 ? 6 : 4;
+                    const bool lg = P.tlog && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x;
                     for (int c = 0; c < nch; ++c) {
+                        if (lg && c == 0) P.tlog[gi * 8 + 0] = clock64();
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
+                        if (lg && c == 0) P.tlog[gi * 8 + 1] = clock64();
                         a_par ^= (1u << c);
                         tc_fence_after();
                         const uint32_t al = a_lo0 + c * (A_CHUNK >> 4);
@@ -763,6 +792,8 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                         }
                     }
                     umma_commit(&acc_full[gc & 1]);
+                    if (gi == 3) umma_commit(a_free);
+                    if (lg) P.tlog[gi * 8 + 2] = clock64();
                 }
         }
     } else if (warp >= EPI_WARP0) {
@@ -771,10 +802,32 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t off0 = sw128_offset(r, gq * 16), off1 = sw128_offset(r, gq * 16 + 8);
         const uint32_t a_s = smem_u32(A);
-        uint32_t gc = 0;
+        uint32_t gc = 0, tcount = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p = tile * TM + r;
             const bool valid = p < N;
+            const bool elg = P.tlog && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x && warp == EPI_WARP0 + 2 && lane == 0;
+            if (elg) P.tlog[64] = clock64();
+            if (streamed) {
+                // features and per-ray inputs arrive as ready-made operand images; only the six per-point columns
+                // (position, normal) of chunk 4 are patched in
+                mbar_wait(in_full, tcount & 1);
+                ++tcount;
+                if (gq < 2) {
+                    const Strided3& src = gq == 0 ? pts : nrm;
+                    const int col = gq == 0 ? 0 : AUX_NORMAL;
+                    const float v3[3] = {src.x[p * src.stride], src.y[p * src.stride], src.z[p * src.stride]};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        *reinterpret_cast<__half*>(A + 4 * A_CHUNK + sw128_offset(r, col + i)) = __float2half_rn(v3[i] * ACT_SCALE);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
+                }
+            } else
             // ---- stage the inputs: features -> chunks 0..3, [pts | PE(view) | n | PE(light) | PE(vis) | PE(spec)] -> chunks 4,5 ----
             {
                 const float* frow = feat + p * 256 + gq * 64;
@@ -818,6 +871,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
                 }
             }
+            if (elg) P.tlog[65] = clock64();
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
             for (int gi = 0; gi < 4; ++gi, ++gc) {
@@ -826,6 +880,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 ldg16(bias16, bA);
                 ldg16(bias16 + 64, bB);
                 mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
+                if (elg) P.tlog[66 + gi * 2] = clock64();
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256 + gq * 16;
                 tmem_ld16(acc, vA);
@@ -838,7 +893,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     if (last) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float4 w = __ldg(reinterpret_cast<const float4*>(P.w4t + (c * 64 + gq * 16 + i) * 4));
+                            const float4 w = *reinterpret_cast<const float4*>(w4s + (c * 64 + gq * 16 + i) * 4);
                             d0 = fmaf(v[i], w.x, d0); d1 = fmaf(v[i], w.y, d1); d2 = fmaf(v[i], w.z, d2);
                         }
                     } else {
@@ -855,15 +910,16 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 step(vB, bB, vA, 1);
                 step(vA, bA, vB, 2);
                 step(vB, bB, vA, 3);
+                if (elg) P.tlog[67 + gi * 2] = clock64();
                 tc_fence_before();
             }
             d0 *= (1.0f / ACT_SCALE); d1 *= (1.0f / ACT_SCALE); d2 *= (1.0f / ACT_SCALE);
             if (gq > 0) { float* pp = part + (gq - 1) * TM + r; pp[0] = d0; pp[3 * TM] = d1; pp[6 * TM] = d2; }
             epi_bar_sync();
             if (gq == 0 && valid) {
-                const float s0 = ((d0 + part[r]) + (part[TM + r] + part[2 * TM + r])) + __ldg(P.b4 + 0);
-                const float s1 = ((d1 + part[3 * TM + r]) + (part[4 * TM + r] + part[5 * TM + r])) + __ldg(P.b4 + 1);
-                const float s2 = ((d2 + part[6 * TM + r]) + (part[7 * TM + r] + part[8 * TM + r])) + __ldg(P.b4 + 2);
+                const float s0 = ((d0 + part[r]) + (part[TM + r] + part[2 * TM + r])) + w4s[1024];
+                const float s1 = ((d1 + part[3 * TM + r]) + (part[4 * TM + r] + part[5 * TM + r])) + w4s[1025];
+                const float s2 = ((d2 + part[6 * TM + r]) + (part[7 * TM + r] + part[8 * TM + r])) + w4s[1026];
                 cr[p] = 1.0f / (1.0f + expf(-s0));
                 cg[p] = 1.0f / (1.0f + expf(-s1));
                 cb[p] = 1.0f / (1.0f + expf(-s2));
@@ -990,11 +1046,13 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
 }
 
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
-               float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat,
+               float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat, bool feat_as_image,
                float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
     if (N <= 0) return NRH_OK;
+    if (feat_as_image && (N % TM != 0 || !feat)) { set_error("feature images need N %% 128 == 0"); return NRH_ERR_INVALID; }
     const float* Pf = reinterpret_cast<const float*>(packed);
     SdfTcParams P;
+    P.feat_image = feat_as_image ? 1 : 0;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
@@ -1027,15 +1085,19 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
 }
 
 int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Strided3 normals,
-                 const float* feat, const float* rayfeat, int64_t R, int64_t N,
+                 const float* feat, const float* rayfeat, const void* aux_img, int64_t R, int64_t N,
                  float* cr, float* cg, float* cb, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
     (void)scratch; (void)scratch_bytes;
     if (N <= 0) return NRH_OK;
+    if (aux_img && (R % TM != 0 || N % TM != 0)) { set_error("streamed reflectance inputs need R %% 128 == 0"); return NRH_ERR_INVALID; }
     const float* Pf = reinterpret_cast<const float*>(packed);
     ColTcParams P;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().col_bias16);
+    { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) + 256 : nullptr; }
     P.w4t = Pf + L.col_w4t; P.b4 = Pf + L.col_b4;
+    P.aux_img = reinterpret_cast<const uint8_t*>(aux_img);
+    P.feat_img = aux_img ? reinterpret_cast<const uint8_t*>(feat) : nullptr;
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     NRH_CUDA_CHECK(cudaFuncSetAttribute(color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));

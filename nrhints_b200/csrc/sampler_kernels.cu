@@ -7,6 +7,9 @@
 #include "nrh_common.cuh"
 #include "ray_math.cuh"
 #include "sampler_kernels.cuh"
+#include "mlp_tc.cuh"
+#include "tc_primitives.cuh"
+#include <cuda_fp16.h>
 
 namespace nrh {
 namespace {
@@ -188,7 +191,7 @@ __global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, i
                              const float* __restrict__ inv_s_ptr, float cos_anneal, const float* __restrict__ ssdf,
                              const float* __restrict__ sgx, const float* __restrict__ sgy, const float* __restrict__ sgz,
                              RayState rs, const float* __restrict__ pl, const float* __restrict__ dirs, int warmup,
-                             bool shadow_marched, float* __restrict__ rayfeat) {
+                             bool shadow_marched, float* __restrict__ rayfeat, unsigned char* __restrict__ aux_img) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= R) return;
     float vis = 0.f;
@@ -216,20 +219,49 @@ __global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, i
     else for (int i = 0; i < 9; ++i) vis_dst[(int64_t)i * R] = 0.f;
     for (int i = 0; i < 36; ++i) spec_dst[(int64_t)i * R] = 0.f;
     if (cfg.specular_hint) fourier_encode(cue, cfg.n_roughness, COL_FREQ, spec_dst, R);
+    if (aux_img) {
+        // operand image row of this ray for the streamed reflectance kernel: 128 aux columns, fp16 x TC_ACT_SCALE, in the
+        // K-major SWIZZLE_128B layout of two [128 x 64] chunks; the per-point columns (position 0..2, normal 30..32)
+        // are left zero and patched in by that kernel
+        unsigned char* img = aux_img + (size_t)(r / 128) * TC_TILE_AUX_BYTES;
+        const unsigned row = (unsigned)(r % 128);
+        for (int k8 = 0; k8 < 128; k8 += 8) {
+            __align__(16) __half h[8];
+            for (int i = 0; i < 8; ++i) {
+                const int j = k8 + i;
+                float v = 0.f;
+                if (j >= AUX_VIEW && j < AUX_NORMAL) v = rayfeat[(int64_t)(j - AUX_VIEW) * R + r];
+                else if (j >= AUX_LIGHT && j < 105) v = rayfeat[(int64_t)(j - AUX_LIGHT + COL_PE3) * R + r];
+                h[i] = __float2half_rn(v * TC_ACT_SCALE);
+            }
+            *reinterpret_cast<uint4*>(img + (k8 >> 6) * 16384 + tc::sw128_offset(row, k8 & 63)) = *reinterpret_cast<const uint4*>(h);
+        }
+    }
 }
 
 // ---- rgb = sum_j w_j c_j + bg (1 - sum w) ---------------------------------------------------------------
 __global__ void k_final_rgb(int64_t R, int S, FineBuffers f, RayState rs, const float* __restrict__ cr,
                             const float* __restrict__ cg, const float* __restrict__ cb, const float* __restrict__ bg,
-                            float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ vis_out) {
+                            float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ vis_out,
+                            float* __restrict__ nmap, float* __restrict__ nnmap, float* __restrict__ spec_ray, int n_rough) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= R) return;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float m[3] = {0.f, 0.f, 0.f}, mn[3] = {0.f, 0.f, 0.f};
+    const bool maps = nmap != nullptr || nnmap != nullptr;
     for (int j = 0; j < S; ++j) {
         const int64_t i = (int64_t)j * R + r;
         const float w = f.w[i];
         a0 += cr[i] * w; a1 += cg[i] * w; a2 += cb[i] * w;
+        if (maps) {                                   // einsum('...ij,...i,...i->...j', normals, weights, inside_sphere)
+            const float wi = w * f.inside[i];
+            m[0] += f.gx[i] * wi; m[1] += f.gy[i] * wi; m[2] += f.gz[i] * wi;
+            mn[0] += f.nx[i] * wi; mn[1] += f.ny[i] * wi; mn[2] += f.nz[i] * wi;
+        }
     }
+    if (nmap) { nmap[r * 3 + 0] = m[0]; nmap[r * 3 + 1] = m[1]; nmap[r * 3 + 2] = m[2]; }
+    if (nnmap) { nnmap[r * 3 + 0] = mn[0]; nnmap[r * 3 + 1] = mn[1]; nnmap[r * 3 + 2] = mn[2]; }
+    if (spec_ray) for (int c = 0; c < n_rough; ++c) spec_ray[r * n_rough + c] = rs.spec[c][r];
     if (bg) {
         const float rest = 1.0f - rs.wsum[r];
         a0 += bg[0] * rest; a1 += bg[1] * rest; a2 += bg[2] * rest;
@@ -320,16 +352,17 @@ int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pt
 int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int cur, int S_shadow, const float* inv_s,
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,
-                      float* rayfeat, cudaStream_t st) {
+                      float* rayfeat, unsigned char* aux_img, cudaStream_t st) {
     k_shade_prep<<<blocks_for(R), TPB, 0, st>>>(R, cfg, sh, cur, S_shadow, inv_s, cos_anneal, ssdf, sgx, sgy, sgz, rs, pl, dirs,
-                                                warmup, shadow_marched, rayfeat);
+                                                warmup, shadow_marched, rayfeat, aux_img);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }
 
 int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, const float* cr, const float* cg,
-                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, cudaStream_t st) {
-    k_final_rgb<<<blocks_for(R), TPB, 0, st>>>(R, S, f, rs, cr, cg, cb, bg, rgb, depth, vis_out);
+                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
+                     float* spec_ray, int n_rough, cudaStream_t st) {
+    k_final_rgb<<<blocks_for(R), TPB, 0, st>>>(R, S, f, rs, cr, cg, cb, bg, rgb, depth, vis_out, nmap, nnmap, spec_ray, n_rough);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

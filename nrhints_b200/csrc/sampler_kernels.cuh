@@ -36,9 +36,10 @@ int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pt
 int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int cur, int S_shadow, const float* inv_s,
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,
-                      float* rayfeat, cudaStream_t st);
+                      float* rayfeat, unsigned char* aux_img, cudaStream_t st);
 int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, const float* cr, const float* cg,
-                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, cudaStream_t st);
+                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
+                     float* spec_ray, int n_rough, cudaStream_t st);
 int launch_to_ray_major(const float* const* src, int C, bool broadcast, int64_t R, int S, float* dst, cudaStream_t st);
 
 }  // namespace nrh

@@ -352,6 +352,52 @@ class NeuSHintRenderer(nn.Module):
                                             dep.data_ptr(), ws.data_ptr(), ws.numel(), stream), "nrh_sphere_trace")
         return pts, dep
 
+    # -- full-image evaluation ------------------------------------------------------------------
+    @torch.no_grad()
+    def render_maps(self, ray_bundle, background_rgb: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Per-ray maps of an evaluation render, reduced on the device: rgb [R,3], depth [R,1], shadow_map [R,1],
+        specular_hint [R,n_rough] and the weighted normal maps `einsum('...ij,...i,...i->...j', normals, weights, inside)`
+        that pipelines/base_pipeline.py:126-133 computes on the host from the per-sample tensors (before its camera
+        rotation).  Nothing per-sample is written or copied: 60 B/ray instead of 7 KB/ray leave the device."""
+        lib = _lib.load()
+        device = ray_bundle.origins.device
+        packed = self._ensure_packed(device)
+        cfg = self._c_config()
+        r = self.config.renderer
+        R = ray_bundle.origins.shape[0]
+        f32 = dict(dtype=torch.float32, device=device)
+
+        def prep(t):
+            return t.detach().to(**f32).contiguous()
+        o, d, pl = prep(ray_bundle.origins), prep(ray_bundle.directions), prep(ray_bundle.pl_positions)
+        near, far = prep(ray_bundle.nears), prep(ray_bundle.fars)
+        bg = prep(background_rgb).reshape(-1) if background_rgb is not None else None
+        maps = dict(rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, 1, **f32),
+                    analytic_normals=torch.empty(R, 3, **f32), normalized_analytic_normals=torch.empty(R, 3, **f32))
+        if r.shadow_hint:
+            maps["shadow_map"] = torch.empty(R, 1, **f32)
+        if r.specular_hint:
+            maps["specular_hint"] = torch.empty(R, len(r.specular_roughness), **f32)
+        hit_pts = hit_dep = None
+        if cfg.depth_type == _lib.DEPTH_TYPES["sphere_tracing"] and R > 0:
+            hit_pts, hit_dep = self.sphere_trace(o, d, 2000, 1e-4, 100.0)
+        c_rays = _lib.NrhRays(o.data_ptr(), d.data_ptr(), pl.data_ptr(), near.data_ptr(), far.data_ptr(),
+                              hit_pts.data_ptr() if hit_pts is not None else None, hit_dep.data_ptr() if hit_dep is not None else None)
+        c_out = _lib.NrhOutputs(rgb=maps["rgb"].data_ptr(), depth=maps["depth"].data_ptr(),
+                                visibilities=maps["shadow_map"].data_ptr() if r.shadow_hint else None,
+                                normal_map=maps["analytic_normals"].data_ptr(),
+                                normalized_normal_map=maps["normalized_analytic_normals"].data_ptr(),
+                                specular_cue_ray=maps["specular_hint"].data_ptr() if r.specular_hint else None)
+        ws = self._ensure_workspace(lib.nrh_workspace_bytes(C.byref(cfg), R), device)
+        if R > 0:
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(lib.nrh_render_forward(C.byref(cfg), packed.data_ptr(), C.byref(c_rays), R,
+                                                  bg.data_ptr() if bg is not None else None, None, None, 1.0, 0,
+                                                  C.byref(c_out), ws.data_ptr(), ws.numel(), stream), "nrh_render_forward")
+            self.last_launch_count = lib.nrh_last_launch_count()
+        return maps
+
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
                 global_step: int = 0, return_extras: bool = False) -> RenderOutput:

@@ -47,7 +47,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 3 * 4
     assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1) * 8
     assert C.sizeof(_lib.NrhRays) == 7 * 8
-    assert C.sizeof(_lib.NrhOutputs) == 12 * 8
+    assert C.sizeof(_lib.NrhOutputs) == 15 * 8
     fields = re.findall(r"float\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
     assert fields == [n for n, _ in _lib.NrhOutputs._fields_]
 

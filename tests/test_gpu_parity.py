@@ -217,3 +217,22 @@ def test_camera_gradients_flow():
     out.rgb.sum().backward()
     for k in ("origins", "directions", "pl_positions", "nears"):
         assert dev[k].grad is not None and torch.isfinite(dev[k].grad).all() and float(dev[k].grad.abs().max()) > 0, k
+
+
+@torch.no_grad()
+def test_render_maps_equal_host_reduction():
+    """render_maps (device-side reduction) == the einsum the reference pipeline applies to the per-sample tensors."""
+    case = T.CASES["cfg2_32x128"]
+    m, cfg, sd = build_module(case, "auto")
+    rays, bg = T.case_inputs(case)
+    b = nb.RayBundle(**rays).to("cuda")
+    full = m(b, background_rgb=bg.cuda())
+    maps = m.render_maps(b, background_rgb=bg.cuda())
+    assert torch.equal(maps["rgb"], full.rgb) and torch.equal(maps["depth"], full.depth)
+    assert torch.equal(maps["shadow_map"], full.visibilities)
+    assert torch.allclose(maps["specular_hint"], full.specular_cue[:, 0, :])
+    want = torch.einsum("...ij,...i,...i->...j", full.analytic_normals, full.weights, full.inside_sphere)
+    wantn = torch.einsum("...ij,...i,...i->...j", full.normalized_analytic_normals, full.weights, full.inside_sphere)
+    assert torch.allclose(maps["analytic_normals"], want, atol=2e-6)
+    assert torch.allclose(maps["normalized_analytic_normals"], wantn, atol=2e-6)
+    assert m.last_launch_count < 29
