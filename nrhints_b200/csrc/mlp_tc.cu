@@ -190,12 +190,13 @@ struct SdfTcParams {
     const float* bias16;               // [8][256] biases * ACT_SCALE (tensor-core section)
     const float* head_w; const float* head_b; const float* feat_b;
     int feat_image;                    // 1: features leave as fp16 operand images (TC_TILE_FEAT_BYTES per tile)
-    int ncta;                          // CTAs per cluster sharing one weight stream (1 or 2, multicast loads)
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
 };
 
-struct Gemm { uint32_t b_off; int nchunks; int ksteps; int n; uint32_t img_bytes; };
+// One gemm = `nsub` sub-chunks of 32 K-columns.  Every weight image serves exactly one sub-chunk: its 64 "K" columns are
+// [W_hi(k0 .. k0+31) | W_lo(k0 .. k0+31)], so K-steps 0,1 of the image are the hi part and 2,3 the lo part.
+struct Gemm { uint32_t b_off; int nsub; int n; uint32_t img_bytes; };
 
 template <bool GRAD, bool FEAT>
 __device__ __forceinline__ constexpr int num_gemms() { return SDF_LAYERS + (FEAT ? 1 : 0) + (GRAD ? SDF_LAYERS : 0); }
@@ -204,10 +205,10 @@ __device__ __forceinline__ constexpr int num_gemms() { return SDF_LAYERS + (FEAT
 template <bool GRAD, bool FEAT>
 __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
     Gemm g;
-    g.nchunks = 4; g.ksteps = 4; g.n = 256; g.img_bytes = IMG;
+    g.nsub = 8; g.n = 256; g.img_bytes = IMG;
     if (idx < SDF_LAYERS) {
         g.b_off = T.fwd[idx];
-        if (idx == 0) { g.nchunks = 1; g.ksteps = 3; }
+        if (idx == 0) g.nsub = 2;
         return g;
     }
     idx -= SDF_LAYERS;
@@ -218,29 +219,36 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
     return g;
 }
 
-// per-thread view of the epilogue: row r of the tile (== TMEM lane), column quarter gq of every 64-wide chunk
+// per-thread view of the epilogue: row r of the tile (== TMEM lane), 8-column group gq of every 32-wide sub-chunk.
+// The hand-off unit between the epilogue and the MMA issuer is a SUB-CHUNK of 32 activation columns (2 K-steps, 6 MMAs):
+// the tensor pipe restarts ~0.5K clk after an accumulator completes and idles only ~0.9K clk behind the last publish.
 struct Epi {
-    uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;
+    uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;      // a_ready[8]: one per sub-chunk
     uint32_t* sig;   // [8][128 column pairs][128 rows] packed softplus' of every forward layer: half2 of copysign(exp(-100|x|), x)
     float* pe_s;     // [40][128] fp32 Fourier encoding (final chain)
     float* pk_s;     // [40][128] encoding * ACT_SCALE / sqrt2 (skip concat operand)
     float* ge_s;     // [40][128] skip-path gradient (G_SCALE units)
     int r, gq, lane;
-    uint32_t off0, off1;                   // swizzled byte offsets of this thread's two 8-column groups inside a chunk
+    uint32_t off[2];                       // swizzled byte offset of this thread's 8 columns inside a chunk (even / odd sub-chunk)
     uint32_t s_hi, s_lo;                   // shared-space addresses of A_hi / A_lo
     long long* tl;                         // timeline slot of the current gemm (nullptr = off)
-    // 16 values -> A chunk c (hi/lo split), then signal the MMA issuer (one arrival per warp).
+    // 8 values -> sub-chunk sc of the A operand (hi/lo split), then signal the MMA issuer (one arrival per warp).
     // NOTE: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it drains every outstanding memory
     // operation of the thread, so callers issue their global loads / stores right AFTER publish(), never before.
-    __device__ __forceinline__ void publish(int c, const float* o) const {
-        store_split8s(s_hi + c * A_CHUNK + off0, s_lo + c * A_CHUNK + off0, o);
-        store_split8s(s_hi + c * A_CHUNK + off1, s_lo + c * A_CHUNK + off1, o + 8);
+    __device__ __forceinline__ void publish(int sc, const float* o) const {
+        const uint32_t o8 = (uint32_t)(sc >> 1) * A_CHUNK + off[sc & 1];
+        store_split8s(s_hi + o8, s_lo + o8, o);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[c]);
+        if (lane == 0) mbar_arrive(&a_ready[sc]);
     }
 };
+
+__device__ __forceinline__ void ldg8(const float* p, float (&b)[8]) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(p)), t1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
+}
 
 // precise trig kept out of line: the range-reduction slow paths are large and would be inlined dozens of times
 __device__ __noinline__ float sin_precise(float x) { return sinf(x); }
@@ -252,8 +260,8 @@ constexpr float OS_F16 = 1.0f / W_SCALE;
 constexpr float SP_K = -144.269504f / ACT_SCALE;
 constexpr float SP_L = 6.93147181e-3f * ACT_SCALE;
 
-// All epilogues are software-pipelined over the four 64-column chunks with two alternating register sets: the
-// TMEM load and the L2 loads of chunk c+1 are in flight while chunk c is processed.  `wait_acc` blocks until the
+// All epilogues are software-pipelined over the eight 32-column sub-chunks with two alternating register sets: the
+// TMEM load and the L2 loads of sub-chunk sc+1 are in flight while sc is processed.  `wait_acc` blocks until the
 // accumulator of this gemm is complete and returns its TMEM address (lane base included); loads that do not
 // depend on it (bias, softplus') are issued before it.
 
@@ -262,28 +270,31 @@ constexpr float SP_L = 6.93147181e-3f * ACT_SCALE;
 template <bool GRAD, int LT, int OUT, class WaitAcc>
 __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, int l, const float* __restrict__ bias16,
                                             const float* __restrict__ head_w, float& dot16) {
-    float vA[16], bA[16], vB[16], bB[16];
-    float wA[LT == 2 ? 16 : 1], wB[LT == 2 ? 16 : 1], pk[LT == 1 ? 16 : 1];
-    const int cq = E.gq * 16;
-    ldg16(bias16 + cq, bA);
-    ldg16(bias16 + cq + 64, bB);
-    if (LT == 2) { ldg16(head_w + cq, reinterpret_cast<float (&)[16]>(wA)); ldg16(head_w + cq + 64, reinterpret_cast<float (&)[16]>(wB)); }
-    if (LT == 1) {                                     // skip-concat operand of the last chunk (columns >= 217)
+    float vA[8], bA[8], vB[8], bB[8];
+    float wA[LT == 2 ? 8 : 1], wB[LT == 2 ? 8 : 1], pk[LT == 1 ? 16 : 1];
+    const int cq = E.gq * 8;
+    ldg8(bias16 + cq, bA);
+    ldg8(bias16 + cq + 32, bB);
+    if (LT == 2) { ldg8(head_w + cq, reinterpret_cast<float (&)[8]>(wA)); ldg8(head_w + cq + 32, reinterpret_cast<float (&)[8]>(wB)); }
+    if (LT == 1) {                                     // skip-concat operand of the last two sub-chunks (columns >= 217)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const int col = 192 + cq + i; pk[LT == 1 ? i : 0] = col >= SKIP_H ? E.pk_s[(col - SKIP_H) * TM + E.r] : 0.f; }
+        for (int i = 0; i < 16; ++i) {
+            const int col = 192 + (i >> 3) * 32 + cq + (i & 7);
+            pk[LT == 1 ? i : 0] = col >= SKIP_H ? E.pk_s[(col - SKIP_H) * TM + E.r] : 0.f;
+        }
     }
     if (E.tl) E.tl[0] = clock64();
     const uint32_t acc = wait_acc() + cq;
     if (E.tl) E.tl[1] = clock64();
-    tmem_ld16(acc, vA);
+    tmem_ld8(acc, vA);
     uint32_t* const sig_l = E.sig + ((size_t)l * 128 + cq / 2) * TM + E.r;
-    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], float* w, const int c) {
+    auto step = [&](float (&v)[8], float (&b)[8], float (&nv)[8], float* w, const int sc) {
         tmem_wait_ld();
-        if (E.tl) E.tl[2 + c * 3] = clock64();
-        if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
-        float s[16];
+        if (E.tl) E.tl[2 + sc * 3] = clock64();
+        if (sc < 7) tmem_ld8(acc + (sc + 1) * 32, nv);
+        float s[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const float x = fmaf(v[i], OS_F16, b[i]);
             const float e = ex2_approx(SP_K * fabsf(x));
             const float t = 1.0f + e;
@@ -291,137 +302,148 @@ __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, in
             v[i] = fmaf(lg2_approx(t), SP_L, fmaxf(x, 0.0f));
         }
         if (LT == 1) {
-            if (c * 64 + cq + 16 <= SKIP_H) {
+            if (sc * 32 + cq + 8 <= SKIP_H) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] *= INV_SQRT2;
+                for (int i = 0; i < 8; ++i) v[i] *= INV_SQRT2;
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int col = c * 64 + cq + i;
-                    v[i] = col < SKIP_H ? v[i] * INV_SQRT2 : pk[LT == 1 ? i : 0];
+                for (int i = 0; i < 8; ++i) {
+                    const int col = sc * 32 + cq + i;
+                    v[i] = col < SKIP_H ? v[i] * INV_SQRT2 : pk[LT == 1 ? ((sc - 6) & 1) * 8 + i : 0];
                 }
             }
         }
         if (LT == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dot16 = fmaf(v[i], w[i], dot16);
+            for (int i = 0; i < 8; ++i) dot16 = fmaf(v[i], w[i], dot16);
         }
-        if (E.tl) E.tl[3 + c * 3] = clock64();
+        if (E.tl) E.tl[3 + sc * 3] = clock64();
         if (OUT == 1) {
-            E.publish(c, v);
+            E.publish(sc, v);
         } else if (OUT == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
-            E.publish(c, v);
+            for (int i = 0; i < 8; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
+            E.publish(sc, v);
         }
-        if (E.tl) E.tl[4 + c * 3] = clock64();
-        // global traffic goes after the fence inside publish(): softplus' stores, bias of the chunk after next
+        if (E.tl) E.tl[4 + sc * 3] = clock64();
+        // global traffic goes after the fence inside publish(): softplus' stores, bias of the sub-chunk after next
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sig_l[(size_t)(c * 32 + i) * TM] = pack_sig2(s[2 * i], s[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) sig_l[(size_t)(sc * 16 + i) * TM] = pack_sig2(s[2 * i], s[2 * i + 1]);
         }
-        if (c < 2) {
-            ldg16(bias16 + cq + (c + 2) * 64, b);
-            if (LT == 2) ldg16(head_w + cq + (c + 2) * 64, *reinterpret_cast<float (*)[16]>(w));
+        if (sc < 6) {
+            ldg8(bias16 + cq + (sc + 2) * 32, b);
+            if (LT == 2) ldg8(head_w + cq + (sc + 2) * 32, *reinterpret_cast<float (*)[8]>(w));
         }
     };
     step(vA, bA, vB, wA, 0);
     step(vB, bB, vA, wB, 1);
     step(vA, bA, vB, wA, 2);
     step(vB, bB, vA, wB, 3);
+    step(vA, bA, vB, wA, 4);
+    step(vB, bB, vA, wB, 5);
+    step(vA, bA, vB, wA, 6);
+    step(vB, bB, vA, wB, 7);
 }
 
-// feature head epilogue: write feat (fp32, row-major) and, with GRAD, seed the reverse sweep
+// feature head epilogue: write feat (fp32 row-major, or the fp16 operand image of the tile) and, with GRAD, seed the reverse sweep
 template <bool GRAD, class WaitAcc>
 __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
                                          float* __restrict__ feat_row, uint8_t* __restrict__ feat_tile_img, bool valid) {
-    float vA[16], bA[16], vB[16], bB[16];
-    const int cq = E.gq * 16;
-    ldg16(bias + cq, bA);
+    float vA[8], bA[8], vB[8], bB[8];
+    const int cq = E.gq * 8;
+    ldg8(bias + cq, bA);
     const uint32_t acc = wait_acc() + cq;
-    tmem_ld16(acc, vA);
+    tmem_ld8(acc, vA);
     const uint32_t* const sig_l = E.sig + ((size_t)(SDF_LAYERS - 1) * 128 + cq / 2) * TM + E.r;
-    auto step = [&](float (&v)[16], float (&b)[16], float (&nv)[16], float (&nb)[16], const int c) {
+    auto step = [&](float (&v)[8], float (&b)[8], float (&nv)[8], float (&nb)[8], const int sc) {
         tmem_wait_ld();
-        if (c < 3) { tmem_ld16(acc + (c + 1) * 64, nv); ldg16(bias + cq + (c + 1) * 64, nb); }
-        float w[16], s[16];
+        if (sc < 7) { tmem_ld8(acc + (sc + 1) * 32, nv); ldg8(bias + cq + (sc + 1) * 32, nb); }
+        float w[8], s[8];
         if (GRAD) {
-            ldg16(head_w + cq + c * 64, w);
+            ldg8(head_w + cq + sc * 32, w);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float2 t2 = unpack_sig2(sig_l[(size_t)(c * 32 + i) * TM]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
+            for (int i = 0; i < 4; ++i) { const float2 t2 = unpack_sig2(sig_l[(size_t)(sc * 16 + i) * TM]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
         if (feat_tile_img) {                           // fp16 operand image of this tile (every row is written)
-            float t16[16];
+            float t16[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t16[i] = valid ? v[i] * ACT_SCALE : 0.f;
-            store_half8(feat_tile_img + c * A_CHUNK, E.off0, t16);
-            store_half8(feat_tile_img + c * A_CHUNK, E.off1, t16 + 8);
+            for (int i = 0; i < 8; ++i) t16[i] = valid ? v[i] * ACT_SCALE : 0.f;
+            store_half8(feat_tile_img + (sc >> 1) * A_CHUNK, E.off[sc & 1], t16);
         } else if (valid) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(feat_row + cq + c * 64 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 2; ++i)
+                *reinterpret_cast<float4*>(feat_row + cq + sc * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
-            E.publish(c, v);
+            for (int i = 0; i < 8; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
+            E.publish(sc, v);
         }
     };
     step(vA, bA, vB, bB, 0);
     step(vB, bB, vA, bA, 1);
     step(vA, bA, vB, bB, 2);
     step(vB, bB, vA, bA, 3);
+    step(vA, bA, vB, bB, 4);
+    step(vB, bB, vA, bA, 5);
+    step(vA, bA, vB, bB, 6);
+    step(vB, bB, vA, bA, 7);
 }
 
 // reverse layer epilogue (l = 7..1): g_pre_{l-1} = (W_l^T g_pre_l) * softplus'_{l-1}; SKIP = (l == 4).
 // sig holds softplus' / W_SCALE, so acc * sig is already in G_SCALE units.
 template <bool SKIP, class WaitAcc>
 __device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, int l) {
-    const int cq = E.gq * 16;
+    const int cq = E.gq * 8;
     const uint32_t* const sig_l = E.sig + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
-    float vA[16], vB[16];
-    uint32_t sA[8], sB[8];
-    auto load_sig = [&](uint32_t (&sg)[8], const int c) {
+    float vA[8], vB[8];
+    uint32_t sA[4], sB[4];
+    auto load_sig = [&](uint32_t (&sg)[4], const int sc) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            sg[i] = (!SKIP || c * 64 + cq + 2 * i < SKIP_H) ? sig_l[(size_t)(c * 32 + i) * TM] : 0u;
+        for (int i = 0; i < 4; ++i)
+            sg[i] = (!SKIP || sc * 32 + cq + 2 * i < SKIP_H) ? sig_l[(size_t)(sc * 16 + i) * TM] : 0u;
     };
     load_sig(sA, 0);
     load_sig(sB, 1);
     const uint32_t acc = wait_acc() + cq;
-    tmem_ld16(acc, vA);
-    auto step = [&](float (&v)[16], uint32_t (&sg)[8], float (&nv)[16], const int c) {
+    tmem_ld8(acc, vA);
+    auto step = [&](float (&v)[8], uint32_t (&sg)[4], float (&nv)[8], const int sc) {
         tmem_wait_ld();
-        if (c < 3) tmem_ld16(acc + (c + 1) * 64, nv);
-        float ge[16];
+        if (sc < 7) tmem_ld8(acc + (sc + 1) * 32, nv);
+        float ge[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const float2 pk = unpack_sig2(sg[i]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int j = 2 * i + h, col = c * 64 + cq + j;
+                const int j = 2 * i + h, col = sc * 32 + cq + j;
                 const float p1 = h ? pk.y : pk.x;
                 if (!SKIP) v[j] *= dsig_from_packed(p1);
                 else if (col >= SKIP_H) { ge[j] = v[j] * (OS_R * INV_SQRT2); v[j] = 0.f; }
                 else v[j] = v[j] * INV_SQRT2 * dsig_from_packed(p1);
             }
         }
-        E.publish(c, v);
+        E.publish(sc, v);
         if (SKIP) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int col = c * 64 + cq + i;
+            for (int i = 0; i < 8; ++i) {
+                const int col = sc * 32 + cq + i;
                 if (col >= SKIP_H) E.ge_s[(col - SKIP_H) * TM + E.r] = ge[i];
             }
         }
-        if (c < 2) load_sig(sg, c + 2);
+        if (sc < 6) load_sig(sg, sc + 2);
     };
     step(vA, sA, vB, 0);
     step(vB, sB, vA, 1);
     step(vA, sA, vB, 2);
     step(vB, sB, vA, 3);
+    step(vA, sA, vB, 4);
+    step(vB, sB, vA, 5);
+    step(vA, sA, vB, 6);
+    step(vB, sB, vA, 7);
 }
 
 template <bool GRAD, bool FEAT>
@@ -435,38 +457,32 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     uint8_t* A_lo = smem + SM_A_LO;
     uint8_t* Bst = smem + SM_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC);
-    uint64_t* b_full = bars;                  // [12]
-    uint64_t* b_empty = bars + NSTAGES;       // [12]
-    uint64_t* a_ready = bars + 2 * NSTAGES;   // [4]
-    uint64_t* acc_full = a_ready + 4;         // [2]
+    uint64_t* b_full = bars;                  // [NSTAGES]
+    uint64_t* b_empty = bars + NSTAGES;       // [NSTAGES]
+    uint64_t* a_ready = bars + 2 * NSTAGES;   // [8] one per 32-column sub-chunk of the A operand
+    uint64_t* acc_full = a_ready + 8;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    uint32_t* ready = tmem_slot + 1;                             // number of sub-chunks whose operands are in place (scout -> issuer)
     float* part = reinterpret_cast<float*>(bars + 32);          // [3][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NG = num_gemms<GRAD, FEAT>();
     const TcLayout T = tc_layout();
 
-    // A cluster of `ncta` CTAs shares one weight stream: every CTA loads 1/ncta of each stage and multicasts it, a
-    // stage is recycled when the MMAs of every CTA that read it have completed (multicast commit -> b_empty).
-    // All CTAs of a cluster run the same number of tile iterations (a CTA without a real tile computes on zeros).
-    const int ncta = P.ncta;
-    const uint32_t crank = ncta > 1 ? cluster_ctarank() : 0;
-    const uint16_t cmask = (uint16_t)((1u << ncta) - 1);
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
-        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], ncta); }
-        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], EPI_WARPS);
+        *ready = 0;
+        for (int i = 0; i < NSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], EPI_WARPS);
         for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1);
         fence_mbar_init();
     }
     tc_fence_before();
-    cluster_sync_all();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t ntiles = (N + TM - 1) / TM;
-    const int64_t tile0 = (int64_t)(blockIdx.x / ncta) * ncta + crank;      // == blockIdx.x
-    const int64_t tstride = gridDim.x;
-    const int64_t tiles_padded = (ntiles + ncta - 1) / ncta * ncta;          // clusters iterate in lock step
+    const int64_t tile0 = blockIdx.x, tstride = gridDim.x, tiles_padded = ntiles;
 
     if (warp == 0) {
         // ======================= weight producer =======================
@@ -475,25 +491,41 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
                 for (int gi = 0; gi < NG; ++gi) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
-                    for (int img = 0; img < G.nchunks * 2; ++img, ++it) {
+                    for (int img = 0; img < G.nsub; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
                         if (P.dbg >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
                         mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
-                        const uint8_t* src = P.tc + G.b_off + (size_t)img * G.img_bytes;
-                        if (ncta == 1) bulk_g2s(Bst + s * STAGE, src, G.img_bytes, &b_full[s]);
-                        else {
-                            const uint32_t part = G.img_bytes / ncta;
-                            bulk_g2s_multicast(Bst + s * STAGE + crank * part, src + crank * part, part, &b_full[s], cmask);
-                        }
+                        bulk_g2s(Bst + s * STAGE, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
+                    }
+                }
+        }
+    } else if (warp == 2) {
+        // ======================= readiness scout =======================
+        // Every mbarrier wait executed by the MMA-issuing thread is tensor-pipe idle time (a try_wait that succeeds at once
+        // still costs ~280 clk there, a plain shared-memory load ~70: tests/tc_probe3.cu).  This thread does the waiting
+        // instead -- operand sub-chunk published by the epilogue, weight image landed -- strictly in issue order, and
+        // publishes one monotonic counter that the issuer polls with an ordinary load, usually once per several sub-chunks.
+        if (lane == 0) {
+            uint32_t it = 0, a_par = 0;
+            const uint32_t ready_s = smem_u32(ready);
+            for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
+                for (int gi = 0; gi < NG; ++gi) {
+                    const int nsub = get_gemm<GRAD, FEAT>(T, gi).nsub;
+                    for (int sc = 0; sc < nsub; ++sc, ++it) {
+                        mbar_wait(&a_ready[sc], (a_par >> sc) & 1);
+                        a_par ^= (1u << sc);
+                        mbar_wait(&b_full[it % NSTAGES], (it / NSTAGES) & 1);
+                        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_s), "r"(it + 1) : "memory");
                     }
                 }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
-            uint32_t it = 0, a_par = 0, gc = 0;
+            uint32_t it = 0, gc = 0, ready_seen = 0;
             const uint32_t a_hi_lo = desc_lo(smem_u32(A_hi)), a_lo_lo = desc_lo(smem_u32(A_lo)), b_lo0 = desc_lo(smem_u32(Bst));
+            const uint32_t ready_s = smem_u32(ready);
             const bool mma_on = (P.dbg != 2 && P.dbg != 4);
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
                 for (int gi = 0; gi < NG; ++gi, ++gc) {
@@ -502,46 +534,35 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
                     const int lgi = (P.dbg == 9) ? gi - 8 : gi;
                     const bool lg = P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
-                    for (int c = 0; c < G.nchunks; ++c) {
-                        if (lg) P.tlog[lgi * 16 + c * 3 + 0] = clock64();
-                        mbar_wait(&a_ready[c], (a_par >> c) & 1);
-                        if (lg) P.tlog[lgi * 16 + c * 3 + 1] = clock64();
-                        a_par ^= (1u << c);
-                        tc_fence_after();
-                        const uint32_t ah = a_hi_lo + c * (A_CHUNK >> 4), al = a_lo_lo + c * (A_CHUNK >> 4);
-                        // W_hi image: A_hi * W_hi + A_lo * W_hi
-                        {
-                            const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
-                            mbar_wait(&b_full[s], u & 1);
-                            tc_fence_after();
-                            if (mma_on) {
-                                const uint32_t bl = b_lo0 + s * (STAGE >> 4), d = acc;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    if (ks < G.ksteps) umma_f16_lo(d, ah + ks * 2, bl + ks * 2, idesc, (uint32_t)((c | ks) != 0));
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    if (ks < G.ksteps) umma_f16_lo(d, al + ks * 2, bl + ks * 2, idesc, 1u);
+                    for (int sc = 0; sc < G.nsub; ++sc, ++it) {
+                        if (lg) P.tlog[lgi * 32 + sc * 3 + 0] = clock64();
+                        if (ready_seen <= it) {
+                            uint32_t spins = 0;
+                            while (true) {
+                                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready_seen) : "r"(ready_s) : "memory");
+                                if (ready_seen > it) break;
+                                if (++spins > (1u << 27)) asm volatile("trap;");
                             }
-                            if (ncta == 1) umma_commit(&b_empty[s]); else umma_commit_multicast(&b_empty[s], cmask);
-                        }
-                        // W_lo image: A_hi * W_lo
-                        {
-                            const uint32_t s = it % NSTAGES, u = it / NSTAGES; ++it;
-                            mbar_wait(&b_full[s], u & 1);
                             tc_fence_after();
-                            if (mma_on) {
-                                const uint32_t bl = b_lo0 + s * (STAGE >> 4), d = acc;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    if (ks < G.ksteps) umma_f16_lo(d, ah + ks * 2, bl + ks * 2, idesc, 1u);
-                            }
-                            if (ncta == 1) umma_commit(&b_empty[s]); else umma_commit_multicast(&b_empty[s], cmask);
                         }
-                        if (lg) P.tlog[lgi * 16 + c * 3 + 2] = clock64();
+                        if (lg) P.tlog[lgi * 32 + sc * 3 + 1] = clock64();
+                        const uint32_t s = it % NSTAGES;
+                        if (mma_on) {
+                            // A: K-steps 2 sc, 2 sc + 1 of the 64-wide chunk sc / 2 (32 B per K-step inside the swizzled rows)
+                            const uint32_t ko = (uint32_t)(sc >> 1) * (A_CHUNK >> 4) + (uint32_t)(sc & 1) * 4;
+                            const uint32_t ah = a_hi_lo + ko, al = a_lo_lo + ko, bl = b_lo0 + s * (STAGE >> 4);
+                            umma_f16_lo(acc, ah, bl, idesc, (uint32_t)(sc != 0));        // A_hi * W_hi
+                            umma_f16_lo(acc, ah + 2, bl + 2, idesc, 1u);
+                            umma_f16_lo(acc, al, bl, idesc, 1u);                          // A_lo * W_hi
+                            umma_f16_lo(acc, al + 2, bl + 2, idesc, 1u);
+                            umma_f16_lo(acc, ah, bl + 4, idesc, 1u);                      // A_hi * W_lo
+                            umma_f16_lo(acc, ah + 2, bl + 6, idesc, 1u);
+                        }
+                        umma_commit(&b_empty[s]);
+                        if (lg) P.tlog[lgi * 32 + sc * 3 + 2] = clock64();
                     }
                     umma_commit(&acc_full[gc & 1]);
-                    if (lg) P.tlog[lgi * 16 + 12] = clock64();
+                    if (lg) P.tlog[lgi * 32 + 24] = clock64();
                 }
         }
     } else if (warp >= EPI_WARP0) {
@@ -558,8 +579,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         E.pe_s = scr + (size_t)SDF_LAYERS * 128 * TM;
         E.pk_s = E.pe_s + PE_PAD * TM;
         E.ge_s = E.pk_s + PE_PAD * TM;
-        E.off0 = sw128_offset(E.r, E.gq * 16);
-        E.off1 = sw128_offset(E.r, E.gq * 16 + 8);
+        E.off[0] = sw128_offset(E.r, E.gq * 8);
+        E.off[1] = sw128_offset(E.r, 32 + E.gq * 8);
         E.s_hi = smem_u32(A_hi); E.s_lo = smem_u32(A_lo);
         uint32_t gc = 0;
         auto wait_acc = [&]() -> uint32_t {
@@ -613,7 +634,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[0]);
+                if (lane == 0) { mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]); }
                 epi_bar_sync();                       // pe_s visible to every epilogue thread
             }
 
@@ -621,7 +642,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             float dot = 0.f;
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
-                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? P.tlog + 128 + l * 16 : nullptr;
+                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? P.tlog + 256 + l * 32 : nullptr;
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 tc_fence_before();
@@ -689,7 +710,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     }
 
     tc_fence_before();
-    cluster_sync_all();            // no CTA may exit while its peer can still multicast into it / arrive on its barriers
+    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -935,13 +956,13 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
 // ===============================================================================================================
 // operand-image builders (weight packing)
 // ===============================================================================================================
-struct Seg { int dst_k0, src_col0, len; };
+struct Seg { int dst_k0, src_col0, len, lo; };      // lo: 0 = fp16(x), 1 = the residual x - fp16(x)
 struct ImgJob {
     const float* src; int src_ld;        // element (n, kcol) = src[n*src_ld + kcol]
     int nrows_valid;                     // rows beyond are zero
     int nrows_img;                       // 256 or 64
     Seg seg[4]; int nseg;                // k-range mapping inside this 64-wide chunk
-    int lo;                              // 0: hi part, 1: lo part (x - fp16(x))
+    int lo;                              // 1: every segment stores the residual part
     float scale;
     __half* dst;
 };
@@ -951,12 +972,15 @@ __global__ void k_build_image(ImgJob J) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i >> 6, k = i & 63;
         float v = 0.f;
+        int lo = J.lo;
         if (n < J.nrows_valid)
             for (int s = 0; s < J.nseg; ++s)
-                if (k >= J.seg[s].dst_k0 && k < J.seg[s].dst_k0 + J.seg[s].len)
+                if (k >= J.seg[s].dst_k0 && k < J.seg[s].dst_k0 + J.seg[s].len) {
                     v = J.src[(size_t)n * J.src_ld + J.seg[s].src_col0 + (k - J.seg[s].dst_k0)] * J.scale;
+                    lo |= J.seg[s].lo;
+                }
         const __half h = __float2half_rn(v);
-        const __half out = J.lo ? __float2half_rn(v - __half2float(h)) : h;
+        const __half out = lo ? __float2half_rn(v - __half2float(h)) : h;
         J.dst[sw128_offset(n, k) >> 1] = out;
     }
 }
@@ -968,23 +992,27 @@ __global__ void k_scale_copy(const float* __restrict__ src, float* __restrict__ 
 int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
                 uint8_t* dst, cudaStream_t st) {
     ImgJob J; J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
-    for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0};
+    for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0, 0};
     J.lo = lo; J.scale = W_SCALE; J.dst = reinterpret_cast<__half*>(dst);
     k_build_image<<<(nrows_img * 64 + 255) / 256, 256, 0, st>>>(J);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }
 
-// a plain K-major matrix [nrows_valid x kcols] -> `nchunks` chunks, each as (hi, lo) or hi-only images
+// a plain K-major matrix [nrows_valid x kcols] -> `nchunks` chunks of 64 K-columns.  split: two images per chunk, one per
+// 32-column sub-chunk, each [hi(32) | lo(32)]; else one hi-only image per chunk.
 int build_matrix(const float* src, int src_ld, int nrows_valid, int nrows_img, int kcols, int nchunks, bool split,
                  uint8_t* dst, uint32_t img_bytes, cudaStream_t st) {
     int rc;
     for (int c = 0; c < nchunks; ++c) {
         int len = kcols - c * 64; if (len > 64) len = 64; if (len < 0) len = 0;
-        Seg s{0, c * 64, len};
+        Seg s{0, c * 64, len, 0};
         if (split) {
-            if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 0, dst + (size_t)(2 * c) * img_bytes, st))) return rc;
-            if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 1, dst + (size_t)(2 * c + 1) * img_bytes, st))) return rc;
+            for (int h = 0; h < 2; ++h) {
+                int l32 = kcols - (c * 64 + h * 32); if (l32 > 32) l32 = 32; if (l32 < 0) l32 = 0;
+                Seg hl[2] = {{0, c * 64 + h * 32, l32, 0}, {32, c * 64 + h * 32, l32, 1}};
+                if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, hl, 2, 0, dst + (size_t)(2 * c + h) * img_bytes, st))) return rc;
+            }
         } else {
             if ((rc = build_image(src, src_ld, nrows_valid, nrows_img, &s, 1, 0, dst + (size_t)c * img_bytes, st))) return rc;
         }
@@ -1059,21 +1087,13 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int64_t ntiles = (N + TM - 1) / TM;
-    { const char* e = getenv("NRH_TC_CLUSTER"); P.ncta = e ? atoi(e) : 2; if (P.ncta != 2 || P.dbg >= 3) P.ncta = 1; }
-    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    if (P.ncta == 2) grid = (grid + 1) / 2 * 2 > num_sms ? num_sms / 2 * 2 : (grid + 1) / 2 * 2;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
     const bool grad = gx != nullptr, wfeat = feat != nullptr;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = SDF_SMEM; lc.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)P.ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr; lc.numAttrs = 1;
 #define NRH_LAUNCH_TC(G, F)                                                                                        \
     do {                                                                                                           \
         NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM)); \
-        NRH_CUDA_CHECK(cudaLaunchKernelEx(&lc, sdf_tc_kernel<G, F>, P, pts, N, sdf, gx, gy, gz, grad_stride, feat, scratch));   \
+        sdf_tc_kernel<G, F><<<grid, NTHREADS, SDF_SMEM, st>>>(P, pts, N, sdf, gx, gy, gz, grad_stride, feat, scratch);           \
     } while (0)
     if (grad && wfeat) NRH_LAUNCH_TC(true, true);
     else if (grad) NRH_LAUNCH_TC(true, false);

@@ -1,3 +1,5 @@
+"""Developer timeline of the tcgen05 SDF kernel (clock64 stamps of block 0, third tile); run on the GPU box.
+usage: tc_tlog.py [sdf|grad] [NRH_TC_DEBUG value]"""
 import os, sys
 import torch
 sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
@@ -15,11 +17,17 @@ buf.zero_(); m.sdf_query(pts, want_grad=grad); torch.cuda.synchronize()
 t = buf.cpu().numpy()
 base = t[t > 0].min()
 print("mode", "grad" if grad else "sdf-only", "dbg", os.environ.get("NRH_TC_DEBUG", "0"))
-print("MMA thread, per gemm gi: [wait_a_start, a_ready, chunk_issued] x4 chunks, then acc commit  (cycles from first stamp)")
+print("MMA thread, per gemm gi: [a_ready, issued] x8 sub-chunks (relative to the wait start of sub-chunk 0), then acc commit")
 for gi in range(8):
-    r = t[gi * 16: gi * 16 + 13] - base
-    print(f" g{gi}: " + " | ".join(f"{r[c*3]:6d} {r[c*3+1]:6d} {r[c*3+2]:6d}" for c in range(4)) + f" | commit {r[12]:6d}")
-print("epilogue warp 2, per layer l: wait_acc_start, acc_ready, then per chunk [ld_done, math_done, published]")
+    r = t[gi * 32: gi * 32 + 25] - base
+    n = 2 if gi == 0 else 8
+    print(f" g{gi}: start {r[0]:6d} | " + " | ".join(f"{r[c*3+1]-r[0]:5d} {r[c*3+2]-r[0]:5d}" for c in range(n)) + f" | commit {r[24]-r[0]:5d}")
+print("epilogue warp 2, per layer l: wait_acc_start, acc_ready, then per sub-chunk [ld_done, math_done, published] relative to acc_ready")
 for l in range(7):
-    r = t[128 + l * 16: 128 + l * 16 + 14] - base
-    print(f" l{l}: {r[0]:6d} {r[1]:6d} | " + " | ".join(f"{r[2+c*3]:6d} {r[3+c*3]:6d} {r[4+c*3]:6d}" for c in range(4)))
+    r = t[256 + l * 32: 256 + l * 32 + 26] - base
+    print(f" l{l}: {r[0]:6d} {r[1]:6d} | " + " | ".join(f"{r[2+c*3]-r[1]:5d} {r[3+c*3]-r[1]:5d} {r[4+c*3]-r[1]:5d}" for c in range(8)))
+cm = [int(t[gi * 32 + 24] - base) for gi in range(8)]
+wa = [int(t[gi * 32 + 1] - t[gi * 32 + 0]) for gi in range(2, 7)]
+ew = [int(t[256 + l * 32 + 1] - t[256 + l * 32]) for l in range(2, 7)]
+print(f"SUMMARY cluster={os.environ.get('NRH_TC_CLUSTER','1')} dbg={os.environ.get('NRH_TC_DEBUG','0')} period/gemm {(cm[6]-cm[2])/4:.0f}  "
+      f"MMA first-sub-chunk wait {sum(wa)/len(wa):.0f}  epilogue accumulator wait {sum(ew)/len(ew):.0f}")
