@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 1
+#define NRH_ABI_VERSION 2
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -112,6 +112,11 @@ typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model
     float* normal_map;            /* [R,3] nullable: sum_j analytic_normal_j * w_j * inside_j               */
     float* normalized_normal_map; /* [R,3] nullable: sum_j normalized_normal_j * w_j * inside_j             */
     float* specular_cue_ray;      /* [R,n_roughness] nullable: the per-ray cue (before broadcast)           */
+    /* nullable cudaEvent_t: recorded on `stream` as soon as the per-sample geometry block (weights, inside_sphere,
+     * analytic_normals, normalized_normals, specular_cue, z_vals -- 95 % of the RenderOutput bytes) is final, i.e. before
+     * the shadow march and the reflectance network run, so that a caller that moves the result to the host
+     * (pipelines/base_pipeline.py:120) can overlap that copy with the rest of the render on a second stream. */
+    void* early_event;
 } NrhOutputs;
 
 int nrh_version(void);

@@ -51,7 +51,7 @@ class NrhOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "weights", "inside_sphere", "analytic_normals", "normalized_normals",
         "visibilities", "specular_cue", "inv_s", "z_vals", "z_shadow", "sampled_color",
-        "normal_map", "normalized_normal_map", "specular_cue_ray")]
+        "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event")]
 
 
 EXPORTS = {

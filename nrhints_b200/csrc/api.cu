@@ -379,6 +379,27 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     if ((rc = launch_composite_primary(R, w.prim, cur, S, sample_dist, inv_s, cos_anneal, w.fine, w.rs, rays->pl_positions,
                                        do_shadow, w.shad, ns, cfg->shadow_ray_offset, jitter_shadow,
                                        cfg->depth_type, rays->hit_points, rays->hit_depths, st))) return rc;
+    if ((rc = launch_specular_cue(R, *cfg, w.rs, rays->pl_positions, rays->directions, warmup, st))) return rc;
+    // ---- per-sample geometry block of the RenderOutput, ray-major: final from here on (95 % of the output bytes) ----
+    {
+        const float* s1[4] = {w.fine.w, nullptr, nullptr, nullptr};
+        if (out->weights && (rc = launch_to_ray_major(s1, 1, false, R, S, out->weights, st))) return rc;
+        const float* s2[4] = {w.fine.inside, nullptr, nullptr, nullptr};
+        if (out->inside_sphere && (rc = launch_to_ray_major(s2, 1, false, R, S, out->inside_sphere, st))) return rc;
+        const float* s3[4] = {w.fine.gx, w.fine.gy, w.fine.gz, nullptr};
+        if (out->analytic_normals && (rc = launch_to_ray_major(s3, 3, false, R, S, out->analytic_normals, st))) return rc;
+        const float* s4[4] = {w.fine.nx, w.fine.ny, w.fine.nz, nullptr};
+        if (out->normalized_normals && (rc = launch_to_ray_major(s4, 3, false, R, S, out->normalized_normals, st))) return rc;
+        if (cfg->specular_hint && out->specular_cue) {
+            const float* s5[4] = {w.rs.spec[0], w.rs.spec[1], w.rs.spec[2], w.rs.spec[3]};
+            if ((rc = launch_to_ray_major(s5, cfg->n_roughness, true, R, S, out->specular_cue, st))) return rc;
+        }
+        if (out->z_vals) {
+            const float* s6[4] = {w.prim.z[cur], nullptr, nullptr, nullptr};
+            if ((rc = launch_to_ray_major(s6, 1, false, R, S, out->z_vals, st))) return rc;
+        }
+        if (out->early_event) NRH_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(out->early_event), st));
+    }
     // ---- shadow march -------------------------------------------------------------------------------------
     int scur = 0;
     if (do_shadow) {
@@ -398,32 +419,14 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     if ((rc = launch_final_rgb(R, S, w.fine, w.rs, w.cr, w.cg, w.cb, bg_rgb, out->rgb, out->depth,
                                cfg->shadow_hint ? out->visibilities : nullptr, out->normal_map, out->normalized_normal_map,
                                cfg->specular_hint ? out->specular_cue_ray : nullptr, cfg->n_roughness, st))) return rc;
-    // ---- ray-major RenderOutput fields -------------------------------------------------------------------------
-    {
-        const float* s1[4] = {w.fine.w, nullptr, nullptr, nullptr};
-        if (out->weights && (rc = launch_to_ray_major(s1, 1, false, R, S, out->weights, st))) return rc;
-        const float* s2[4] = {w.fine.inside, nullptr, nullptr, nullptr};
-        if (out->inside_sphere && (rc = launch_to_ray_major(s2, 1, false, R, S, out->inside_sphere, st))) return rc;
-        const float* s3[4] = {w.fine.gx, w.fine.gy, w.fine.gz, nullptr};
-        if (out->analytic_normals && (rc = launch_to_ray_major(s3, 3, false, R, S, out->analytic_normals, st))) return rc;
-        const float* s4[4] = {w.fine.nx, w.fine.ny, w.fine.nz, nullptr};
-        if (out->normalized_normals && (rc = launch_to_ray_major(s4, 3, false, R, S, out->normalized_normals, st))) return rc;
-        if (cfg->specular_hint && out->specular_cue) {
-            const float* s5[4] = {w.rs.spec[0], w.rs.spec[1], w.rs.spec[2], w.rs.spec[3]};
-            if ((rc = launch_to_ray_major(s5, cfg->n_roughness, true, R, S, out->specular_cue, st))) return rc;
-        }
-        if (out->z_vals) {
-            const float* s6[4] = {w.prim.z[cur], nullptr, nullptr, nullptr};
-            if ((rc = launch_to_ray_major(s6, 1, false, R, S, out->z_vals, st))) return rc;
-        }
-        if (out->z_shadow && do_shadow) {
-            const float* s7[4] = {w.shad.z[scur], nullptr, nullptr, nullptr};
-            if ((rc = launch_to_ray_major(s7, 1, false, R, Ss, out->z_shadow, st))) return rc;
-        }
-        if (out->sampled_color) {
-            const float* s8[4] = {w.cr, w.cg, w.cb, nullptr};
-            if ((rc = launch_to_ray_major(s8, 3, false, R, S, out->sampled_color, st))) return rc;
-        }
+    // ---- late ray-major RenderOutput fields ---------------------------------------------------------------------
+    if (out->z_shadow && do_shadow) {
+        const float* s7[4] = {w.shad.z[scur], nullptr, nullptr, nullptr};
+        if ((rc = launch_to_ray_major(s7, 1, false, R, Ss, out->z_shadow, st))) return rc;
+    }
+    if (out->sampled_color) {
+        const float* s8[4] = {w.cr, w.cg, w.cb, nullptr};
+        if ((rc = launch_to_ray_major(s8, 3, false, R, S, out->sampled_color, st))) return rc;
     }
     if (out->inv_s) { k_copy_scalar<<<1, 1, 0, st>>>(inv_s, out->inv_s); NRH_LAUNCH_CHECK(); }
     return NRH_OK;

@@ -186,7 +186,23 @@ __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, flo
     }
 }
 
-// ---- shadow transmittance, specular cue, per-ray reflectance inputs ---------------------------------
+// ---- specular cue of the hit point (needs only the primary compositor's hit point / normal) --------------------
+__global__ void k_specular_cue(int64_t R, NrhConfig cfg, RayState rs, const float* __restrict__ pl, const float* __restrict__ dirs,
+                               int warmup) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float cue[NRH_MAX_ROUGHNESS] = {0.f, 0.f, 0.f, 0.f};
+    if (cfg.specular_hint && !warmup) {
+        float d[3] = {dirs[r * 3 + 0], dirs[r * 3 + 1], dirs[r * 3 + 2]};
+        float l[3] = {pl[r * 3 + 0], pl[r * 3 + 1], pl[r * 3 + 2]};
+        float hit[3] = {rs.hit[0][r], rs.hit[1][r], rs.hit[2][r]};
+        float hn[3] = {rs.hitn[0][r], rs.hitn[1][r], rs.hitn[2][r]};
+        specular_cue(hn, l, hit, d, cfg.n_roughness, cfg.roughness, cue);
+    }
+    for (int i = 0; i < NRH_MAX_ROUGHNESS; ++i) rs.spec[i][r] = cue[i];
+}
+
+// ---- shadow transmittance, per-ray reflectance inputs ---------------------------------------------------------
 __global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, int S_shadow,
                              const float* __restrict__ inv_s_ptr, float cos_anneal, const float* __restrict__ ssdf,
                              const float* __restrict__ sgx, const float* __restrict__ sgy, const float* __restrict__ sgz,
@@ -203,13 +219,8 @@ __global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, i
     rs.vis[r] = vis;
     float d[3] = {dirs[r * 3 + 0], dirs[r * 3 + 1], dirs[r * 3 + 2]};
     float l[3] = {pl[r * 3 + 0], pl[r * 3 + 1], pl[r * 3 + 2]};
-    float cue[NRH_MAX_ROUGHNESS] = {0.f, 0.f, 0.f, 0.f};
-    if (cfg.specular_hint && !warmup) {
-        float hit[3] = {rs.hit[0][r], rs.hit[1][r], rs.hit[2][r]};
-        float hn[3] = {rs.hitn[0][r], rs.hitn[1][r], rs.hitn[2][r]};
-        specular_cue(hn, l, hit, d, cfg.n_roughness, cfg.roughness, cue);
-    }
-    for (int i = 0; i < NRH_MAX_ROUGHNESS; ++i) rs.spec[i][r] = cue[i];
+    float cue[NRH_MAX_ROUGHNESS];                        // written by k_specular_cue right after the primary compositor
+    for (int i = 0; i < NRH_MAX_ROUGHNESS; ++i) cue[i] = rs.spec[i][r];
     // per-ray encoded reflectance inputs: PE(view) 27 | PE(light) 27 | PE(vis) 9 | PE(spec) 36
     fourier_encode(d, 3, COL_FREQ, rayfeat + r, R);
     fourier_encode(l, 3, COL_FREQ, rayfeat + (int64_t)COL_PE3 * R + r, R);
@@ -345,6 +356,12 @@ int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, flo
 int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pts, float* depth, float threshold, float far_limit,
                        int* moving, cudaStream_t st) {
     k_sphere_step<<<blocks_for(R), TPB, 0, st>>>(R, dirs, sdf, pts, depth, threshold, far_limit, moving);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_specular_cue(int64_t R, const NrhConfig& cfg, const RayState& rs, const float* pl, const float* dirs, int warmup, cudaStream_t st) {
+    k_specular_cue<<<blocks_for(R), TPB, 0, st>>>(R, cfg, rs, pl, dirs, warmup);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

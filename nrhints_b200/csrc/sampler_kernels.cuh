@@ -33,6 +33,7 @@ int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, flo
                              int depth_type, const float* hit_pts, const float* hit_depth, cudaStream_t st);
 int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pts, float* depth, float threshold, float far_limit,
                        int* moving, cudaStream_t st);
+int launch_specular_cue(int64_t R, const NrhConfig& cfg, const RayState& rs, const float* pl, const float* dirs, int warmup, cudaStream_t st);
 int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int cur, int S_shadow, const float* inv_s,
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,

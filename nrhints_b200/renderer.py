@@ -400,7 +400,7 @@ class NeuSHintRenderer(nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
-                global_step: int = 0, return_extras: bool = False) -> RenderOutput:
+                global_step: int = 0, return_extras: bool = False, _early_event=None) -> RenderOutput:
         lib = _lib.load()
         rays_o = ray_bundle.origins
         device = rays_o.device
@@ -452,6 +452,8 @@ class NeuSHintRenderer(nn.Module):
                               hit_pts.data_ptr() if hit_pts is not None else None,
                               hit_dep.data_ptr() if hit_dep is not None else None)
         c_out = _lib.NrhOutputs(**{k: (v.data_ptr() if v is not None else None) for k, v in out.items()})
+        if _early_event is not None:
+            c_out.early_event = _early_event.cuda_event
         wsb = lib.nrh_workspace_bytes(C.byref(cfg), R)
         ws = self._ensure_workspace(wsb, device)
         if R > 0:
@@ -511,9 +513,17 @@ class NeuSHintRenderer(nn.Module):
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy
     #    per field on the current stream, one sync) -------------------------------------------------------------------
-    def to_host(self, out: RenderOutput) -> RenderOutput:
+    def _pinned_like(self, name: str, v: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_pinned"):
             self._pinned = {}
+        key = (name, tuple(v.shape), v.dtype)
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            self._pinned[key] = buf
+        return buf
+
+    def to_host(self, out: RenderOutput, _skip=()) -> RenderOutput:
         host = {}
         for k, v in out.as_dict().items():
             if v is None:
@@ -521,17 +531,42 @@ class NeuSHintRenderer(nn.Module):
                 continue
             if k == "relax_inside_sphere":
                 continue
-            v = v.detach()
-            key = (k, tuple(v.shape), v.dtype)
-            buf = self._pinned.get(key)
-            if buf is None:
-                buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-                self._pinned[key] = buf
-            buf.copy_(v, non_blocking=True)
+            buf = self._pinned_like(k, v)
+            if k not in _skip:
+                buf.copy_(v.detach(), non_blocking=True)
             host[k] = buf
         host["relax_inside_sphere"] = host["inside_sphere"]
         torch.cuda.current_stream(out.rgb.device).synchronize()
         return RenderOutput(**host)
+
+    # the per-sample geometry block is final before the shadow march and the reflectance network run (NrhOutputs.early_event)
+    _EARLY_FIELDS = ("weights", "inside_sphere", "analytic_normals", "normalized_analytic_normals", "specular_cue", "z_vals")
+
+    @torch.no_grad()
+    def render_to_host(self, ray_bundle, background_rgb: Optional[torch.Tensor] = None, device=None,
+                       return_extras: bool = False) -> RenderOutput:
+        """Inference render of a (host or device) RayBundle with the whole RenderOutput delivered in pinned host memory --
+        the `renderer(rays); rendering_res.to('cpu')` pattern of the reference's evaluation loop
+        (pipelines/base_pipeline.py:114-120) as one call.  The 7 KB/ray of per-sample geometry are copied on a second
+        stream while the shadow march and the reflectance network still run, so the call costs about one forward."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._early_event = torch.cuda.Event()
+        rays = ray_bundle.to(device, non_blocking=True)
+        bg = background_rgb.to(device, non_blocking=True) if background_rgb is not None else None
+        self._early_event.record(main)                       # materialises the CUDA event; the library re-records it
+        out = self.forward(rays, is_training=False, background_rgb=bg, return_extras=return_extras,
+                           _early_event=self._early_event)
+        early = {k: getattr(out, k) for k in self._EARLY_FIELDS if getattr(out, k, None) is not None}
+        self._copy_stream.wait_event(self._early_event)
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in early.items():
+                self._pinned_like(k, v).copy_(v, non_blocking=True)
+        host = self.to_host(out, _skip=tuple(early))           # the remaining small fields, then a sync of the main stream
+        self._copy_stream.synchronize()
+        return host
 
     # -- meshing helpers (models/neus_hint_model.py:68-93,753-758) -------------------------------------------
     @torch.no_grad()

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_version_and_config_validation_without_gpu():
     lib = _lib.load()
-    assert lib.nrh_version() == 1
+    assert lib.nrh_version() == 2
     import nrhints_b200 as nb
     m = nb.NeuSHintRenderer(nb.NeuSModelConfig())
     cfg = m._c_config()
@@ -47,8 +47,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 3 * 4
     assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1) * 8
     assert C.sizeof(_lib.NrhRays) == 7 * 8
-    assert C.sizeof(_lib.NrhOutputs) == 15 * 8
-    fields = re.findall(r"float\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
+    assert C.sizeof(_lib.NrhOutputs) == 16 * 8
+    fields = re.findall(r"(?:float|void)\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
     assert fields == [n for n, _ in _lib.NrhOutputs._fields_]
 
 
