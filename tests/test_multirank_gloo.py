@@ -60,3 +60,60 @@ def test_two_rank_ray_sharding():
         assert p.exitcode == 0
     assert ok, "sharded render != unsharded render"
     assert tmax == 2.0 and total == 8
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(T.ROOT))
+    from nrhints_b200.workload import synthetic_rays, shard_rays
+    from nrhints_b200 import autograd_fine
+    from nrhints_b200.grad_sync import allreduce_gradients
+    import nrhints_b200 as nb
+    torch.set_num_threads(2)
+    calls = []
+    real_all_reduce = dist.all_reduce
+    dist.all_reduce = lambda *a, **k: (calls.append(a[0].numel()), real_all_reduce(*a, **k))[1]
+
+    cfg = nb.NeuSModelConfig()
+    m = nb.NeuSHintRenderer(cfg)                                  # parameters on the CPU; the kernels are not touched
+    m.load_state_dict(T.make_state("init", cfg))
+    R, S = 8, 12
+    rays = synthetic_rays(R, seed=5, crop=300)
+
+    def loss_of(batch):
+        n = batch["origins"].shape[0]
+        z = batch["nears"] + (batch["fars"] - batch["nears"]) * torch.linspace(0, 1, S)[None, :]
+        out = autograd_fine.render_fine(m._autograd_weights(), batch["origins"], batch["directions"], batch["pl_positions"], z,
+                                        2.0 / S, torch.full((n, 1), 0.5), torch.full((n, 4), 0.1), torch.ones(1, 3), 1.0,
+                                        torch.exp(m.deviation_network.variance * 10.0), True)
+        return out["rgb"].square().mean() + 0.1 * (out["analytic_normals"].norm(dim=-1) - 1.0).square().mean()
+
+    loss_of(shard_rays(rays, rank, world)).backward()              # my slice of the batch
+    flat = allreduce_gradients(m)                                  # mean over ranks, one collective
+    got = [p.grad.clone() for p in m.parameters()]
+    if rank == 0:
+        m.zero_grad(set_to_none=True)
+        loss_of(rays).backward()                                   # the unsharded step
+        want = [p.grad for p in m.parameters()]
+        err = max(float((g - w).abs().max() / (w.abs().max() + 1e-12)) for g, w in zip(got, want))
+        q.put((err, calls, flat.numel(), sum(p.numel() for p in m.parameters())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_is_one_flat_collective():
+    """the data-parallel step exchanges exactly one flat gradient buffer; the averaged sharded gradient
+    equals the gradient of the unsharded batch (equal slices, mean losses)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, calls, nflat, nparams = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert calls == [nparams] and nflat == nparams, (calls, nflat, nparams)
+    assert err < 1e-4, err
