@@ -9,6 +9,10 @@
  *   extract_fields (mesh grid queries)  models/neus_hint_model.py:68-83     -> nrh_sdf_query
  *   weight_norm materialisation         fields/sdf_field.py:81-82,100-101   -> done by the caller
  *                                       (torch._weight_norm), then nrh_pack_weights
+ *   render_outside + NeRF.forward       models/neus_hint_model.py:434-473,
+ *                                       fields/nerf_density_field.py:66-89  -> inside nrh_render_forward
+ *                                       when NrhConfig.use_outside_nerf (off by default in the reference)
+ *   HashEncoding.pytorch_fwd            fields/encodings.py:306-366         -> nrh_hash_encode
  *
  * Conventions
  *  - Every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer.
@@ -20,6 +24,8 @@
  *  - Network architecture is the reference default and fixed at compile time:
  *    SDF  : Fourier(6) -> 8 x 256 softplus(beta=100), skip-concat at layer 4, heads 1 + 256
  *    Color: 361(316/325/352)-in -> 4 x 256 ReLU -> 3 sigmoid, Fourier(4) on view/light/hints
+ *    NeRF : Fourier(10) of the 4-D inverted-sphere point -> 8 x 256 ReLU, input re-concatenated after layer 4,
+ *           density head, feature head, 128-wide view/light layer (Fourier(4) of 6-D), rgb head
  *    nrh_check_config() reports anything else as NRH_ERR_UNSUPPORTED.
  */
 #ifndef NRHINTS_B200_H
@@ -32,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 2
+#define NRH_ABI_VERSION 3
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -42,6 +48,7 @@ extern "C" {
 
 #define NRH_MAX_ROUGHNESS 4
 #define NRH_MAX_SAMPLES 128      /* n_samples + n_importance (and the shadow pair) <= 128   */
+#define NRH_MAX_OUTSIDE 64       /* n_outside_samples of the outside NeRF <= 64             */
 
 /* MLP engine selection */
 #define NRH_MLP_AUTO 0
@@ -68,6 +75,8 @@ typedef struct NrhConfig {
     int32_t normalized_normals;   /* 1: NormalizedAnalytic feeds the reflectance net, 0: Analytic */
     int32_t mlp_impl;             /* NRH_MLP_*                                                */
     int32_t depth_type;           /* NRH_DEPTH_* (DepthComputationType, models/neus_hint_model.py:113-121) */
+    int32_t use_outside_nerf;     /* NeRF++ background model (models/neus_hint_model.py:137, default 0)   */
+    int32_t n_outside;            /* its samples per ray (32), <= NRH_MAX_OUTSIDE                          */
 } NrhConfig;
 
 /* Effective (weight-norm already applied) weights, torch layout W[out][in], b[out]. */
@@ -81,6 +90,17 @@ typedef struct NrhRawWeights {
     const float* col_W[5];        /* [256,Cin] [256,256]x3 [3,256]; Cin = 316 + 9*shadow + 9*n_rough*specular */
     const float* col_b[5];
     const float* variance;        /* device scalar: deviation_network.variance                */
+    /* outside NeRF (fields/nerf_density_field.py:57-64); read only when use_outside_nerf            */
+    const float* nerf_W[8];       /* pts_linears: [256,84] [256,256]x4 [256,340] [256,256]x2         */
+    const float* nerf_b[8];
+    const float* nerf_alpha_W;    /* alpha_linear   [1,256]                                          */
+    const float* nerf_alpha_b;    /* [1]                                                             */
+    const float* nerf_feat_W;     /* feature_linear [256,256]                                        */
+    const float* nerf_feat_b;
+    const float* nerf_view_W;     /* views_linears[0] [128,310] = [feature 256 | PE(view,light) 54]  */
+    const float* nerf_view_b;
+    const float* nerf_rgb_W;      /* rgb_linear [3,128]                                              */
+    const float* nerf_rgb_b;
 } NrhRawWeights;
 
 typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-235)           */
@@ -93,7 +113,9 @@ typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-2
     const float* hit_depths;      /* [R,1] nullable: required when depth_type == NRH_DEPTH_SPHERE_TRACE */
 } NrhRays;
 
-typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance */
+typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance;
+                                   * with the outside NeRF `weights` and `sampled_color` have S + n_outside entries per ray
+                                   * (the reference returns the concatenated weights, :521-524,:640) */
     float* rgb;                   /* [R,3]   */
     float* depth;                 /* [R,1]   */
     float* weights;               /* [R,S]   nullable (see the per-ray maps below)                          */
@@ -134,13 +156,14 @@ int nrh_pack_weights(const NrhConfig* cfg, const NrhRawWeights* raw, void* packe
 size_t nrh_workspace_bytes(const NrhConfig* cfg, int64_t R);
 size_t nrh_query_workspace_bytes(const NrhConfig* cfg, int64_t N);
 
-/* NeuSHintRenderer.forward.  jitter_primary [R] and jitter_shadow [R,n_shadow_samples] are the two
- * torch.rand draws of training mode (:682, :394) made by the caller; NULL = inference (no perturbation).
+/* NeuSHintRenderer.forward.  jitter_primary [R], jitter_outside [R,n_outside] (outside NeRF only) and
+ * jitter_shadow [R,n_shadow_samples] are the torch.rand draws of training mode (:682, :689, :394), made by
+ * the caller in that order; NULL = inference (no perturbation).
  * bg_rgb: device [3] or NULL.  cos_anneal = min(1, step/anneal_end) in training, 1 otherwise.
  * warmup != 0 zeroes both hints (geometry warm-up, :577-579,:617-619). */
 int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* rays, int64_t R,
-                       const float* bg_rgb, const float* jitter_primary, const float* jitter_shadow,
-                       float cos_anneal, int warmup, const NrhOutputs* out,
+                       const float* bg_rgb, const float* jitter_primary, const float* jitter_outside,
+                       const float* jitter_shadow, float cos_anneal, int warmup, const NrhOutputs* out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* SDFNetwork.sdf / .gradient / .forward on arbitrary points: pts [N,3] ->
@@ -156,6 +179,20 @@ int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, in
 int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
                      int max_iterations, float threshold, float far_limit, int check_every,
                      float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream);
+
+/* HashEncoding.pytorch_fwd (fields/encodings.py:306-366; unreachable from the reference's shipped presets, kept as a
+ * standalone operator): multi-resolution hash-grid lookup with trilinear interpolation.
+ *   pts [N,3] in [0,1]; table [n_levels * 2^log2_T, F] fp32; scalings [n_levels] fp32 (host array: floor(min_res * g^l));
+ *   out [N, n_levels * F].  Index arithmetic is the reference's: corners ceil/floor of pts*scaling as int32, hash
+ *   (x*1) ^ (y*2654435761) ^ (z*805459861) in int64 (no 32-bit wrap), mod 2^log2_T, + level * 2^log2_T; the
+ *   interpolation weight `offset = scaled - floor` goes to the CEIL corner.  F <= 8, n_levels <= 32. */
+int nrh_hash_encode(const float* pts, int64_t N, const float* table, const float* host_scalings, int n_levels,
+                    int log2_table_size, int features_per_level, float* out, void* stream);
+
+/* Gradient of nrh_hash_encode w.r.t. the table: d_table[idx] += w * d_out (fp32 atomics; d_table must be zeroed
+ * by the caller). */
+int nrh_hash_encode_backward(const float* pts, int64_t N, const float* d_out, const float* host_scalings, int n_levels,
+                             int log2_table_size, int features_per_level, float* d_table, void* stream);
 
 /* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
 int nrh_last_launch_count(void);

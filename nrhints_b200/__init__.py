@@ -4,11 +4,11 @@ Public surface (mirrors /root/reference/models/neus_hint_model.py for this path)
     NeuSHintRenderer, RenderOutput, NeuSModelConfig (+ sub-configs), RayBundle
 The compute lives in nrhints_b200/csrc (hand-written CUDA behind the C ABI in include/nrhints_b200.h).
 """
-from .config import (DepthComputationType, NeuSModelConfig, NeuSRendererConfig, NormalComputationType,
+from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NeuSRendererConfig, NormalComputationType,
                      ReflectanceNetConfig, SDFNetConfig, SingleVarianceNetConfig)
 from .rays import RayBundle
 from .renderer import NeuSHintRenderer, ReflectanceNetwork, RenderOutput, SDFNetwork, SingleVarianceNetwork
 
 __all__ = ["NeuSHintRenderer", "RenderOutput", "RayBundle", "NeuSModelConfig", "NeuSRendererConfig", "SDFNetConfig",
-           "ReflectanceNetConfig", "SingleVarianceNetConfig", "DepthComputationType", "NormalComputationType",
+           "ReflectanceNetConfig", "SingleVarianceNetConfig", "NeRFConfig", "DepthComputationType", "NormalComputationType",
            "SDFNetwork", "ReflectanceNetwork", "SingleVarianceNetwork"]

@@ -14,10 +14,13 @@ from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
 _LIB_PATH = _CSRC / "libnrhints_b200.so"
-_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "../../include/nrhints_b200.h"]
+_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu"]
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh",
+            "../../include/nrhints_b200.h"]
 
+NRH_ABI_VERSION = 3
 NRH_MAX_ROUGHNESS = 4
+NRH_MAX_OUTSIDE = 64
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
 DEPTH_TYPES = {"alpha_blending": 0, "maximum_point": 1, "sphere_tracing": 2}
 MLP_IMPLS = {"auto": NRH_MLP_AUTO, "fp32": NRH_MLP_FP32_SIMT, "tcgen05": NRH_MLP_TCGEN05}
@@ -30,6 +33,7 @@ class NrhConfig(C.Structure):
         ("shadow_hint", C.c_int32), ("specular_hint", C.c_int32), ("n_roughness", C.c_int32),
         ("roughness", C.c_float * NRH_MAX_ROUGHNESS), ("shadow_ray_offset", C.c_float),
         ("normalized_normals", C.c_int32), ("mlp_impl", C.c_int32), ("depth_type", C.c_int32),
+        ("use_outside_nerf", C.c_int32), ("n_outside", C.c_int32),
     ]
 
 
@@ -40,6 +44,11 @@ class NrhRawWeights(C.Structure):
         ("feat_W", C.c_void_p), ("feat_b", C.c_void_p),
         ("col_W", C.c_void_p * 5), ("col_b", C.c_void_p * 5),
         ("variance", C.c_void_p),
+        ("nerf_W", C.c_void_p * 8), ("nerf_b", C.c_void_p * 8),
+        ("nerf_alpha_W", C.c_void_p), ("nerf_alpha_b", C.c_void_p),
+        ("nerf_feat_W", C.c_void_p), ("nerf_feat_b", C.c_void_p),
+        ("nerf_view_W", C.c_void_p), ("nerf_view_b", C.c_void_p),
+        ("nerf_rgb_W", C.c_void_p), ("nerf_rgb_b", C.c_void_p),
     ]
 
 
@@ -63,12 +72,16 @@ EXPORTS = {
     "nrh_workspace_bytes": (C.c_size_t, [C.POINTER(NrhConfig), C.c_int64]),
     "nrh_query_workspace_bytes": (C.c_size_t, [C.POINTER(NrhConfig), C.c_int64]),
     "nrh_render_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.POINTER(NrhRays), C.c_int64,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
                                      C.POINTER(NrhOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_sdf_query": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_sphere_trace": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_hash_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "nrh_hash_encode_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

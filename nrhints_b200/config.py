@@ -7,8 +7,7 @@ interchangeable:
   SDFNetConfig                           /root/reference/fields/sdf_field.py:11-36
   ReflectanceNetConfig                   /root/reference/fields/reflectance_network.py:9-22
   SingleVarianceNetConfig                /root/reference/models/neus_hint_model.py:96-101
-The outside-NeRF config (fields/nerf_density_field.py) is out of scope:
-`use_outside_nerf=True` is rejected loudly by the renderer.
+  NeRFConfig (outside model)             /root/reference/fields/nerf_density_field.py:12-26
 """
 from dataclasses import dataclass, field
 from enum import Enum
@@ -51,6 +50,15 @@ class ReflectanceNetConfig:
 
 
 @dataclass(frozen=True)
+class NeRFConfig:
+    d_hidden: int = 256
+    n_layers: int = 8
+    multi_res: int = 10
+    multi_res_view: int = 4
+    skips: List[int] = field(default_factory=lambda: [4])
+
+
+@dataclass(frozen=True)
 class SingleVarianceNetConfig:
     init_val: float = 0.3
 
@@ -81,6 +89,7 @@ class NeuSRendererConfig:
 @dataclass(frozen=True)
 class NeuSModelConfig:
     sdf_network: SDFNetConfig = field(default_factory=SDFNetConfig)
+    outside_nerf: NeRFConfig = field(default_factory=NeRFConfig)
     deviation_network: SingleVarianceNetConfig = field(default_factory=SingleVarianceNetConfig)
     reflectance_network: ReflectanceNetConfig = field(default_factory=ReflectanceNetConfig)
     renderer: NeuSRendererConfig = field(default_factory=NeuSRendererConfig)

@@ -41,6 +41,20 @@ PackedLayout make_layout(const NrhConfig& cfg) {
     L.col_wt0a = take((size_t)256 * 256); L.col_wt0b = take((size_t)AUX_ROWS * 256); L.col_b0 = take(256);
     for (int l = 0; l < 3; ++l) { L.col_wt[l] = take((size_t)256 * 256); L.col_b[l] = take(256); }
     L.col_w4t = take((size_t)256 * 4); L.col_b4 = take(4);
+    for (int l = 0; l < NERF_LAYERS; ++l) { L.nerf_wt[l] = 0; L.nerf_b[l] = 0; }
+    L.nerf_wt5e = L.nerf_alpha_w = L.nerf_alpha_b = L.nerf_feat_wt = L.nerf_feat_b = 0;
+    L.nerf_view_wta = L.nerf_view_wtb = L.nerf_view_b = L.nerf_rgb_wt = L.nerf_rgb_b = 0;
+    if (cfg.use_outside_nerf) {
+        for (int l = 0; l < NERF_LAYERS; ++l) {
+            L.nerf_wt[l] = take((size_t)(l == 0 ? NERF_PE_PAD : 256) * 256);
+            L.nerf_b[l] = take(256);
+        }
+        L.nerf_wt5e = take((size_t)NERF_PE_PAD * 256);
+        L.nerf_alpha_w = take(256); L.nerf_alpha_b = take(4);
+        L.nerf_feat_wt = take((size_t)256 * 256); L.nerf_feat_b = take(256);
+        L.nerf_view_wta = take((size_t)256 * 256); L.nerf_view_wtb = take((size_t)NERF_VPE_PAD * 256); L.nerf_view_b = take(256);
+        L.nerf_rgb_wt = take((size_t)NERF_VIEW_H * 4); L.nerf_rgb_b = take(4);
+    }
     L.total_floats = off;
     L.tc_offset_bytes = align_up(off * sizeof(float), 1024);
     L.total_bytes = L.tc_offset_bytes + tc_packed_bytes(cfg);
@@ -95,6 +109,7 @@ struct Workspace {
     float* rayfeat;              // [RAYFEAT][R]
     float* aux_img;              // [R/128] operand images of the per-ray reflectance inputs (streamed tcgen05 path)
     float* cr; float* cg; float* cb;
+    OutsideBuffers ob;           // outside NeRF (null when off)
     float* mlp_scratch; size_t mlp_scratch_bytes;
     size_t total_bytes;
 };
@@ -123,7 +138,9 @@ Workspace carve(const NrhConfig& cfg, int64_t R, char* base, int num_sms) {
     march(w.prim); march(w.shad);
     FineBuffers& f = w.fine;
     f.sdf = take((size_t)S * R); f.gx = take((size_t)S * R); f.gy = take((size_t)S * R); f.gz = take((size_t)S * R);
-    f.w = take((size_t)S * R); f.inside = take((size_t)S * R);
+    const int n_out = cfg.use_outside_nerf ? cfg.n_outside : 0;
+    const int St = S + n_out;                                   // weights / colours carry the appended outside samples
+    f.w = take((size_t)St * R); f.inside = take((size_t)S * R);
     f.nx = take((size_t)S * R); f.ny = take((size_t)S * R); f.nz = take((size_t)S * R);
     RayState& rs = w.rs;
     rs.depth = take(R); rs.wsum = take(R); rs.vis = take(R); rs.light_dist = take(R);
@@ -133,7 +150,11 @@ Workspace carve(const NrhConfig& cfg, int64_t R, char* base, int num_sms) {
     w.ssdf = take((size_t)Ss * R); w.sgx = take((size_t)Ss * R); w.sgy = take((size_t)Ss * R); w.sgz = take((size_t)Ss * R);
     w.rayfeat = take((size_t)RAYFEAT * R);
     w.aux_img = take((size_t)((R + 127) / 128) * (TC_TILE_AUX_BYTES / sizeof(float)));
-    w.cr = take((size_t)S * R); w.cg = take((size_t)S * R); w.cb = take((size_t)S * R);
+    w.cr = take((size_t)St * R); w.cg = take((size_t)St * R); w.cb = take((size_t)St * R);
+    if (n_out > 0) {
+        w.ob.mid = take((size_t)St * R); w.ob.dist = take((size_t)St * R); w.ob.density = take((size_t)St * R);
+        w.ob.r = take((size_t)St * R); w.ob.g = take((size_t)St * R); w.ob.b = take((size_t)St * R);
+    }
     size_t sb = sdf_mlp_simt_scratch_bytes(num_sms);
     size_t tb = tc_scratch_bytes(num_sms);
     w.mlp_scratch_bytes = sb > tb ? sb : tb;
@@ -229,6 +250,7 @@ int nrh_check_config(const NrhConfig* c) {
     }
     if (c->specular_hint && (c->n_roughness < 1 || c->n_roughness > NRH_MAX_ROUGHNESS)) { set_error("n_roughness must be in [1,%d]", NRH_MAX_ROUGHNESS); return NRH_ERR_UNSUPPORTED; }
     if (c->depth_type < NRH_DEPTH_ALPHA_BLEND || c->depth_type > NRH_DEPTH_SPHERE_TRACE) { set_error("unknown depth_type %d", c->depth_type); return NRH_ERR_INVALID; }
+    if (c->use_outside_nerf && (c->n_outside < 1 || c->n_outside > NRH_MAX_OUTSIDE)) { set_error("n_outside must be in [1,%d]", NRH_MAX_OUTSIDE); return NRH_ERR_UNSUPPORTED; }
     if (c->mlp_impl < NRH_MLP_AUTO || c->mlp_impl > NRH_MLP_TCGEN05) { set_error("unknown mlp_impl %d", c->mlp_impl); return NRH_ERR_INVALID; }
     if (c->mlp_impl == NRH_MLP_TCGEN05 && !tc_available()) { set_error("tcgen05 engine not built"); return NRH_ERR_UNSUPPORTED; }
     return NRH_OK;
@@ -273,6 +295,28 @@ int nrh_pack_weights(const NrhConfig* cfg, const NrhRawWeights* raw, void* packe
     }
     if ((rc = transpose_slice(raw->col_W[4], 256, 3, 0, 256, P + L.col_w4t, 4, 0, st))) return rc;
     if ((rc = copy_rows(raw->col_b[4], 1, 3, P + L.col_b4, 4, st))) return rc;
+    if (cfg->use_outside_nerf) {           // fields/nerf_density_field.py:57-64
+        for (int l = 0; l < NERF_LAYERS; ++l) {
+            if (!raw->nerf_W[l] || !raw->nerf_b[l]) { set_error("use_outside_nerf: null outside-NeRF weight"); return NRH_ERR_INVALID; }
+            if (l == 0) { if ((rc = transpose_slice(raw->nerf_W[0], NERF_PE, 256, 0, NERF_PE, P + L.nerf_wt[0], 256, 0, st))) return rc; }
+            else if (l == NERF_SKIP + 1) {
+                if ((rc = transpose_slice(raw->nerf_W[l], NERF_PE + 256, 256, 0, NERF_PE, P + L.nerf_wt5e, 256, 0, st))) return rc;
+                if ((rc = transpose_slice(raw->nerf_W[l], NERF_PE + 256, 256, NERF_PE, 256, P + L.nerf_wt[l], 256, 0, st))) return rc;
+            } else { if ((rc = transpose_slice(raw->nerf_W[l], 256, 256, 0, 256, P + L.nerf_wt[l], 256, 0, st))) return rc; }
+            if ((rc = copy_rows(raw->nerf_b[l], 1, 256, P + L.nerf_b[l], 256, st))) return rc;
+        }
+        if (!raw->nerf_alpha_W || !raw->nerf_alpha_b || !raw->nerf_feat_W || !raw->nerf_feat_b || !raw->nerf_view_W ||
+            !raw->nerf_view_b || !raw->nerf_rgb_W || !raw->nerf_rgb_b) { set_error("use_outside_nerf: null outside-NeRF head weight"); return NRH_ERR_INVALID; }
+        if ((rc = copy_rows(raw->nerf_alpha_W, 1, 256, P + L.nerf_alpha_w, 256, st))) return rc;
+        k_copy_scalar<<<1, 1, 0, st>>>(raw->nerf_alpha_b, P + L.nerf_alpha_b); NRH_LAUNCH_CHECK();
+        if ((rc = transpose_slice(raw->nerf_feat_W, 256, 256, 0, 256, P + L.nerf_feat_wt, 256, 0, st))) return rc;
+        if ((rc = copy_rows(raw->nerf_feat_b, 1, 256, P + L.nerf_feat_b, 256, st))) return rc;
+        if ((rc = transpose_slice(raw->nerf_view_W, 256 + NERF_VPE, NERF_VIEW_H, 0, 256, P + L.nerf_view_wta, 256, 0, st))) return rc;
+        if ((rc = transpose_slice(raw->nerf_view_W, 256 + NERF_VPE, NERF_VIEW_H, 256, NERF_VPE, P + L.nerf_view_wtb, 256, 0, st))) return rc;
+        if ((rc = copy_rows(raw->nerf_view_b, 1, NERF_VIEW_H, P + L.nerf_view_b, 256, st))) return rc;
+        if ((rc = transpose_slice(raw->nerf_rgb_W, NERF_VIEW_H, 3, 0, NERF_VIEW_H, P + L.nerf_rgb_wt, 4, 0, st))) return rc;
+        if ((rc = copy_rows(raw->nerf_rgb_b, 1, 3, P + L.nerf_rgb_b, 4, st))) return rc;
+    }
     if (tc_available()) { if ((rc = tc_pack(*cfg, L, *raw, packed, st))) return rc; }
     return NRH_OK;
 }
@@ -340,8 +384,8 @@ int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* orig
 }
 
 int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* rays, int64_t R,
-                       const float* bg_rgb, const float* jitter_primary, const float* jitter_shadow,
-                       float cos_anneal, int warmup, const NrhOutputs* out,
+                       const float* bg_rgb, const float* jitter_primary, const float* jitter_outside,
+                       const float* jitter_shadow, float cos_anneal, int warmup, const NrhOutputs* out,
                        void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     int rc = nrh_check_config(cfg); if (rc) return rc;
@@ -375,15 +419,25 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     const bool streamed = resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
     if ((rc = run_sdf(*cfg, packed, L, P, (int64_t)S * R, w.fine.sdf, w.fine.gx, w.fine.gy, w.fine.gz, 1, w.feat,
                       w.mlp_scratch, w.mlp_scratch_bytes, sms, st, streamed))) return rc;
+    // ---- outside NeRF on the merged sample set (render_outside, :716-724): background alpha / colour per section ----
+    const int n_out = cfg->use_outside_nerf ? cfg->n_outside : 0;
+    const int St = S + n_out;
+    if (n_out > 0) {
+        if ((rc = launch_outside_setup(R, w.prim, cur, S, n, n_out, rays->fars, jitter_outside, sample_dist, w.ob, st))) return rc;
+        const float* oo[3] = {w.prim.o[0], w.prim.o[1], w.prim.o[2]};
+        const float* dd[3] = {w.prim.d[0], w.prim.d[1], w.prim.d[2]};
+        if ((rc = nerf_mlp_simt(Pf, L, oo, dd, rays->pl_positions, w.ob.mid, R, (int64_t)St * R, w.ob.density, w.ob.r, w.ob.g,
+                                w.ob.b, sms, st))) return rc;
+    }
     const bool do_shadow = cfg->shadow_hint && !warmup;
     if ((rc = launch_composite_primary(R, w.prim, cur, S, sample_dist, inv_s, cos_anneal, w.fine, w.rs, rays->pl_positions,
                                        do_shadow, w.shad, ns, cfg->shadow_ray_offset, jitter_shadow,
-                                       cfg->depth_type, rays->hit_points, rays->hit_depths, st))) return rc;
+                                       cfg->depth_type, rays->hit_points, rays->hit_depths, n_out, w.ob, st))) return rc;
     if ((rc = launch_specular_cue(R, *cfg, w.rs, rays->pl_positions, rays->directions, warmup, st))) return rc;
     // ---- per-sample geometry block of the RenderOutput, ray-major: final from here on (95 % of the output bytes) ----
     {
         const float* s1[4] = {w.fine.w, nullptr, nullptr, nullptr};
-        if (out->weights && (rc = launch_to_ray_major(s1, 1, false, R, S, out->weights, st))) return rc;
+        if (out->weights && (rc = launch_to_ray_major(s1, 1, false, R, St, out->weights, st))) return rc;
         const float* s2[4] = {w.fine.inside, nullptr, nullptr, nullptr};
         if (out->inside_sphere && (rc = launch_to_ray_major(s2, 1, false, R, S, out->inside_sphere, st))) return rc;
         const float* s3[4] = {w.fine.gx, w.fine.gy, w.fine.gz, nullptr};
@@ -418,7 +472,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
                         w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
     if ((rc = launch_final_rgb(R, S, w.fine, w.rs, w.cr, w.cg, w.cb, bg_rgb, out->rgb, out->depth,
                                cfg->shadow_hint ? out->visibilities : nullptr, out->normal_map, out->normalized_normal_map,
-                               cfg->specular_hint ? out->specular_cue_ray : nullptr, cfg->n_roughness, st))) return rc;
+                               cfg->specular_hint ? out->specular_cue_ray : nullptr, cfg->n_roughness, n_out, w.ob, st))) return rc;
     // ---- late ray-major RenderOutput fields ---------------------------------------------------------------------
     if (out->z_shadow && do_shadow) {
         const float* s7[4] = {w.shad.z[scur], nullptr, nullptr, nullptr};
@@ -426,7 +480,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     }
     if (out->sampled_color) {
         const float* s8[4] = {w.cr, w.cg, w.cb, nullptr};
-        if ((rc = launch_to_ray_major(s8, 3, false, R, S, out->sampled_color, st))) return rc;
+        if ((rc = launch_to_ray_major(s8, 3, false, R, St, out->sampled_color, st))) return rc;
     }
     if (out->inv_s) { k_copy_scalar<<<1, 1, 0, st>>>(inv_s, out->inv_s); NRH_LAUNCH_CHECK(); }
     return NRH_OK;

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "nrh_common.cuh"
+#include "ray_math.cuh"
 
 namespace nrh {
 namespace {
@@ -397,6 +398,141 @@ color_mlp_kernel(ColParams P, Strided3 pts, Strided3 nrm, const float* __restric
 
 constexpr size_t col_smem_bytes() { return (size_t)(256 * TMP + 2 * KC * 256) * sizeof(float); }
 
+// ===========================================================================================
+// Outside NeRF (NeRF.forward, /root/reference/fields/nerf_density_field.py:66-89, called from
+// render_outside, models/neus_hint_model.py:434-473).  Non-default background model: fp32 FFMA only.
+// ===========================================================================================
+struct NerfParams {
+    const float* wt[NERF_LAYERS]; const float* b[NERF_LAYERS]; const float* wt5e;
+    const float* alpha_w; const float* alpha_b; const float* feat_wt; const float* feat_b;
+    const float* view_wta; const float* view_wtb; const float* view_b; const float* rgb_wt; const float* rgb_b;
+    const float* o[3]; const float* d[3]; const float* pl;       // rays: SoA origins / directions [R], lights [R,3]
+};
+
+__device__ __forceinline__ void relu_store(const Acc& acc, float* act, int lane, int tp) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const int n = out_index(lane, o);
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = fmaxf(acc.v[i][o], 0.f);
+        store_col8(act + n * TMP + tp * 8, h);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+nerf_mlp_kernel(NerfParams P, const float* __restrict__ mid, int64_t R, int64_t N, float* __restrict__ density,
+                float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb) {
+    extern __shared__ __align__(16) float smem[];
+    float* act = smem;                        // [256][TMP]
+    float* pe = act + 256 * TMP;              // [88][TMP]: PE(10) of the 4-D point; later [56][TMP]: PE(4) of (view, light)
+    float* wstage = pe + NERF_PE_PAD * TMP;   // [2][KC*256]
+    const int tid = threadIdx.x, lane = tid & 31, tp = tid >> 5;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * TM;
+        // ---- inverted-sphere point and its Fourier encoding: rows [x(4) | sin (d-major, k-minor)(40) | cos(40) | 0(4)] ----
+        {
+            const int pt = tid & 63, q = tid >> 6;            // q = coordinate of the 4-D point
+            const int64_t p = p0 + pt;
+            float x = 0.f;
+            if (p < N) {
+                const int64_t r = p % R;
+                const float o[3] = {P.o[0][r], P.o[1][r], P.o[2][r]}, d[3] = {P.d[0][r], P.d[1][r], P.d[2][r]};
+                float p4[4];
+                outside_point(o, d, mid[p], p4);
+                x = p4[q];
+            }
+            pe[q * TMP + pt] = x;
+            pe[(NERF_PE + q) * TMP + pt] = 0.f;
+            float f = 1.0f;
+#pragma unroll
+            for (int k = 0; k < NERF_FREQ; ++k) {
+                const float s = x * f;
+                pe[(4 + q * NERF_FREQ + k) * TMP + pt] = sinf(s);
+                pe[(4 + 4 * NERF_FREQ + q * NERF_FREQ + k) * TMP + pt] = sinf(s + 1.57079637050628662109375f);
+                f *= 2.0f;
+            }
+        }
+        __syncthreads();
+        // ---- trunk: 8 x 256 ReLU; layer 5 consumes cat([pe, h]) ----
+        Acc acc;
+#pragma unroll 1
+        for (int l = 0; l < NERF_LAYERS; ++l) {
+            acc_set_bias(acc, P.b[l], lane);
+            if (l == 0) gemm_accumulate(acc, pe, NERF_PE_PAD, P.wt[0], wstage);
+            else {
+                if (l == NERF_SKIP + 1) gemm_accumulate(acc, pe, NERF_PE_PAD, P.wt5e, wstage);
+                gemm_accumulate(acc, act, 256, P.wt[l], wstage);
+            }
+            relu_store(acc, act, lane, tp);
+            __syncthreads();
+        }
+        // ---- density head (raw; softplus / alpha are applied by the compositor) + (view, light) encoding into `pe` ----
+        {
+            const int pt = tid & 63, part = tid >> 6;
+            float s = 0.f;
+#pragma unroll 8
+            for (int k = part * 64; k < part * 64 + 64; ++k) s = fmaf(act[k * TMP + pt], __ldg(P.alpha_w + k), s);
+            wstage[part * TM + pt] = s;
+            const int64_t p = p0 + pt;
+            // 6-D input [view(3), light(3)]: thread group `part` encodes coordinates part and part + 4 (< 6)
+            for (int c = part; c < 6; c += 4) {
+                float x = 0.f;
+                if (p < N) { const int64_t r = p % R; x = (c < 3) ? P.d[c][r] : P.pl[r * 3 + (c - 3)]; }
+                pe[c * TMP + pt] = x;
+                float f = 1.0f;
+#pragma unroll
+                for (int k = 0; k < NERF_VFREQ; ++k) {
+                    const float sv = x * f;
+                    pe[(6 + c * NERF_VFREQ + k) * TMP + pt] = sinf(sv);
+                    pe[(6 + 6 * NERF_VFREQ + c * NERF_VFREQ + k) * TMP + pt] = sinf(sv + 1.57079637050628662109375f);
+                    f *= 2.0f;
+                }
+            }
+            if (part < 2) pe[(NERF_VPE + part) * TMP + pt] = 0.f;
+            __syncthreads();
+            if (part == 0) {
+                const float tot = ((wstage[pt] + wstage[TM + pt]) + (wstage[2 * TM + pt] + wstage[3 * TM + pt])) + __ldg(P.alpha_b);
+                if (p < N) density[p] = tot;
+            }
+            __syncthreads();
+        }
+        // ---- feature head (linear) -> act ----
+        acc_set_bias(acc, P.feat_b, lane);
+        gemm_accumulate(acc, act, 256, P.feat_wt, wstage);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int n = out_index(lane, o);
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = acc.v[i][o];
+            store_col8(act + n * TMP + tp * 8, h);
+        }
+        __syncthreads();
+        // ---- view/light layer: relu(W [feature | PE(view, light)] + b), 128 wide (columns 128..255 are zero weights) ----
+        acc_set_bias(acc, P.view_b, lane);
+        gemm_accumulate(acc, act, 256, P.view_wta, wstage);
+        gemm_accumulate(acc, pe, NERF_VPE_PAD, P.view_wtb, wstage);
+        relu_store(acc, act, lane, tp);
+        __syncthreads();
+        // ---- rgb head + sigmoid (render_outside :460) ----
+        {
+            const int pt = tid & 63, ch = tid >> 6;
+            if (ch < 3) {
+                float s = __ldg(P.rgb_b + ch);
+                for (int k = 0; k < NERF_VIEW_H; ++k) s = fmaf(act[k * TMP + pt], __ldg(P.rgb_wt + k * 4 + ch), s);
+                const float c = 1.0f / (1.0f + expf(-s));
+                const int64_t p = p0 + pt;
+                if (p < N) (ch == 0 ? cr : (ch == 1 ? cg : cb))[p] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+constexpr size_t nerf_smem_bytes() { return (size_t)(256 * TMP + NERF_PE_PAD * TMP + 2 * KC * 256) * sizeof(float); }
+
 }  // namespace
 
 size_t sdf_mlp_simt_scratch_bytes(int num_sms) {
@@ -444,6 +580,28 @@ int color_mlp_simt(const float* packed, const PackedLayout& L, Strided3 pts, Str
     const size_t smem = col_smem_bytes();
     NRH_CUDA_CHECK(cudaFuncSetAttribute(color_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     color_mlp_kernel<<<grid, NT, smem, st>>>(P, pts, normals, feat, rayfeat, R, N, cr, cg, cb);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int nerf_mlp_simt(const float* packed, const PackedLayout& L, const float* const o[3], const float* const d[3], const float* pl,
+                  const float* mid, int64_t R, int64_t N, float* density, float* cr, float* cg, float* cb, int num_sms,
+                  cudaStream_t st) {
+    if (N <= 0) return NRH_OK;
+    NerfParams P;
+    for (int l = 0; l < NERF_LAYERS; ++l) { P.wt[l] = packed + L.nerf_wt[l]; P.b[l] = packed + L.nerf_b[l]; }
+    P.wt5e = packed + L.nerf_wt5e;
+    P.alpha_w = packed + L.nerf_alpha_w; P.alpha_b = packed + L.nerf_alpha_b;
+    P.feat_wt = packed + L.nerf_feat_wt; P.feat_b = packed + L.nerf_feat_b;
+    P.view_wta = packed + L.nerf_view_wta; P.view_wtb = packed + L.nerf_view_wtb; P.view_b = packed + L.nerf_view_b;
+    P.rgb_wt = packed + L.nerf_rgb_wt; P.rgb_b = packed + L.nerf_rgb_b;
+    for (int c = 0; c < 3; ++c) { P.o[c] = o[c]; P.d[c] = d[c]; }
+    P.pl = pl;
+    int64_t ntiles = (N + TM - 1) / TM;
+    int grid = (int)(ntiles < (int64_t)num_sms * 2 ? ntiles : (int64_t)num_sms * 2);
+    const size_t smem = nerf_smem_bytes();
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nerf_mlp_kernel<<<grid, NT, smem, st>>>(P, mid, R, N, density, cr, cg, cb);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

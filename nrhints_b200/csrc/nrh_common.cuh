@@ -22,6 +22,16 @@ constexpr int COL_PE3 = 27;         // 3 * (2*4 + 1)
 constexpr int AUX_ROWS = 112;       // non-feature reflectance inputs: 3+27+3+27+9+36 = 105, padded
 constexpr int AUX_PTS = 0, AUX_VIEW = 3, AUX_NORMAL = 30, AUX_LIGHT = 33, AUX_VIS = 60, AUX_SPEC = 69;
 constexpr int RAYFEAT = 99;         // per-ray encoded inputs: PE(view) 27, PE(light) 27, PE(vis) 9, PE(spec) 36
+// outside NeRF (fields/nerf_density_field.py:12-64, reference defaults)
+constexpr int NERF_LAYERS = 8;
+constexpr int NERF_SKIP = 4;        // the encoded point is re-concatenated (in front) after layer 4 -> layer 5 has 340 inputs
+constexpr int NERF_FREQ = 10;
+constexpr int NERF_PE = 84;         // 4 * (2*10 + 1)
+constexpr int NERF_PE_PAD = 88;
+constexpr int NERF_VFREQ = 4;
+constexpr int NERF_VPE = 54;        // 6 * (2*4 + 1)
+constexpr int NERF_VPE_PAD = 56;
+constexpr int NERF_VIEW_H = 128;    // width of the view/light layer
 
 // ---- packed weight buffer (fp32 section; offsets in floats) --------------------------------
 struct PackedLayout {
@@ -41,6 +51,13 @@ struct PackedLayout {
     size_t col_wt[3], col_b[3];      // hidden layers 1..3
     size_t col_w4t;                  // [256][4]
     size_t col_b4;                   // [4]
+    // outside NeRF (present only when cfg.use_outside_nerf): trunk Wt[l] [Kpad][256] (layer 0: 88 rows; layer 5: the 256
+    // hidden inputs, its 84 encoded-point inputs live in nerf_wt5e [88][256]), heads, view layer split [feature | PE]
+    size_t nerf_wt[NERF_LAYERS], nerf_b[NERF_LAYERS], nerf_wt5e;
+    size_t nerf_alpha_w, nerf_alpha_b;       // [256], [1]
+    size_t nerf_feat_wt, nerf_feat_b;        // [256][256], [256]
+    size_t nerf_view_wta, nerf_view_wtb, nerf_view_b;   // [256][256] (128 real columns), [56][256], [256]
+    size_t nerf_rgb_wt, nerf_rgb_b;          // [128][4], [4]
     size_t total_floats;
     // tcgen05 section (bytes from the start of the packed buffer); 0 if absent
     size_t tc_offset_bytes;
@@ -89,5 +106,11 @@ size_t sdf_mlp_simt_scratch_bytes(int num_sms);
 int color_mlp_simt(const float* packed, const PackedLayout& L, Strided3 pts, Strided3 normals,
                    const float* feat, const float* rayfeat, int64_t R, int64_t N,
                    float* cr, float* cg, float* cb, int num_sms, cudaStream_t st);
+
+// Outside NeRF over N = St*R sample-major section mid-points (p = j*R + r) of the merged sample set: the kernel forms the
+// inverted-sphere point from (o, d, mid) itself.  o/d: SoA [R] each; pl: [R,3]; outputs density[N] (raw), c{r,g,b}[N] (sigmoid).
+int nerf_mlp_simt(const float* packed, const PackedLayout& L, const float* const o[3], const float* const d[3], const float* pl,
+                  const float* mid, int64_t R, int64_t N, float* density, float* cr, float* cg, float* cb, int num_sms,
+                  cudaStream_t st);
 
 }  // namespace nrh

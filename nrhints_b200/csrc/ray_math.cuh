@@ -10,6 +10,8 @@
 //   get_visibility            :373-432    -> nrh::shadow_ray_init / nrh::shadow_transmittance
 //   render_core               :475-651    -> nrh::composite_primary / nrh::specular_cue
 //   forward (coarse z)        :673-683    -> nrh::coarse_z
+//   forward (outside z)       :677-694    -> nrh::outside_z
+//   render_outside            :434-473    -> nrh::outside_sections / nrh::outside_point / nrh::outside_alpha
 // Encoding: /root/reference/fields/encodings.py:168-176 -> nrh::fourier_encode
 //
 // All per-ray arrays are "sample-major": element j of ray r lives at base[j*stride + r]
@@ -208,6 +210,70 @@ NRH_HD float neus_alpha(float sdf, float gx, float gy, float gz, const float d[3
     return fminf(fmaxf(a, 0.0f), 1.0f);
 }
 
+// ------------------------------------------------------------------------------------------
+// outside (NeRF++) model: sample positions beyond `far`, inverse-depth spaced (forward :677-694)
+//   zo = linspace(1e-3, 1 - 1/(n_out+1), n_out); training: stratified jitter inside [lower, upper] bins;
+//   z_out = far / flip(zo) + 1/n_samples.  `zo` (n_out entries) receives z_out in ascending order.
+// ------------------------------------------------------------------------------------------
+NRH_HD float linspace_general(float start, float end, int j, int n) {       // torch.linspace, scalar formula
+    if (n <= 1) return start;
+    const float step = (end - start) / (float)(n - 1);
+    return (j < n / 2) ? start + step * (float)j : end - step * (float)(n - 1 - j);
+}
+
+NRH_HD void outside_z(float far, int n_samples, int n_out, bool has_jitter, CSoA jitter, float* zo) {
+    const float start = 1e-3f, end = (float)(1.0 - 1.0 / ((double)n_out + 1.0));
+    for (int j = 0; j < n_out; ++j) zo[j] = linspace_general(start, end, j, n_out);
+    if (has_jitter) {
+        float prev = zo[0];
+        for (int j = 0; j < n_out; ++j) {
+            const float cur = zo[j];
+            const float next = (j + 1 < n_out) ? zo[j + 1] : cur;
+            const float lower = (j == 0) ? cur : 0.5f * (cur + prev);
+            const float upper = (j + 1 < n_out) ? 0.5f * (next + cur) : cur;
+            prev = cur;
+            zo[j] = lower + (upper - lower) * jitter[j];
+        }
+    }
+    const float add = (float)(1.0 / (double)n_samples);
+    // flip, then far / . + 1/n
+    for (int j = 0; j < n_out / 2; ++j) { const float t = zo[j]; zo[j] = zo[n_out - 1 - j]; zo[n_out - 1 - j] = t; }
+    for (int j = 0; j < n_out; ++j) zo[j] = far / zo[j] + add;
+    // torch.sort of the concatenation follows; the run is ascending whenever far > 0 -- make it so in any case
+    for (int i = 1; i < n_out; ++i) {
+        const float v = zo[i]; int k = i - 1;
+        while (k >= 0 && zo[k] > v) { zo[k + 1] = zo[k]; --k; }
+        zo[k + 1] = v;
+    }
+}
+
+// z_feed = sort(cat(z[S], z_out[n_out])); section lengths (last = sample_dist) and mid-points (render_outside :441-444)
+NRH_HD void outside_sections(int S, CSoA z, int n_out, const float* zo, float sample_dist, SoA dist_out, SoA mid_out) {
+    int a = 0, b = 0;
+    float prev = 0.f;
+    const int St = S + n_out;
+    for (int i = 0; i < St; ++i) {
+        float cur;
+        if (b >= n_out || (a < S && z[a] <= zo[b])) { cur = z[a]; ++a; } else { cur = zo[b]; ++b; }
+        if (i > 0) { const float dd = cur - prev; dist_out[i - 1] = dd; mid_out[i - 1] = prev + dd * 0.5f; }
+        prev = cur;
+    }
+    dist_out[St - 1] = sample_dist; mid_out[St - 1] = prev + sample_dist * 0.5f;
+}
+
+// inverted-sphere parametrisation of a section mid-point (render_outside :447-450)
+NRH_HD void outside_point(const float o[3], const float d[3], float mid, float p4[4]) {
+    const float x = o[0] + d[0] * mid, y = o[1] + d[1] * mid, z = o[2] + d[2] * mid;
+    const float dis = fminf(fmaxf(norm3(x, y, z), 1.0f), 1e10f);
+    p4[0] = x / dis; p4[1] = y / dis; p4[2] = z / dis; p4[3] = 1.0f / dis;
+}
+
+// alpha = 1 - exp(-softplus(density) * dist)   (render_outside :461; F.softplus beta 1, threshold 20)
+NRH_HD float outside_alpha(float density, float dist) {
+    const float sp = density > 20.0f ? density : log1pf(expf(density));
+    return 1.0f - expf(-sp * dist);
+}
+
 struct PrimaryComposite {
     float wsum, depth, nsum[3];
     float max_w, max_mid;          // largest weight and its section mid-point (first maximum, like torch.argmax)
@@ -215,9 +281,13 @@ struct PrimaryComposite {
 
 // weights, inside mask, normals, depth (render_core :508-533, :583-587).
 // sdf/grad are the fine-pass MLP outputs at the section mid-points.
+// With the outside model (n_out > 0; bg_density / bg_dist hold S + n_out entries from render_outside) the NeuS alpha is
+// replaced by the background alpha outside the unit sphere and the n_out far samples are appended (:517-519);
+// w_out then has S + n_out entries, depth / normals still use the first S (`neus_weights`, :525).
 NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], int S, CSoA z, float last_dist,
                                           CSoA sdf, CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal,
-                                          SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz) {
+                                          SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz,
+                                          int n_out = 0, CSoA bg_density = CSoA{nullptr, 0}, CSoA bg_dist = CSoA{nullptr, 0}) {
     PrimaryComposite r; r.wsum = 0.f; r.depth = 0.f; r.nsum[0] = r.nsum[1] = r.nsum[2] = 0.f;
     r.max_w = -1.f; r.max_mid = 0.f;
     float T = 1.0f;
@@ -225,17 +295,26 @@ NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], in
         float dist, mid; section(z, j, S, last_dist, dist, mid);
         const float px = o[0] + d[0] * mid, py = o[1] + d[1] * mid, pz = o[2] + d[2] * mid;
         const float g0 = gx[j], g1 = gy[j], g2 = gz[j];
-        const float a = neus_alpha(sdf[j], g0, g1, g2, d, dist, inv_s, cos_anneal);
+        float a = neus_alpha(sdf[j], g0, g1, g2, d, dist, inv_s, cos_anneal);
+        const float inside = norm3(px, py, pz) < 1.0f ? 1.0f : 0.0f;
+        if (n_out > 0) a = a * inside + outside_alpha(bg_density[j], bg_dist[j]) * (1.0f - inside);
         const float w = a * T;
         T = T * (1.0f - a + 1e-7f);
         w_out[j] = w;
-        inside_out[j] = norm3(px, py, pz) < 1.0f ? 1.0f : 0.0f;
+        inside_out[j] = inside;
         const float gn = fmaxf(norm3(g0, g1, g2), 1e-12f);       // F.normalize eps
         const float n0 = g0 / gn, n1 = g1 / gn, n2 = g2 / gn;
         nx[j] = n0; ny[j] = n1; nz[j] = n2;
         if (w > r.max_w) { r.max_w = w; r.max_mid = mid; }
         r.wsum += w; r.depth += mid * w;
         r.nsum[0] += n0 * w; r.nsum[1] += n1 * w; r.nsum[2] += n2 * w;
+    }
+    for (int j = S; j < S + n_out; ++j) {
+        const float a = outside_alpha(bg_density[j], bg_dist[j]);
+        const float w = a * T;
+        T = T * (1.0f - a + 1e-7f);
+        w_out[j] = w;
+        r.wsum += w;
     }
     return r;
 }

@@ -154,7 +154,8 @@ __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, flo
                                     const float* __restrict__ inv_s_ptr, float cos_anneal, FineBuffers f,
                                     RayState rs, const float* __restrict__ pl, bool do_shadow, MarchState sh,
                                     int n_shadow, float shadow_offset, const float* __restrict__ jitter_shadow,
-                                    int depth_type, const float* __restrict__ hit_pts, const float* __restrict__ hit_depth) {
+                                    int depth_type, const float* __restrict__ hit_pts, const float* __restrict__ hit_depth,
+                                    int n_out, OutsideBuffers ob) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= R) return;
     float o[3], d[3];
@@ -162,7 +163,8 @@ __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, flo
     const float inv_s = inv_s_ptr[0];
     PrimaryComposite pc = composite_primary(o, d, S, CSoA{m.z[cur] + r, R}, last_dist, CSoA{f.sdf + r, R},
                                             CSoA{f.gx + r, R}, CSoA{f.gy + r, R}, CSoA{f.gz + r, R}, inv_s, cos_anneal,
-                                            SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R});
+                                            SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R},
+                                            n_out, CSoA{n_out > 0 ? ob.density + r : nullptr, R}, CSoA{n_out > 0 ? ob.dist + r : nullptr, R});
     float hit[3], hn[3];
     float depth = pc.depth;                                              // AlphaBlend (:530-533)
     if (depth_type == NRH_DEPTH_MAX_WEIGHT) depth = pc.max_mid;           // MaximalWeightPoint (:534-538)
@@ -184,6 +186,17 @@ __global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, flo
         for (int c = 0; c < 3; ++c) { sh.o[c][r] = l[c]; sh.d[c][r] = sd[c]; }
         for (int j = 0; j < n_shadow; ++j) write_points(l, sd, z[j], (int64_t)j * R + r, sh.px, sh.py, sh.pz);
     }
+}
+
+// ---- outside NeRF: sample positions beyond `far`, merged with the primary samples; section lengths / mid-points ----
+__global__ void k_outside_setup(int64_t R, MarchState m, int cur, int S, int n_samples, int n_out, const float* __restrict__ fars,
+                                const float* __restrict__ jitter_outside, float sample_dist, OutsideBuffers ob) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float zo[NRH_MAX_OUTSIDE];
+    outside_z(fars[r], n_samples, n_out, jitter_outside != nullptr,
+              CSoA{jitter_outside ? jitter_outside + r * (int64_t)n_out : nullptr, 1}, zo);
+    outside_sections(S, CSoA{m.z[cur] + r, R}, n_out, zo, sample_dist, SoA{ob.dist + r, R}, SoA{ob.mid + r, R});
 }
 
 // ---- specular cue of the hit point (needs only the primary compositor's hit point / normal) --------------------
@@ -251,10 +264,13 @@ __global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, i
 }
 
 // ---- rgb = sum_j w_j c_j + bg (1 - sum w) ---------------------------------------------------------------
-__global__ void k_final_rgb(int64_t R, int S, FineBuffers f, RayState rs, const float* __restrict__ cr,
-                            const float* __restrict__ cg, const float* __restrict__ cb, const float* __restrict__ bg,
+// With the outside NeRF (n_out > 0) the sampled colour is blended with the background colour outside the unit sphere and the
+// n_out far samples are appended (render_core :630-633); the blended colours are written back to cr/cg/cb ([(S+n_out)*R]).
+__global__ void k_final_rgb(int64_t R, int S, FineBuffers f, RayState rs, float* __restrict__ cr,
+                            float* __restrict__ cg, float* __restrict__ cb, const float* __restrict__ bg,
                             float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ vis_out,
-                            float* __restrict__ nmap, float* __restrict__ nnmap, float* __restrict__ spec_ray, int n_rough) {
+                            float* __restrict__ nmap, float* __restrict__ nnmap, float* __restrict__ spec_ray, int n_rough,
+                            int n_out, OutsideBuffers ob) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= R) return;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -263,12 +279,25 @@ __global__ void k_final_rgb(int64_t R, int S, FineBuffers f, RayState rs, const 
     for (int j = 0; j < S; ++j) {
         const int64_t i = (int64_t)j * R + r;
         const float w = f.w[i];
-        a0 += cr[i] * w; a1 += cg[i] * w; a2 += cb[i] * w;
+        float c0 = cr[i], c1 = cg[i], c2 = cb[i];
+        if (n_out > 0) {
+            const float ins = f.inside[i], ou = 1.0f - ins;
+            c0 = c0 * ins + ob.r[i] * ou; c1 = c1 * ins + ob.g[i] * ou; c2 = c2 * ins + ob.b[i] * ou;
+            cr[i] = c0; cg[i] = c1; cb[i] = c2;
+        }
+        a0 += c0 * w; a1 += c1 * w; a2 += c2 * w;
         if (maps) {                                   // einsum('...ij,...i,...i->...j', normals, weights, inside_sphere)
             const float wi = w * f.inside[i];
             m[0] += f.gx[i] * wi; m[1] += f.gy[i] * wi; m[2] += f.gz[i] * wi;
             mn[0] += f.nx[i] * wi; mn[1] += f.ny[i] * wi; mn[2] += f.nz[i] * wi;
         }
+    }
+    for (int j = S; j < S + n_out; ++j) {
+        const int64_t i = (int64_t)j * R + r;
+        const float w = f.w[i];
+        const float c0 = ob.r[i], c1 = ob.g[i], c2 = ob.b[i];
+        cr[i] = c0; cg[i] = c1; cb[i] = c2;
+        a0 += c0 * w; a1 += c1 * w; a2 += c2 * w;
     }
     if (nmap) { nmap[r * 3 + 0] = m[0]; nmap[r * 3 + 1] = m[1]; nmap[r * 3 + 2] = m[2]; }
     if (nnmap) { nnmap[r * 3 + 0] = mn[0]; nnmap[r * 3 + 1] = mn[1]; nnmap[r * 3 + 2] = mn[2]; }
@@ -346,9 +375,18 @@ int launch_sections_only(int64_t R, const MarchState& m, int cur, int S, float l
 int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, float last_dist, const float* inv_s,
                              float cos_anneal, const FineBuffers& f, const RayState& rs, const float* pl, bool do_shadow,
                              const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow,
-                             int depth_type, const float* hit_pts, const float* hit_depth, cudaStream_t st) {
+                             int depth_type, const float* hit_pts, const float* hit_depth, int n_out, const OutsideBuffers& ob,
+                             cudaStream_t st) {
     k_composite_primary<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, last_dist, inv_s, cos_anneal, f, rs, pl, do_shadow, sh,
-                                                       n_shadow, shadow_offset, jitter_shadow, depth_type, hit_pts, hit_depth);
+                                                       n_shadow, shadow_offset, jitter_shadow, depth_type, hit_pts, hit_depth,
+                                                       n_out, ob);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int launch_outside_setup(int64_t R, const MarchState& m, int cur, int S, int n_samples, int n_out, const float* fars,
+                         const float* jitter_outside, float sample_dist, const OutsideBuffers& ob, cudaStream_t st) {
+    k_outside_setup<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, n_samples, n_out, fars, jitter_outside, sample_dist, ob);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }
@@ -376,10 +414,11 @@ int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int
     return NRH_OK;
 }
 
-int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, const float* cr, const float* cg,
-                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
-                     float* spec_ray, int n_rough, cudaStream_t st) {
-    k_final_rgb<<<blocks_for(R), TPB, 0, st>>>(R, S, f, rs, cr, cg, cb, bg, rgb, depth, vis_out, nmap, nnmap, spec_ray, n_rough);
+int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, float* cr, float* cg,
+                     float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
+                     float* spec_ray, int n_rough, int n_out, const OutsideBuffers& ob, cudaStream_t st) {
+    k_final_rgb<<<blocks_for(R), TPB, 0, st>>>(R, S, f, rs, cr, cg, cb, bg, rgb, depth, vis_out, nmap, nnmap, spec_ray, n_rough,
+                                               n_out, ob);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -18,6 +18,11 @@ struct FineBuffers {                  // fine pass of the primary march, [S*R] e
     float* w; float* inside; float* nx; float* ny; float* nz;   // compositor outputs
 };
 
+struct OutsideBuffers {               // outside NeRF, [(S + n_out) * R] each (p = j*R + r); all null when the model is off
+    float* mid; float* dist;          // section mid-points / lengths of the merged sample set (render_outside :441-444)
+    float* density; float* r; float* g; float* b;   // NeRF outputs (raw density, sigmoid colour)
+};
+
 struct RayState {                     // per-ray scalars, [R] each
     float* depth; float* wsum; float* hit[3]; float* hitn[3]; float* vis; float* light_dist;
     float* spec[NRH_MAX_ROUGHNESS];
@@ -30,7 +35,10 @@ int launch_sections_only(int64_t R, const MarchState& m, int cur, int S, float l
 int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, float last_dist, const float* inv_s,
                              float cos_anneal, const FineBuffers& f, const RayState& rs, const float* pl, bool do_shadow,
                              const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow,
-                             int depth_type, const float* hit_pts, const float* hit_depth, cudaStream_t st);
+                             int depth_type, const float* hit_pts, const float* hit_depth, int n_out, const OutsideBuffers& ob,
+                             cudaStream_t st);
+int launch_outside_setup(int64_t R, const MarchState& m, int cur, int S, int n_samples, int n_out, const float* fars,
+                         const float* jitter_outside, float sample_dist, const OutsideBuffers& ob, cudaStream_t st);
 int launch_sphere_step(int64_t R, const float* dirs, const float* sdf, float* pts, float* depth, float threshold, float far_limit,
                        int* moving, cudaStream_t st);
 int launch_specular_cue(int64_t R, const NrhConfig& cfg, const RayState& rs, const float* pl, const float* dirs, int warmup, cudaStream_t st);
@@ -38,9 +46,9 @@ int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,
                       float* rayfeat, unsigned char* aux_img, cudaStream_t st);
-int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, const float* cr, const float* cg,
-                     const float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
-                     float* spec_ray, int n_rough, cudaStream_t st);
+int launch_final_rgb(int64_t R, int S, const FineBuffers& f, const RayState& rs, float* cr, float* cg,
+                     float* cb, const float* bg, float* rgb, float* depth, float* vis_out, float* nmap, float* nnmap,
+                     float* spec_ray, int n_rough, int n_out, const OutsideBuffers& ob, cudaStream_t st);
 int launch_to_ray_major(const float* const* src, int C, bool broadcast, int64_t R, int S, float* dst, cudaStream_t st);
 
 }  // namespace nrh

@@ -13,6 +13,7 @@ Mirrored reference pieces:
   SingleVarianceNetwork /root/reference/models/neus_hint_model.py:104-110
   RenderOutput          /root/reference/models/neus_hint_model.py:216-233
   extract_fields/_geometry  /root/reference/models/neus_hint_model.py:68-93,753-758
+  NeRF (outside model)  /root/reference/fields/nerf_density_field.py:30-64  (params; evaluated inside nrh_render_forward)
 """
 from __future__ import annotations
 
@@ -28,7 +29,8 @@ from torch import nn
 
 from . import _lib
 from . import autograd_fine
-from .config import (DepthComputationType, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig, SDFNetConfig)
+from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig,
+                     SDFNetConfig)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,6 +199,36 @@ class ReflectanceNetwork(nn.Module):
         raise RuntimeError("ReflectanceNetwork is evaluated inside NeuSHintRenderer.forward (fused CUDA pipeline)")
 
 
+class OutsideNeRF(nn.Module):
+    """Parameter container of the NeRF++ background model (fields/nerf_density_field.py:30-64): same submodule names,
+    shapes and construction order as the reference's `NeRF`, so the seeded init and the state_dict keys
+    (`outside_nerf.pts_linears.{i}.weight`, `views_linears.0`, `feature_linear`, `alpha_linear`, `rgb_linear`) match.
+    Evaluated only inside the fused render pipeline (render_outside, models/neus_hint_model.py:434-473)."""
+
+    def __init__(self, d_in: int = 4, d_in_view: int = 6, config: NeRFConfig = None):
+        super().__init__()
+        config = config if config is not None else NeRFConfig()
+        if not (d_in == 4 and d_in_view == 6 and config.d_hidden == 256 and config.n_layers == 8 and config.multi_res == 10
+                and config.multi_res_view == 4 and list(config.skips) == [4]):
+            raise NotImplementedError("nrhints_b200 kernels implement the reference-default outside NeRF "
+                                      "(8x256, multi_res=10, multi_res_view=4, skips=[4]); got " + repr(config))
+        self.config = config
+        W = config.d_hidden
+        self.input_ch = d_in * (2 * config.multi_res + 1)
+        self.input_ch_view = d_in_view * (2 * config.multi_res_view + 1)
+        self.skips = list(config.skips)
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(self.input_ch, W)] +
+            [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + self.input_ch, W) for i in range(config.n_layers - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(self.input_ch_view + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("the outside NeRF is evaluated inside NeuSHintRenderer.forward (fused CUDA pipeline)")
+
+
 class SingleVarianceNetwork(nn.Module):
     def __init__(self, init_val):
         super().__init__()
@@ -214,8 +246,8 @@ class NeuSHintRenderer(nn.Module):
         super().__init__()
         config = config if config is not None else NeuSModelConfig()
         r = config.renderer
-        if r.use_outside_nerf:
-            raise NotImplementedError("use_outside_nerf=True is outside the B200 hot path (SURVEY.md section 8a row A15)")
+        if r.use_outside_nerf and not (1 <= r.n_outside_samples <= _lib.NRH_MAX_OUTSIDE):
+            raise NotImplementedError(f"n_outside_samples must be in [1, {_lib.NRH_MAX_OUTSIDE}]")
         if r.n_shadow_importance_clip != -1:
             raise NotImplementedError("n_shadow_importance_clip != -1 is not implemented (reference default is -1)")
         if r.shadow_hint_gradient or r.specular_hint_gradient:
@@ -231,7 +263,9 @@ class NeuSHintRenderer(nn.Module):
         self.color_network = ReflectanceNetwork(
             d_feature=config.sdf_network.d_out_feat, d_in=color_d_in, d_out=3, config=config.reflectance_network,
             shadow_hint=r.shadow_hint, specular_hint=r.specular_hint, specular_hint_len=len(r.specular_roughness))
-        self.has_outside_nerf = False
+        self.has_outside_nerf = bool(r.use_outside_nerf)
+        if self.has_outside_nerf:
+            self.outside_nerf = OutsideNeRF(d_in=4, d_in_view=6, config=getattr(config, "outside_nerf", None))
         self.config = config
         self.mlp_impl = mlp_impl
         import weakref
@@ -259,6 +293,7 @@ class NeuSHintRenderer(nn.Module):
         c.normalized_normals = int(getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value)
         c.mlp_impl = _lib.MLP_IMPLS[self.mlp_impl]
         c.depth_type = _lib.DEPTH_TYPES[getattr(r.depth_type, "value", r.depth_type)]
+        c.use_outside_nerf, c.n_outside = int(self.has_outside_nerf), int(r.n_outside_samples)
         return c
 
     def _weight_tensors(self) -> List[torch.Tensor]:
@@ -272,6 +307,10 @@ class NeuSHintRenderer(nn.Module):
             lin = getattr(self.color_network, f"lin{l}")
             ws += [lin.effective_weight(), lin.bias]
         ws.append(self.deviation_network.variance)
+        if self.has_outside_nerf:                  # 31..: 8 x (W, b), alpha, feature, view, rgb
+            on = self.outside_nerf
+            for lin in list(on.pts_linears) + [on.alpha_linear, on.feature_linear, on.views_linears[0], on.rgb_linear]:
+                ws += [lin.weight, lin.bias]
         return ws
 
     def _ensure_packed(self, device: torch.device) -> torch.Tensor:
@@ -292,6 +331,11 @@ class NeuSHintRenderer(nn.Module):
         for l in range(5):
             raw.col_W[l], raw.col_b[l] = ws[20 + 2 * l].data_ptr(), ws[21 + 2 * l].data_ptr()
         raw.variance = ws[30].data_ptr()
+        if self.has_outside_nerf:
+            for l in range(8):
+                raw.nerf_W[l], raw.nerf_b[l] = ws[31 + 2 * l].data_ptr(), ws[32 + 2 * l].data_ptr()
+            (raw.nerf_alpha_W, raw.nerf_alpha_b, raw.nerf_feat_W, raw.nerf_feat_b, raw.nerf_view_W, raw.nerf_view_b,
+             raw.nerf_rgb_W, raw.nerf_rgb_b) = (w.data_ptr() for w in ws[47:55])
         nbytes = lib.nrh_packed_weights_bytes(C.byref(cfg))
         if self._packed is None or self._packed.numel() < nbytes or self._packed.device != device:
             self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -393,7 +437,7 @@ class NeuSHintRenderer(nn.Module):
             with torch.cuda.device(device):
                 stream = torch.cuda.current_stream(device).cuda_stream
                 _lib.check(lib.nrh_render_forward(C.byref(cfg), packed.data_ptr(), C.byref(c_rays), R,
-                                                  bg.data_ptr() if bg is not None else None, None, None, 1.0, 0,
+                                                  bg.data_ptr() if bg is not None else None, None, None, None, 1.0, 0,
                                                   C.byref(c_out), ws.data_ptr(), ws.numel(), stream), "nrh_render_forward")
             self.last_launch_count = lib.nrh_last_launch_count()
         return maps
@@ -409,6 +453,7 @@ class NeuSHintRenderer(nn.Module):
         r = self.config.renderer
         R = rays_o.shape[0]
         S = r.n_samples + r.n_importance_samples
+        St = S + (r.n_outside_samples if self.has_outside_nerf else 0)    # weights carry the appended outside samples (:521-524)
         Ss = r.n_shadow_samples + r.n_shadow_importance_samples
         f32 = dict(dtype=torch.float32, device=device)
 
@@ -417,6 +462,9 @@ class NeuSHintRenderer(nn.Module):
         needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                                   or any(t.requires_grad for t in ray_fields))
         want_z = return_extras or needs_grad
+        if needs_grad and self.has_outside_nerf:
+            raise NotImplementedError("gradients with use_outside_nerf=True are not implemented: the outside NeRF runs in the "
+                                      "CUDA forward only (wrap the call in torch.no_grad(), as the reference's evaluation does)")
 
         def prep(t):
             return t.detach().to(**f32).contiguous()
@@ -428,15 +476,17 @@ class NeuSHintRenderer(nn.Module):
         cos_anneal = 1.0
         if is_training and self.config.anneal_end > 0:
             cos_anneal = min(1.0, global_step / self.config.anneal_end)
-        # RNG draws in the reference's order (:682 then :394)
-        jit_p = jit_s = None
+        # RNG draws in the reference's order (:682, :689 (outside NeRF only), then :394)
+        jit_p = jit_s = jit_o = None
         if is_training:
             jit_p = torch.rand([R, 1], device=device)
+            if self.has_outside_nerf:
+                jit_o = torch.rand([R, r.n_outside_samples], device=device)
             if self.has_shadow_hint and not warmup and r.shadow_hint:
                 jit_s = torch.rand([R, r.n_shadow_samples], device=device)
 
         out = dict(
-            rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, 1, **f32), weights=torch.empty(R, S, **f32),
+            rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, 1, **f32), weights=torch.empty(R, St, **f32),
             inside_sphere=torch.empty(R, S, **f32), analytic_normals=torch.empty(R, S, 3, **f32),
             normalized_normals=torch.empty(R, S, 3, **f32),
             visibilities=torch.empty(R, 1, **f32) if r.shadow_hint else None,
@@ -444,7 +494,7 @@ class NeuSHintRenderer(nn.Module):
             inv_s=torch.empty(1, **f32),
             z_vals=torch.empty(R, S, **f32) if want_z else None,
             z_shadow=torch.zeros(R, Ss, **f32) if (return_extras and r.shadow_hint) else None,
-            sampled_color=torch.empty(R, S, 3, **f32) if return_extras else None)
+            sampled_color=torch.empty(R, St, 3, **f32) if return_extras else None)
         hit_pts = hit_dep = None
         if cfg.depth_type == _lib.DEPTH_TYPES["sphere_tracing"] and R > 0:
             hit_pts, hit_dep = self.sphere_trace(o, d, 2000, 1e-4, 100.0)        # models/neus_hint_model.py:529
@@ -461,7 +511,8 @@ class NeuSHintRenderer(nn.Module):
                 stream = torch.cuda.current_stream(device).cuda_stream
                 _lib.check(lib.nrh_render_forward(
                     C.byref(cfg), packed.data_ptr(), C.byref(c_rays), R, bg.data_ptr() if bg is not None else None,
-                    jit_p.data_ptr() if jit_p is not None else None, jit_s.data_ptr() if jit_s is not None else None,
+                    jit_p.data_ptr() if jit_p is not None else None, jit_o.data_ptr() if jit_o is not None else None,
+                    jit_s.data_ptr() if jit_s is not None else None,
                     float(cos_anneal), int(warmup), C.byref(c_out), ws.data_ptr(), ws.numel(), stream),
                     "nrh_render_forward")
             self.last_launch_count = lib.nrh_last_launch_count()

@@ -13,6 +13,9 @@ the reference algorithm, written against /root/reference (commit 291800d):
     fields/sdf_field.py:106-148         SDFNetwork.forward/.gradient -> sdf_mlp (manual reverse pass)
     fields/encodings.py:155-176         NeRFEncoding.forward  -> fourier_encode
     fields/reflectance_network.py:68-96 ReflectanceNetwork.forward -> reflectance_mlp
+    fields/nerf_density_field.py:66-89  NeRF.forward (outside model)  -> nerf_mlp
+    models/neus_hint_model.py:434-473   render_outside        -> render_outside
+    models/neus_hint_model.py:677-694   outside sample positions -> outside_z
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import it.  The product (nrhints_b200/) never does: the product path is the
@@ -69,11 +72,24 @@ class OracleConfig:
     refl_n_layers: int = 4
     refl_multires: int = 4
     refl_squeeze_out: bool = True
+    # outside NeRF (NeRF++ background, fields/nerf_density_field.py:12-26; off by default)
+    use_outside_nerf: bool = False
+    n_outside_samples: int = 32
+    nerf_n_layers: int = 8
+    nerf_multires: int = 10
+    nerf_multires_view: int = 4
+    nerf_skips: tuple = (4,)
 
     @staticmethod
     def from_model_config(cfg) -> "OracleConfig":
         r, s, c = cfg.renderer, cfg.sdf_network, cfg.reflectance_network
+        nerf = getattr(cfg, "outside_nerf", None)
+        extra = {}
+        if nerf is not None:
+            extra = dict(nerf_n_layers=nerf.n_layers, nerf_multires=nerf.multi_res, nerf_multires_view=nerf.multi_res_view,
+                         nerf_skips=tuple(nerf.skips))
         return OracleConfig(
+            use_outside_nerf=bool(r.use_outside_nerf), n_outside_samples=r.n_outside_samples, **extra,
             n_samples=r.n_samples, n_importance_samples=r.n_importance_samples,
             up_sample_steps=r.up_sample_steps, n_shadow_samples=r.n_shadow_samples,
             n_shadow_importance_samples=r.n_shadow_importance_samples,
@@ -192,6 +208,53 @@ def reflectance_mlp(W, pts, normals, view_dirs, feat, lights, vis, spec, cfg: Or
         if l < n - 1:
             x = torch.relu(x)
     return torch.sigmoid(x) if cfg.refl_squeeze_out else x
+
+
+def nerf_mlp(W, pts4: Tensor, views: Tensor, pls: Tensor, cfg: OracleConfig):
+    """NeRF.forward of the outside model (fields/nerf_density_field.py:66-89): PE(10) of the 4-D inverted-sphere point,
+    8 x 256 ReLU with the encoded point re-concatenated IN FRONT after layer 4, density head, feature head,
+    one 128-wide view/light layer on [feature, PE(4)(view, light)], rgb head.  Returns (density [N,1], rgb_raw [N,3])."""
+    e = fourier_encode(pts4, cfg.nerf_multires)
+    ev = fourier_encode(torch.cat([views, pls], dim=-1), cfg.nerf_multires_view)
+    h = e
+    for i in range(cfg.nerf_n_layers):
+        h = torch.relu(F.linear(h, W[f"outside_nerf.pts_linears.{i}.W"], W[f"outside_nerf.pts_linears.{i}.b"]))
+        if i in cfg.nerf_skips:
+            h = torch.cat([e, h], dim=-1)
+    density = F.linear(h, W["outside_nerf.alpha_linear.W"], W["outside_nerf.alpha_linear.b"])
+    feature = F.linear(h, W["outside_nerf.feature_linear.W"], W["outside_nerf.feature_linear.b"])
+    h = torch.cat([feature, ev], dim=-1)
+    h = torch.relu(F.linear(h, W["outside_nerf.views_linears.0.W"], W["outside_nerf.views_linears.0.b"]))
+    rgb = F.linear(h, W["outside_nerf.rgb_linear.W"], W["outside_nerf.rgb_linear.b"])
+    return density, rgb
+
+
+def outside_z(cfg: OracleConfig, far: Tensor, jitter_outside: Optional[Tensor], dtype) -> Tensor:
+    """Sample positions of the outside model (models/neus_hint_model.py:677-694): inverse-depth spacing beyond `far`."""
+    n_out = cfg.n_outside_samples
+    zo = torch.linspace(1e-3, 1.0 - 1.0 / (n_out + 1.0), n_out, dtype=dtype)
+    if jitter_outside is not None:
+        mids = 0.5 * (zo[..., 1:] + zo[..., :-1])
+        upper = torch.cat([mids, zo[..., -1:]], -1)
+        lower = torch.cat([zo[..., :1], mids], -1)
+        zo = lower[None, :] + (upper - lower)[None, :] * jitter_outside.to(dtype)
+    return far / torch.flip(zo, dims=[-1]) + 1.0 / cfg.n_samples
+
+
+def render_outside(W, cfg: OracleConfig, o, d, pl, z_feed, sample_dist):
+    """render_outside (models/neus_hint_model.py:434-473) -> (sigmoid colour [R,St,3], alpha [R,St])."""
+    R, St = z_feed.shape
+    dists = torch.cat([z_feed[..., 1:] - z_feed[..., :-1], torch.full((R, 1), sample_dist, dtype=z_feed.dtype)], -1)
+    mid_z = z_feed + dists * 0.5
+    pts = o[:, None, :] + d[:, None, :] * mid_z[..., :, None]
+    dis = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
+    pts4 = torch.cat([pts / dis, 1.0 / dis], dim=-1).reshape(-1, 4)
+    dirs = d[:, None, :].expand(R, St, 3).reshape(-1, 3)
+    pls = pl[:, None, :].expand(R, St, 3).reshape(-1, 3)
+    density, rgb = nerf_mlp(W, pts4, dirs, pls, cfg)
+    color = torch.sigmoid(rgb).reshape(R, St, 3)
+    alpha = 1.0 - torch.exp(-F.softplus(density.reshape(R, St)) * dists)
+    return color, alpha
 
 
 # --------------------------------------------------------------------------------------
@@ -344,8 +407,10 @@ def specular_cue(cfg: OracleConfig, hit_normal, lights, hits, d):
 # --------------------------------------------------------------------------------------
 # render
 # --------------------------------------------------------------------------------------
-def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, warmup, jitter_shadow):
-    """render_core (models/neus_hint_model.py:475-651), AlphaBlend depth, no outside NeRF."""
+def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, warmup, jitter_shadow,
+                background_alpha=None, background_color=None):
+    """render_core (models/neus_hint_model.py:475-651); background_alpha / background_color [R, S + n_outside] come from
+    render_outside when the outside NeRF is on (:517-519, :630-633)."""
     R, S = z.shape
     dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((R, 1), sample_dist, dtype=z.dtype)], -1)
     mid_z = z + dists * 0.5
@@ -358,8 +423,12 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
     alpha = alpha.reshape(R, S)
     pts_norm = torch.linalg.norm(pts, ord=2, dim=-1).reshape(R, S)
     inside = (pts_norm < 1.0).to(z.dtype).detach()
-    weights = alpha * _excl_cumprod(1.0 - alpha + 1e-7)
-    wsum = weights.sum(-1, keepdim=True)
+    if background_alpha is not None:                                # :517-519
+        alpha = alpha * inside + background_alpha[:, :S] * (1.0 - inside)
+        alpha = torch.cat([alpha, background_alpha[:, S:]], dim=-1)
+    weights_all = alpha * _excl_cumprod(1.0 - alpha + 1e-7)
+    wsum = weights_all.sum(-1, keepdim=True)
+    weights = weights_all[:, :S]                                    # neus_weights (:525)
     with torch.no_grad():
         if cfg.depth_type == "sphere_tracing":                      # :528-529
             hits, depth = sphere_trace(W, cfg, o, d, 2000, 1e-4, 100.0)
@@ -395,11 +464,14 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
 
     normal_in = n_hat if cfg.normalized_normals else grad
     color = reflectance_mlp(W, pts, normal_in, dirs, feat, pls, vis, spec, cfg).reshape(R, S, 3)
-    rgb = (color * weights[..., None]).sum(1)
+    if background_alpha is not None:                                # :630-633
+        color = color * inside[:, :, None] + background_color[:, :S] * (1.0 - inside)[:, :, None]
+        color = torch.cat([color, background_color[:, S:]], dim=1)
+    rgb = (color * weights_all[..., None]).sum(1)
     if bg is not None:
         rgb = rgb + bg * (1.0 - wsum)
     out = {
-        "rgb": rgb, "depth": depth, "weights": weights,
+        "rgb": rgb, "depth": depth, "weights": weights_all,
         "s_val": (1.0 / inv_s).expand(R, S),
         "inside_sphere": inside, "relax_inside_sphere": inside,         # quirk Q1 (:746)
         "analytic_normals": grad.reshape(R, S, 3),
@@ -415,12 +487,13 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
 def render_forward(state: Dict[str, Tensor], cfg: OracleConfig, origins, directions, pl_positions, nears, fars,
                    is_training=False, background_rgb: Optional[Tensor] = None, cos_anneal: float = 1.0,
                    warmup: bool = False, jitter_primary: Optional[Tensor] = None,
-                   jitter_shadow: Optional[Tensor] = None, dtype=torch.float32, effective: bool = False):
+                   jitter_shadow: Optional[Tensor] = None, dtype=torch.float32, effective: bool = False,
+                   jitter_outside: Optional[Tensor] = None):
     """NeuSHintRenderer.forward (models/neus_hint_model.py:653-751).
 
     `state` is a renderer state_dict (or already-effective weights if effective=True).
-    RNG is explicit: jitter_primary [R,1] ~ U(0,1) (:682) and jitter_shadow [R,n_shadow] (:394)
-    are drawn by the caller in that order when is_training, else None.
+    RNG is explicit: jitter_primary [R,1] ~ U(0,1) (:682), jitter_outside [R,n_outside] (:689, outside NeRF only) and
+    jitter_shadow [R,n_shadow] (:394) are drawn by the caller in that order when is_training, else None.
     cos_anneal = min(1, global_step/anneal_end) when training (:669-671)."""
     W = state if effective else effective_weights(state, dtype)
     o, d, pl = origins.to(dtype), directions.to(dtype), pl_positions.to(dtype)
@@ -435,7 +508,13 @@ def render_forward(state: Dict[str, Tensor], cfg: OracleConfig, origins, directi
     with torch.no_grad():
         z = hierarchical_z(W, cfg, o, d, z, cfg.n_importance_samples, cfg.up_sample_steps)
     js = jitter_shadow.to(dtype) if (is_training and jitter_shadow is not None) else None
-    return render_core(W, cfg, o, d, pl, z, sample_dist, bg, cos_anneal if is_training else 1.0, warmup, js)
+    bg_alpha = bg_color = None
+    if cfg.use_outside_nerf:                                         # :716-724
+        z_out = outside_z(cfg, far, jitter_outside if is_training else None, dtype)
+        z_feed, _ = torch.sort(torch.cat([z, z_out.expand(z.shape[0], -1)], dim=-1), dim=-1)
+        bg_color, bg_alpha = render_outside(W, cfg, o, d, pl, z_feed, sample_dist)
+    return render_core(W, cfg, o, d, pl, z, sample_dist, bg, cos_anneal if is_training else 1.0, warmup, js,
+                       background_alpha=bg_alpha, background_color=bg_color)
 
 
 def training_loss(out, rgb_gt, igr_weight=0.1):

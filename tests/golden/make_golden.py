@@ -41,7 +41,10 @@ def ref_config(M, case):
 def main():
     M, RayBundle = import_reference()
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])                       # optional: regenerate just the named cases
     for name, case in T.CASES.items():
+        if only and name not in only:
+            continue
         cfg = T.make_config(case)
         sd = T.make_state(case["weights"], cfg)
         rays, bg = T.case_inputs(case)
@@ -71,6 +74,9 @@ def main():
         np.savez_compressed(HERE / f"{name}.npz", digest=np.array(T.state_digest(sd)),
                             **{"in_" + k: v.numpy() for k, v in rays.items()}, in_bg=bg.numpy(),
                             **{"out_" + k: v for k, v in ref_np.items()})
+    if only and "train_16x128_grads" not in only:
+        print("fixtures written to", HERE)
+        return
     # ---- gradients of the training loss (pipelines/base_pipeline.py:57-62) from the reference's autograd --------
     name = "train_16x128"
     case = T.CASES[name]

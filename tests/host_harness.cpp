@@ -59,4 +59,25 @@ void h_specular_cue(const float* hit_n, const float* pl, const float* hit, const
 
 void h_normalize3(const float* v, float* out) { normalize3(v, out); }
 
+// ---- outside (NeRF++) model ------------------------------------------------------------------------------------
+void h_outside_z(float far, int n_samples, int n_out, int has_jitter, const float* jitter, float* zo) {
+    outside_z(far, n_samples, n_out, has_jitter != 0, CSoA{jitter, 1}, zo);
+}
+void h_outside_sections(int S, const float* z, int n_out, const float* zo, float sample_dist, float* dist, float* mid) {
+    outside_sections(S, CSoA{z, 1}, n_out, zo, sample_dist, SoA{dist, 1}, SoA{mid, 1});
+}
+void h_outside_point(const float* o, const float* d, float mid, float* p4) { outside_point(o, d, mid, p4); }
+float h_outside_alpha(float density, float dist) { return outside_alpha(density, dist); }
+
+// composite with the background model: w has S + n_out entries
+void h_composite_primary_bg(const float* o, const float* d, int S, const float* z, float last_dist, const float* sdf,
+                            const float* gx, const float* gy, const float* gz, float inv_s, float cos_anneal,
+                            float* w, float* inside, float* nx, float* ny, float* nz, float* res,
+                            int n_out, const float* bg_density, const float* bg_dist) {
+    PrimaryComposite pc = composite_primary(o, d, S, CSoA{z, 1}, last_dist, CSoA{sdf, 1}, CSoA{gx, 1}, CSoA{gy, 1}, CSoA{gz, 1},
+                                            inv_s, cos_anneal, SoA{w, 1}, SoA{inside, 1}, SoA{nx, 1}, SoA{ny, 1}, SoA{nz, 1},
+                                            n_out, CSoA{bg_density, 1}, CSoA{bg_dist, 1});
+    res[0] = pc.wsum; res[1] = pc.depth; res[2] = pc.nsum[0]; res[3] = pc.nsum[1]; res[4] = pc.nsum[2];
+}
+
 }  // extern "C"

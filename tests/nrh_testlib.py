@@ -44,6 +44,13 @@ CASES = {
     "sphere_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, n_shadow_samples=32,
                                              n_shadow_importance_samples=32, depth_type=nb.DepthComputationType.SphereTracing),
                          weights="init", ray_seed=22),
+    # NeRF++ outside model (use_outside_nerf, models/neus_hint_model.py:434-473; off in the shipped presets): inference ...
+    "outside_16x64": dict(R=16, renderer=dict(use_outside_nerf=True, n_samples=32, n_importance_samples=32, n_shadow_samples=32,
+                                              n_shadow_importance_samples=32, n_outside_samples=16),
+                          weights="init", ray_seed=31, crop=800),
+    # ... and training-mode forward (third RNG draw for the outside samples, :689), default 32 outside samples, black bg
+    "outside_train_8x128": dict(R=8, renderer=dict(use_outside_nerf=True), weights="sharp", ray_seed=32, crop=800, bg=0.0,
+                                training=True, global_step=60000, rng_seed=321),
 }
 
 
@@ -63,7 +70,7 @@ def make_state(kind: str, cfg: nb.NeuSModelConfig) -> Dict[str, torch.Tensor]:
         for k in sorted(sd):
             if k.endswith("weight_v"):
                 sd[k] = sd[k] + 0.02 * sd[k].std() * torch.randn(sd[k].shape, generator=g)
-            elif k.endswith("bias") and "out_" not in k:
+            elif k.endswith("bias") and "out_" not in k and "outside_nerf" not in k:
                 sd[k] = sd[k] + 0.01 * torch.randn(sd[k].shape, generator=g)
         sd["deviation_network.variance"] = torch.tensor(0.6)
     return sd
@@ -84,27 +91,28 @@ def case_inputs(case: dict):
 
 
 def case_jitters(case: dict, cfg: nb.NeuSModelConfig):
-    """The two torch.rand draws of training mode, in the reference's order."""
+    """The torch.rand draws of training mode, in the reference's order (:682, :689 with the outside NeRF, :394)."""
     if not case.get("training"):
-        return None, None
+        return None, None, None
     torch.manual_seed(case["rng_seed"])
     jp = torch.rand([case["R"], 1])
+    jo = torch.rand([case["R"], cfg.renderer.n_outside_samples]) if cfg.renderer.use_outside_nerf else None
     js = torch.rand([case["R"], cfg.renderer.n_shadow_samples]) if cfg.renderer.shadow_hint else None
-    return jp, js
+    return jp, jo, js
 
 
 def run_oracle(case: dict, dtype=torch.float32):
     cfg = make_config(case)
     sd = make_state(case["weights"], cfg)
     rays, bg = case_inputs(case)
-    jp, js = case_jitters(case, cfg)
+    jp, jo, js = case_jitters(case, cfg)
     ocfg = orc.OracleConfig.from_model_config(cfg)
     training = bool(case.get("training"))
     cos_anneal = min(1.0, case.get("global_step", 0) / cfg.anneal_end) if training else 1.0
     with torch.no_grad():
         out = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
                                  rays["fars"], is_training=training, background_rgb=bg, cos_anneal=cos_anneal,
-                                 jitter_primary=jp, jitter_shadow=js, dtype=dtype)
+                                 jitter_primary=jp, jitter_shadow=js, jitter_outside=jo, dtype=dtype)
     return out
 
 
@@ -165,7 +173,13 @@ def compare_outputs(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], per_ray_
             assert d < lim, f"{label}: max |d {k}| = {d:.3e} >= {lim}"
     mse = float(np.mean((a["rgb"].astype(np.float64) - b["rgb"].astype(np.float64)) ** 2))
     stats["psnr_between"] = float(10 * np.log10(1.0 / max(mse, 1e-30)))
-    R, S = a["weights"].shape
+    R, S = a["inside_sphere"].shape           # weights carry n_outside extra columns with the outside NeRF
+    if a["weights"].shape[1] > S:
+        assert a["weights"].shape == b["weights"].shape
+        d = float(np.max(np.abs(a["weights"][:, S:].astype(np.float64) - b["weights"][:, S:].astype(np.float64))))
+        stats["weights_outside"] = d
+        assert d < per_sample_tol, f"{label}: max |d weights (outside samples)| = {d:.3e} >= {per_sample_tol}"
+        a = dict(a, weights=a["weights"][:, :S]); b = dict(b, weights=b["weights"][:, :S])
     ok = np.ones((R, S), dtype=bool)
     if "z_vals" in a and "z_vals" in b:
         same = np.abs(a["z_vals"] - b["z_vals"]) < 2e-5

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_version_and_config_validation_without_gpu():
     lib = _lib.load()
-    assert lib.nrh_version() == 2
+    assert lib.nrh_version() == 3
     import nrhints_b200 as nb
     m = nb.NeuSHintRenderer(nb.NeuSModelConfig())
     cfg = m._c_config()
@@ -44,8 +44,9 @@ def test_version_and_config_validation_without_gpu():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 3 * 4
-    assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1) * 8
+    assert C.sizeof(_lib.NrhConfig) == 8 * 4 + 4 * 4 + 4 + 3 * 4 + 2 * 4
+    assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1 + 8 + 8 + 8) * 8
+    assert _lib.NRH_ABI_VERSION == int(re.search(r"#define NRH_ABI_VERSION (\d+)", HEADER).group(1))
     assert C.sizeof(_lib.NrhRays) == 7 * 8
     assert C.sizeof(_lib.NrhOutputs) == 16 * 8
     fields = re.findall(r"(?:float|void)\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
@@ -65,7 +66,10 @@ def test_cpu_tensors_are_rejected_loudly():
 def test_unsupported_configs_raise():
     import nrhints_b200 as nb
     with pytest.raises(NotImplementedError):
-        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(use_outside_nerf=True)))
+        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(use_outside_nerf=True, n_outside_samples=100)))
+    with pytest.raises(NotImplementedError):
+        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(use_outside_nerf=True),
+                                               outside_nerf=nb.NeRFConfig(multi_res=6)))
     with pytest.raises(NotImplementedError):
         nb.NeuSHintRenderer(nb.NeuSModelConfig(sdf_network=nb.SDFNetConfig(d_hidden=128)))
     with pytest.raises(NotImplementedError):
@@ -82,3 +86,16 @@ def test_state_dict_layout_matches_reference_inventory():
     assert tuple(sd["sdf_network.lin3.weight_v"].shape) == (217, 256)
     assert tuple(sd["color_network.lin0.weight_v"].shape) == (256, 361)
     assert tuple(sd["deviation_network.variance"].shape) == ()
+    # with the outside NeRF: the reference's `outside_nerf.*` keys (fields/nerf_density_field.py:57-64), registered last
+    m2 = nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(use_outside_nerf=True)))
+    sd2 = m2.state_dict()
+    assert list(sd2)[:46] == list(sd) and len(sd2) == 46 + 24
+    assert tuple(sd2["outside_nerf.pts_linears.5.weight"].shape) == (256, 340)
+    assert tuple(sd2["outside_nerf.views_linears.0.weight"].shape) == (128, 310)
+    assert list(sd2)[-2:] == ["outside_nerf.rgb_linear.weight", "outside_nerf.rgb_linear.bias"]
+    cfg = m2._c_config()
+    from nrhints_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    assert lib.nrh_check_config(C.byref(cfg)) == 0
+    assert lib.nrh_packed_weights_bytes(C.byref(cfg)) > lib.nrh_packed_weights_bytes(C.byref(m._c_config())) + 600000 * 4

@@ -64,15 +64,17 @@ def test_forward_matches_oracle_and_fixture(name, impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-def test_training_mode_forward(impl):
-    """jitter on both marches + cos annealing; the jitters are drawn by torch.rand on the device, so the oracle
-    is fed the very same numbers."""
-    case = T.CASES["train_16x128"]
+@pytest.mark.parametrize("name", ["train_16x128", "outside_train_8x128"])
+def test_training_mode_forward(name, impl):
+    """jitter on both marches (+ the outside samples with the outside NeRF) + cos annealing; the jitters are drawn by
+    torch.rand on the device in the reference's order, so the oracle is fed the very same numbers."""
+    case = T.CASES[name]
     m, cfg, sd = build_module(case, impl)
     rays, bg = T.case_inputs(case)
     R = case["R"]
     torch.manual_seed(7)
     jp = torch.rand([R, 1], device="cuda")
+    jo = torch.rand([R, cfg.renderer.n_outside_samples], device="cuda") if cfg.renderer.use_outside_nerf else None
     js = torch.rand([R, cfg.renderer.n_shadow_samples], device="cuda")
     torch.manual_seed(7)
     with torch.no_grad():
@@ -81,9 +83,15 @@ def test_training_mode_forward(impl):
     ocfg = orc.OracleConfig.from_model_config(cfg)
     with torch.no_grad():
         want = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
-                                  rays["fars"], is_training=True, background_rgb=bg, cos_anneal=0.5,
-                                  jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
-    T.compare_outputs(T.to_np(out), T.to_np(want), label=f"cuda[{impl}]-train", **(T.TOL if impl == "fp32" else T.TOL_TC)["init"])
+                                  rays["fars"], is_training=True, background_rgb=bg,
+                                  cos_anneal=min(1.0, case["global_step"] / cfg.anneal_end),
+                                  jitter_primary=jp.cpu(), jitter_shadow=js.cpu(),
+                                  jitter_outside=jo.cpu() if jo is not None else None)
+    got = T.to_np(out)
+    assert got["weights"].shape == (R, cfg.renderer.n_samples + cfg.renderer.n_importance_samples
+                                    + (cfg.renderer.n_outside_samples if cfg.renderer.use_outside_nerf else 0))
+    T.compare_outputs(got, T.to_np(want), label=f"cuda[{impl}]-train[{name}]",
+                      **(T.TOL if impl == "fp32" else T.TOL_TC)[case["weights"]])
 
 
 @pytest.mark.parametrize("impl", IMPLS)

@@ -75,7 +75,7 @@ def test_oracle_autograd_gradients_match_reference_fixture():
     cfg = T.make_config(case)
     sd = {k: v.clone().requires_grad_(True) for k, v in T.make_state(case["weights"], cfg).items()}
     rays, bg = T.case_inputs(case)
-    jp, js = T.case_jitters(case, cfg)
+    jp, _, js = T.case_jitters(case, cfg)
     ocfg = orc.OracleConfig.from_model_config(cfg)
     out = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"], rays["fars"],
                              is_training=True, background_rgb=bg, cos_anneal=0.5, jitter_primary=jp, jitter_shadow=js)

@@ -191,3 +191,82 @@ def test_specular_cue(hlib):
         cue = np.empty(4, np.float32)
         hlib.h_specular_cue(_p(f32(hn[0])), _p(f32(pl[0])), _p(f32(hit[0])), _p(f32(d[0])), 4, _p(rough), _p(cue))
         np.testing.assert_allclose(cue, want, rtol=2e-5, atol=1e-7)
+
+
+# ---- outside (NeRF++) model: models/neus_hint_model.py:677-694 (sample positions), :434-473 (render_outside) ----------
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("n_out", [16, 32])
+def test_outside_z_and_sections(hlib, jitter, n_out):
+    hlib.h_outside_alpha.restype = C.c_float
+    cfg = orc.OracleConfig(n_samples=64, n_outside_samples=n_out, use_outside_nerf=True)
+    far = torch.tensor([[4.93]])
+    g = torch.Generator().manual_seed(n_out)
+    jit = torch.rand(1, n_out, generator=g)
+    want = orc.outside_z(cfg, far, jit if jitter else None, torch.float32)
+    zo = np.empty(n_out, np.float32)
+    hlib.h_outside_z(C.c_float(far.item()), 64, n_out, int(jitter), _p(f32(jit[0])), _p(zo))
+    np.testing.assert_allclose(zo, want.reshape(-1).numpy(), rtol=3e-7)
+    assert np.all(np.diff(zo) > 0)
+    # merged sections against torch.sort(cat(...))
+    S = 40
+    z = torch.sort(2.9 + 2.0 * torch.rand(1, S, generator=g), dim=-1)[0]
+    z_feed, _ = torch.sort(torch.cat([z, torch.from_numpy(zo)[None, :]], -1), -1)
+    sd = 2.0 / 64
+    dists = torch.cat([z_feed[:, 1:] - z_feed[:, :-1], torch.full((1, 1), sd)], -1)
+    mids = z_feed + dists * 0.5
+    dist, mid = np.empty(S + n_out, np.float32), np.empty(S + n_out, np.float32)
+    hlib.h_outside_sections(S, _p(f32(z[0])), n_out, _p(zo), C.c_float(sd), _p(dist), _p(mid))
+    np.testing.assert_array_equal(dist, dists[0].numpy())
+    np.testing.assert_array_equal(mid, mids[0].numpy())
+
+
+def test_outside_point_and_alpha(hlib):
+    hlib.h_outside_alpha.restype = C.c_float
+    o = torch.tensor([[0.3, 3.2, -2.1]]); d = torch.nn.functional.normalize(torch.tensor([[-0.1, -0.8, 0.55]]), dim=-1)
+    for mid in (0.2, 3.0, 4.7, 40.0, 4000.0):
+        pts = o + d * mid
+        dis = torch.linalg.norm(pts, dim=-1, keepdim=True).clip(1.0, 1e10)
+        want = torch.cat([pts / dis, 1.0 / dis], -1)[0].numpy()
+        p4 = np.empty(4, np.float32)
+        hlib.h_outside_point(_p(f32(o[0])), _p(f32(d[0])), C.c_float(mid), _p(p4))
+        np.testing.assert_allclose(p4, want, rtol=1e-6, atol=1e-7)
+    for dens, dist in ((-3.0, 0.1), (0.0, 0.03), (2.5, 1.7), (25.0, 0.2), (-30.0, 5.0)):
+        want = float(1.0 - torch.exp(-torch.nn.functional.softplus(torch.tensor(dens)) * dist))
+        got = hlib.h_outside_alpha(C.c_float(dens), C.c_float(dist))
+        assert abs(got - want) < 2e-7, (dens, dist, got, want)
+
+
+def test_composite_primary_with_background(hlib):
+    """alpha blending with the background alpha outside the unit sphere + appended far samples (render_core :517-525)."""
+    g = torch.Generator().manual_seed(8)
+    S, n_out = 24, 8
+    o = torch.tensor([[0.0, 0.0, -2.0]]); d = torch.tensor([[0.05, 0.0, 1.0]]); d = d / d.norm()
+    z = torch.sort(0.6 + 2.4 * torch.rand(1, S, generator=g), -1)[0]             # some mid-points outside the unit sphere
+    last, inv_s, ca = 2.0 / 64, 55.0, 1.0
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((1, 1), last)], -1)
+    mid = z + dists * 0.5
+    pts = o + d * mid[0, :, None]
+    grad = torch.nn.functional.normalize(pts, dim=-1)
+    sdf_mid = torch.linalg.norm(pts, dim=-1) - 0.5
+    true_cos = (d.expand(S, 3) * grad).sum(-1, keepdim=True)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - ca) + torch.relu(-true_cos) * ca)
+    pc = torch.sigmoid((sdf_mid[:, None] - iter_cos * dists.reshape(-1, 1) * 0.5) * inv_s)
+    nc = torch.sigmoid((sdf_mid[:, None] + iter_cos * dists.reshape(-1, 1) * 0.5) * inv_s)
+    alpha = ((pc - nc + 1e-5) / (pc + 1e-5)).clip(0, 1).reshape(1, S)
+    inside = (torch.linalg.norm(pts, dim=-1) < 1.0).float()[None, :]
+    assert 0 < inside.sum() < S
+    dens = torch.randn(1, S + n_out, generator=g) * 2.0
+    bdist = 0.02 + torch.rand(1, S + n_out, generator=g)
+    bg_alpha = 1.0 - torch.exp(-torch.nn.functional.softplus(dens) * bdist)
+    a = torch.cat([alpha * inside + bg_alpha[:, :S] * (1.0 - inside), bg_alpha[:, S:]], -1)
+    w = a * orc._excl_cumprod(1.0 - a + 1e-7)
+    wout = np.empty(S + n_out, np.float32); ins = np.empty(S, np.float32)
+    nx, ny, nz = (np.empty(S, np.float32) for _ in range(3))
+    res = np.empty(5, np.float32)
+    hlib.h_composite_primary_bg(_p(f32(o[0])), _p(f32(d[0])), S, _p(f32(z[0])), C.c_float(last), _p(f32(sdf_mid)),
+                                _p(f32(grad[:, 0])), _p(f32(grad[:, 1])), _p(f32(grad[:, 2])), C.c_float(inv_s), C.c_float(ca),
+                                _p(wout), _p(ins), _p(nx), _p(ny), _p(nz), _p(res), n_out, _p(f32(dens[0])), _p(f32(bdist[0])))
+    np.testing.assert_allclose(wout, w[0].numpy(), atol=2e-6)
+    np.testing.assert_allclose(res[0], w.sum().item(), atol=3e-6)
+    np.testing.assert_allclose(res[1], (mid * w[:, :S]).sum().item(), atol=1e-5)
+    np.testing.assert_array_equal(ins, inside[0].numpy())
