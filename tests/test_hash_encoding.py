@@ -69,6 +69,6 @@ def test_cuda_full_size_table_matches_oracle():
     g = torch.Generator().manual_seed(3)
     pts = torch.rand(100000, 3, generator=g)
     pts[:1000] = pts[:1000] * 3.0 - 1.0
-    out = enc(pts.cuda()).cpu().numpy()
+    out = enc(pts.cuda()).detach().cpu().numpy()
     want = ho.hash_encode(pts.numpy(), enc.hash_table.detach().cpu().numpy(), enc.scalings.numpy(), 19)
     np.testing.assert_array_equal(out, want)
