@@ -442,6 +442,62 @@ class NeuSHintRenderer(nn.Module):
             self.last_launch_count = lib.nrh_last_launch_count()
         return maps
 
+    @torch.no_grad()
+    def render_image(self, ray_bundle, background_rgb: Optional[torch.Tensor] = None, chunk_rays: int = 16384,
+                     device=None, to_host: bool = True) -> Dict[str, torch.Tensor]:
+        """Full-image evaluation: all rays of a view in one call.  The reference renders a view as
+        H*W/512 separate forward calls, each followed by `.to('cpu')` of the 7 KB/ray RenderOutput, concatenates them on
+        the host and reduces the normal maps there (pipelines/base_pipeline.py:107-133).  Here the (host or device)
+        RayBundle is walked in `chunk_rays` slices through render_maps -- per-ray maps reduced on the device, 60 B/ray --
+        the slices are written straight into full-size device maps, and ONE pinned device->host copy per map ends the
+        call.  Host->device copies of slice i+1 are issued on a second stream while slice i renders.
+        Returns rgb [N,3], depth [N,1], analytic_normals [N,3], normalized_analytic_normals [N,3] (weighted normal maps
+        before the camera rotation of :127-133), shadow_map [N,1], specular_hint [N,n_rough]."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        N = ray_bundle.origins.shape[0]
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._early_event = torch.cuda.Event()
+        bg = background_rgb.to(device, non_blocking=True) if background_rgb is not None else None
+        fields = ("origins", "directions", "pl_positions", "nears", "fars")
+        on_device = ray_bundle.origins.device == device
+
+        def stage(i0):
+            sl = {k: getattr(ray_bundle, k)[i0:i0 + chunk_rays] for k in fields}
+            if on_device:
+                return type(ray_bundle)(**sl), None
+            with torch.cuda.stream(self._copy_stream):
+                dev = type(ray_bundle)(**{k: v.to(device, non_blocking=True) for k, v in sl.items()})
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return dev, ev
+
+        full: Dict[str, torch.Tensor] = {}
+        nxt = stage(0) if N > 0 else None
+        for i0 in range(0, N, chunk_rays):
+            cur, ev = nxt
+            if ev is not None:
+                main.wait_event(ev)
+            nxt = stage(i0 + chunk_rays) if i0 + chunk_rays < N else None
+            maps = self.render_maps(cur, background_rgb=bg)
+            for k, v in maps.items():
+                if k not in full:
+                    full[k] = torch.empty((N,) + tuple(v.shape[1:]), dtype=v.dtype, device=device)
+                full[k][i0:i0 + v.shape[0]].copy_(v)
+            if ev is not None:
+                for t in (cur.origins, cur.directions, cur.pl_positions, cur.nears, cur.fars):
+                    t.record_stream(main)                    # allocated on the copy stream, consumed on the main stream
+        if not to_host:
+            return full
+        host = {}
+        for k, v in full.items():
+            buf = self._pinned_like("image::" + k, v)
+            buf.copy_(v, non_blocking=True)
+            host[k] = buf
+        main.synchronize()
+        return host
+
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
                 global_step: int = 0, return_extras: bool = False, _early_event=None) -> RenderOutput:

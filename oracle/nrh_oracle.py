@@ -28,7 +28,9 @@ seeded rays/weights, asserts agreement, and commits the reference outputs as
 fixtures under tests/golden/*.npz.  tests/test_oracle_golden.py re-checks the oracle
 against those fixtures wherever the tests run (the GPU box has no /root/reference).
 
-dtype: float32 by default; pass dtype=torch.float64 for a "truth" evaluation.
+dtype: float32 by default; pass dtype=torch.float64 for a "truth" evaluation.  Every tensor is created on the
+device of its inputs, so the same restatement also runs with torch CUDA ops (tools_bench_extra.py times it on the B200
+as the "unfused PyTorch on the same GPU" baseline of BASELINE.md section 3.6); the CPU is the default and what the tests use.
 The SDF input gradient is computed by an explicit reverse pass (not autograd) so
 that it doubles as the executable spec of the CUDA kernel's reverse sweep; all ops are
 differentiable torch ops, so autograd through it yields the second-order terms
@@ -131,7 +133,7 @@ def effective_weights(state: Dict[str, Tensor], dtype=torch.float32) -> Dict[str
 def fourier_encode(x: Tensor, n_freq: int) -> Tensor:
     """[N,D] -> [N, D*(2F+1)] = [x, sin(x_d 2^k) (d-major,k-minor), sin(x_d 2^k + pi/2)]
     (fields/encodings.py:168-176; the cosine is sin(.+pi/2) evaluated in the working dtype)."""
-    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, dtype=x.dtype)
+    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, dtype=x.dtype, device=x.device)
     s = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
     enc = torch.sin(torch.cat([s, s + torch.pi / 2.0], dim=-1))
     return torch.cat([x, enc], dim=-1)
@@ -140,7 +142,7 @@ def fourier_encode(x: Tensor, n_freq: int) -> Tensor:
 def fourier_encode_jvp_T(x: Tensor, n_freq: int, g_enc: Tensor) -> Tensor:
     """Transposed Jacobian of fourier_encode applied to g_enc: [N, D*(2F+1)] -> [N, D]."""
     D = x.shape[-1]
-    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, dtype=x.dtype)
+    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, dtype=x.dtype, device=x.device)
     s = x[..., None] * freqs                                            # [N,D,F]
     g_id = g_enc[..., :D]
     g_sin = g_enc[..., D:D + D * n_freq].reshape(*x.shape, n_freq)
@@ -232,7 +234,7 @@ def nerf_mlp(W, pts4: Tensor, views: Tensor, pls: Tensor, cfg: OracleConfig):
 def outside_z(cfg: OracleConfig, far: Tensor, jitter_outside: Optional[Tensor], dtype) -> Tensor:
     """Sample positions of the outside model (models/neus_hint_model.py:677-694): inverse-depth spacing beyond `far`."""
     n_out = cfg.n_outside_samples
-    zo = torch.linspace(1e-3, 1.0 - 1.0 / (n_out + 1.0), n_out, dtype=dtype)
+    zo = torch.linspace(1e-3, 1.0 - 1.0 / (n_out + 1.0), n_out, dtype=dtype, device=far.device)
     if jitter_outside is not None:
         mids = 0.5 * (zo[..., 1:] + zo[..., :-1])
         upper = torch.cat([mids, zo[..., -1:]], -1)
@@ -244,7 +246,7 @@ def outside_z(cfg: OracleConfig, far: Tensor, jitter_outside: Optional[Tensor], 
 def render_outside(W, cfg: OracleConfig, o, d, pl, z_feed, sample_dist):
     """render_outside (models/neus_hint_model.py:434-473) -> (sigmoid colour [R,St,3], alpha [R,St])."""
     R, St = z_feed.shape
-    dists = torch.cat([z_feed[..., 1:] - z_feed[..., :-1], torch.full((R, 1), sample_dist, dtype=z_feed.dtype)], -1)
+    dists = torch.cat([z_feed[..., 1:] - z_feed[..., :-1], torch.full((R, 1), sample_dist, dtype=z_feed.dtype, device=z_feed.device)], -1)
     mid_z = z_feed + dists * 0.5
     pts = o[:, None, :] + d[:, None, :] * mid_z[..., :, None]
     dis = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
@@ -266,7 +268,7 @@ def sample_pdf_det(bins: Tensor, weights: Tensor, n: int) -> Tensor:
     pdf = weights / torch.sum(weights, -1, keepdim=True)
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
-    u = torch.linspace(0.0, 1.0, steps=n, dtype=bins.dtype).expand(list(cdf.shape[:-1]) + [n]).contiguous()
+    u = torch.linspace(0.0, 1.0, steps=n, dtype=bins.dtype, device=bins.device).expand(list(cdf.shape[:-1]) + [n]).contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = torch.clamp(inds - 1, min=0)
     above = torch.clamp(inds, max=cdf.shape[-1] - 1)
@@ -352,7 +354,7 @@ def shadow_visibility(W, cfg: OracleConfig, lights, targets, cos_anneal=1.0, jit
     L = torch.linalg.norm(dvec, ord=2, dim=-1, keepdim=True)
     sample_dist = L / n
     d = dvec / L
-    z = torch.linspace(0.0, 1.0, steps=n, dtype=o.dtype) * L * (1.0 - cfg.shadow_ray_offset)
+    z = torch.linspace(0.0, 1.0, steps=n, dtype=o.dtype, device=o.device) * L * (1.0 - cfg.shadow_ray_offset)
     if jitter is not None:                                     # stratified, one draw per sample (:388-395)
         mids = 0.5 * (z[..., 1:] + z[..., :-1])
         upper = torch.cat([mids, z[..., -1:]], -1)
@@ -372,7 +374,7 @@ def shadow_visibility(W, cfg: OracleConfig, lights, targets, cos_anneal=1.0, jit
 def sphere_trace(W, cfg: OracleConfig, o, d, num_iterations=2000, threshold=1e-4, far=100.0):
     """sphere_trace (models/neus_hint_model.py:359-371): march p += sdf * d until |sdf| < threshold or depth > far."""
     pts = o
-    depths = torch.zeros((o.shape[0], 1), dtype=o.dtype)
+    depths = torch.zeros((o.shape[0], 1), dtype=o.dtype, device=o.device)
     for _ in range(num_iterations):
         sdf = sdf_mlp(W, pts, cfg)["sdf"]
         converged = (torch.abs(sdf) < threshold) | (depths > far)
@@ -412,7 +414,7 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
     """render_core (models/neus_hint_model.py:475-651); background_alpha / background_color [R, S + n_outside] come from
     render_outside when the outside NeRF is on (:517-519, :630-633)."""
     R, S = z.shape
-    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((R, 1), sample_dist, dtype=z.dtype)], -1)
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((R, 1), sample_dist, dtype=z.dtype, device=z.device)], -1)
     mid_z = z + dists * 0.5
     pts = (o[:, None, :] + d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
     dirs = d[:, None, :].expand(R, S, 3).reshape(-1, 3)
@@ -444,7 +446,7 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
     z_shadow = None
     if cfg.shadow_hint:
         if warmup:
-            vis_map = torch.zeros((R, 1), dtype=z.dtype)
+            vis_map = torch.zeros((R, 1), dtype=z.dtype, device=z.device)
         else:
             with torch.no_grad():
                 vis_map, z_shadow = shadow_visibility(W, cfg, pl, hits, cos_anneal, jitter_shadow)
@@ -456,7 +458,7 @@ def render_core(W, cfg: OracleConfig, o, d, pl, z, sample_dist, bg, cos_anneal, 
     if cfg.specular_hint:
         nr = len(cfg.specular_roughness)
         if warmup:
-            spec_ray = torch.zeros((R, nr), dtype=z.dtype)
+            spec_ray = torch.zeros((R, nr), dtype=z.dtype, device=z.device)
         else:
             with torch.no_grad():
                 spec_ray = specular_cue(cfg, hit_n, pl, hits, d)
@@ -501,7 +503,7 @@ def render_forward(state: Dict[str, Tensor], cfg: OracleConfig, origins, directi
     bg = background_rgb.to(dtype) if background_rgb is not None else None
     n = cfg.n_samples
     sample_dist = 2.0 / n
-    z = near + (far - near) * torch.linspace(0.0, 1.0, n, dtype=dtype)[None, :]
+    z = near + (far - near) * torch.linspace(0.0, 1.0, n, dtype=dtype, device=near.device)[None, :]
     if is_training:
         assert jitter_primary is not None
         z = z + (jitter_primary.to(dtype) - 0.5) * 2.0 / n

@@ -264,3 +264,23 @@ def test_render_to_host_equals_forward():
             continue
         assert g.device.type == "cpu" and g.is_pinned(), k
         assert torch.equal(g, v.cpu()), k
+
+
+@torch.no_grad()
+def test_render_image_equals_chunked_render_maps():
+    """render_image (whole view in one call, ragged last slice, host rays staged on a second stream) delivers exactly the
+    per-ray maps of separate render_maps calls -- the reference's per-chunk evaluation loop, pipelines/base_pipeline.py:107-133."""
+    m, cfg, sd = build_module(T.CASES["cfg2_32x128"], "auto")
+    from nrhints_b200.workload import synthetic_rays
+    N = 1000
+    rays = nb.RayBundle(**synthetic_rays(N, seed=5)).pin_memory()
+    bg = torch.ones(1, 3)
+    want = m.render_maps(rays.to("cuda"), background_rgb=bg.cuda())
+    for src in (rays, rays.to("cuda")):
+        got = m.render_image(src, background_rgb=bg, chunk_rays=384)
+        assert set(got) == set(want)
+        for k, v in want.items():
+            assert not got[k].is_cuda and got[k].shape == v.shape
+            assert torch.allclose(got[k], v.cpu(), atol=1e-5), k         # chunk composition changes nothing (rays are independent)
+    dev = m.render_image(rays, background_rgb=bg, chunk_rays=384, to_host=False)
+    assert dev["rgb"].is_cuda and torch.allclose(dev["rgb"].cpu(), want["rgb"].cpu(), atol=1e-5)

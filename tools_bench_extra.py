@@ -1,7 +1,7 @@
 """Secondary measurements (not the headline bench.py line): hash encoding, outside-NeRF render, training step of the
 interim autograd backend, grid SDF query.  One JSON line per measurement; CUDA events, L2 flushed between iterations.
 
-    python tools_bench_extra.py [--what hash,outside,train,grid] [--iters 5]
+    python tools_bench_extra.py [--what hash,outside,train,grid,torchgpu] [--iters 5]
 """
 import argparse
 import json
@@ -33,7 +33,7 @@ def timed(fn, iters, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="hash,outside,train,grid")
+    ap.add_argument("--what", default="hash,outside,train,grid,torchgpu,image")
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
     what = set(args.what.split(","))
@@ -95,6 +95,51 @@ def main():
             ms = timed(step, max(3, args.iters // 2), flush)
             print(json.dumps({"what": "training step (BASELINE config #3: fwd + bwd + Adam), interim autograd backend", "rays": R,
                               "ms": ms, "rays_per_s": R / ms * 1e3, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+
+    if "torchgpu" in what:
+        # the reference ALGORITHM as unfused PyTorch ops on the same B200 (oracle port, fp32,
+        # allow_tf32 = False as in the reference), chunked at the reference's inference_chunk_size = 512 and at 4096
+        from oracle import nrh_oracle as orc
+        torch.backends.cuda.matmul.allow_tf32 = False
+        cfg = nb.NeuSModelConfig()
+        torch.manual_seed(3407)
+        state = {k: v.detach().to(dev) for k, v in nb.NeuSHintRenderer(cfg).state_dict().items()}
+        ocfg = orc.OracleConfig.from_model_config(cfg)
+        W = orc.effective_weights(state)
+        R = 4096
+        rays = {k: v.to(dev) for k, v in synthetic_rays(R, seed=3407).items()}
+        bg = torch.ones(1, 3, device=dev)
+        for chunk in (512, 4096):
+            def run():
+                for i in range(0, R, chunk):
+                    with torch.no_grad():
+                        orc.render_forward(W, ocfg, rays["origins"][i:i + chunk], rays["directions"][i:i + chunk],
+                                           rays["pl_positions"][i:i + chunk], rays["nears"][i:i + chunk], rays["fars"][i:i + chunk],
+                                           background_rgb=bg, effective=True)
+            torch.cuda.reset_peak_memory_stats()
+            ms = timed(run, 3, flush)
+            print(json.dumps({"what": "reference algorithm as unfused PyTorch CUDA ops on the same B200 (oracle port, fp32, TF32 off)",
+                              "rays": R, "chunk": chunk, "ms": ms, "rays_per_s": R / ms * 1e3,
+                              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+
+    if "image" in what:
+        # one 800x800 view (640 000 rays) from pinned host rays to pinned host maps
+        import time
+        torch.manual_seed(3407)
+        m = nb.NeuSHintRenderer(nb.NeuSModelConfig()).to(dev)
+        N = 800 * 800
+        rays = nb.RayBundle(**synthetic_rays(N, seed=1)).pin_memory()
+        bg = torch.ones(1, 3)
+        for chunk in (4096, 16384, 65536):
+            m.render_image(rays, background_rgb=bg, chunk_rays=chunk)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = m.render_image(rays, background_rgb=bg, chunk_rays=chunk)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            print(json.dumps({"what": "render_image: 800x800 view, pinned host rays -> pinned host per-ray maps", "chunk_rays": chunk,
+                              "s": dt, "rays_per_s": N / dt, "d2h_bytes": sum(v.numel() * 4 for v in out.values()),
+                              "workspace_gb": m._workspace.numel() / 2**30}))
 
     if "grid" in what:
         torch.manual_seed(3407)
