@@ -563,3 +563,108 @@ def synthetic_rays(R: int, seed: int = 3407, crop: int = 800):
     mid = 0.5 * (-b) / a
     return {"origins": o32, "directions": d32, "pl_positions": torch.tensor(pl, dtype=torch.float32),
             "nears": mid - 1.0, "fars": mid + 1.0}
+
+
+# --------------------------------------------------------------------------------------
+# explicit backward of (sdf, feat, grad) = sdf_mlp(pts)  -- executable spec of the fused CUDA backward
+# --------------------------------------------------------------------------------------
+def _softplus100_grad2(x: Tensor) -> Tensor:
+    """d^2 softplus(beta=100)/dx^2 = 100 s (1 - s), s = sigmoid(100 x); 0 beyond the linear threshold."""
+    s = torch.sigmoid(x * 100.0)
+    return torch.where(x * 100.0 > 20.0, torch.zeros_like(x), 100.0 * s * (1.0 - s))
+
+
+def sdf_mlp_backward(W: Dict[str, Tensor], pts: Tensor, cfg: OracleConfig, d_sdf: Tensor, d_feat: Tensor, d_grad: Tensor):
+    """Vector-Jacobian product of sdf_mlp(want_feat, want_grad) written out by hand (no autograd): given the adjoints
+    d_sdf [N,1], d_feat [N,256], d_grad [N,3] of its three outputs, returns d_pts [N,3] and the gradients of every
+    effective weight / bias.  Because `grad` is itself the result of a reverse sweep (fields/sdf_field.py:136-148 with
+    create_graph=True), its adjoint needs the second-order terms.  Two chained passes per point:
+
+      phase A (adjoint of the reverse sweep; runs in FORWARD layer order with the forward weights):
+          gb_0 = 3 PE'(3x) d_grad ;   ub_l = W_l gb_l ;   gb_{l+1} = s'_l * ub_l ;   t_l = s''_l * g_{l+1} * ub_l
+          dW_l += u_l (x) gb_l                      (u_l = s'_l * g_{l+1}: the reverse-sweep signal of the forward call)
+      phase B (ordinary backward of the forward; REVERSE layer order with the transposed weights):
+          ab_8 = w_s d_sdf / 3 + W_f^T d_feat ;   zb_l = s'_l * ab_{l+1} + t_l ;   ab_l = W_l^T zb_l
+          dW_l += zb_l (x) a_l ;  db_l += zb_l
+
+    where a_l / z_l are the forward activations / pre-activations, s' / s'' the softplus derivatives at z_l and g_l the
+    reverse-sweep adjoints.  The skip connection (a_4 = [softplus(z_3), e] / sqrt 2) splits / joins both chains.
+    This is the per-tile GEMM chain of the CUDA backward kernel; tests check it against torch.autograd in float64."""
+    L = cfg.sdf_n_layers
+    scale = cfg.sdf_scale
+    inv_sqrt2 = 1.0 / math.sqrt(2.0)
+    x0 = pts * scale
+    e = fourier_encode(x0, cfg.sdf_multires)
+    n_e = e.shape[1]
+    Wl = [W[f"sdf_network.lin{l}.W"] for l in range(L)]
+    bl = [W[f"sdf_network.lin{l}.b"] for l in range(L)]
+    w_s, W_f = W["sdf_network.out_sdf.W"], W["sdf_network.out_feat.W"]
+    # ---- forward, keeping a_l (layer inputs), s', s'' ----
+    a, s1, s2 = [], [], []
+    h = e
+    for l in range(L):
+        if l in cfg.sdf_skip_in:
+            h = torch.cat([h, e], dim=1) * inv_sqrt2
+        a.append(h)
+        pre = F.linear(h, Wl[l], bl[l])
+        s1.append(_softplus100_grad(pre)); s2.append(_softplus100_grad2(pre))
+        h = _softplus100(pre)
+    a.append(h)                                                   # a_8
+    # ---- reverse sweep, keeping g_{l+1} (adjoint of a_{l+1}, before the softplus' gate) and u_l ----
+    g_next, u = [None] * L, [None] * L
+    g = (w_s / scale).expand(pts.shape[0], -1)
+    ge_skip = None
+    for l in reversed(range(L)):
+        g_next[l] = g
+        u[l] = g * s1[l]
+        g = u[l] @ Wl[l]
+        if l in cfg.sdf_skip_in:
+            ge_skip = g[:, -n_e:] * inv_sqrt2
+            g = g[:, :-n_e] * inv_sqrt2
+    g_e = g + (ge_skip if ge_skip is not None else 0.0)           # adjoint of e
+    # ---- phase A ----
+    D, Fq = pts.shape[-1], cfg.sdf_multires
+    freqs = 2 ** torch.linspace(0.0, Fq - 1, Fq, dtype=pts.dtype, device=pts.device)
+    sarg = x0[..., None] * freqs                                                     # [N,3,F]
+    dq = d_grad * scale                                                             # adjoint of PE'^T g_e (a 3-vector)
+    gb_e = torch.cat([dq, (dq[..., None] * torch.cos(sarg) * freqs).reshape(pts.shape[0], -1),
+                      (dq[..., None] * torch.cos(sarg + torch.pi / 2.0) * freqs).reshape(pts.shape[0], -1)], dim=-1)
+    # second derivative of the encoding: d/dx0 of (PE'(x0)^T g_e) contracted with dq
+    ge_sin = g_e[:, D:D + D * Fq].reshape(-1, D, Fq)
+    ge_cos = g_e[:, D + D * Fq:].reshape(-1, D, Fq)
+    d_x0 = dq * ((-ge_sin * torch.sin(sarg) * freqs * freqs).sum(-1) + (-ge_cos * torch.sin(sarg + torch.pi / 2.0) * freqs * freqs).sum(-1))
+    dW = [torch.zeros_like(w) for w in Wl]
+    db = [torch.zeros_like(b) for b in bl]
+    t = [None] * L
+    gb = gb_e
+    for l in range(L):
+        if l in cfg.sdf_skip_in:
+            gb = torch.cat([gb, gb_e], dim=1) * inv_sqrt2          # adjoint of g_4 = [g'_4 ; ge_skip] (each was * 1/sqrt2)
+        dW[l] = dW[l] + u[l].t() @ gb
+        ub = gb @ Wl[l].t()
+        t[l] = s2[l] * g_next[l] * ub
+        gb = s1[l] * ub
+    d_ws = gb.sum(0, keepdim=True) / scale                        # g_8 = w_s / scale
+    # ---- phase B ----
+    d_ws = d_ws + (d_sdf * a[L]).sum(0, keepdim=True) / scale
+    d_bs = d_sdf.sum(0) / scale
+    dW_f = d_feat.t() @ a[L]
+    db_f = d_feat.sum(0)
+    ab = d_sdf * (w_s / scale) + d_feat @ W_f
+    eb = torch.zeros_like(e)
+    for l in reversed(range(L)):
+        zb = s1[l] * ab + t[l]
+        dW[l] = dW[l] + zb.t() @ a[l]
+        db[l] = zb.sum(0)
+        ab = zb @ Wl[l]
+        if l in cfg.sdf_skip_in:
+            eb = eb + ab[:, -n_e:] * inv_sqrt2
+            ab = ab[:, :-n_e] * inv_sqrt2
+    eb = eb + ab
+    d_x0 = d_x0 + fourier_encode_jvp_T(x0, Fq, eb)
+    out = {"d_pts": d_x0 * scale, "sdf_network.out_sdf.W": d_ws, "sdf_network.out_sdf.b": d_bs,
+           "sdf_network.out_feat.W": dW_f, "sdf_network.out_feat.b": db_f}
+    for l in range(L):
+        out[f"sdf_network.lin{l}.W"] = dW[l]
+        out[f"sdf_network.lin{l}.b"] = db[l]
+    return out
