@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 3
+#define NRH_ABI_VERSION 4
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -179,6 +179,40 @@ int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, in
 int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
                      int max_iterations, float threshold, float far_limit, int check_every,
                      float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- training: SDF fine pass with a tape + its hand-written backward (tcgen05 engine only) ------------------------------
+ * Replaces, for a training step, the reference's `sdf_network(pts)` + `sdf_network.gradient(pts)` pair of render_core /
+ * get_alpha (models/neus_hint_model.py:504-508,:335-336; fields/sdf_field.py:106-148 with create_graph=True) and the
+ * autograd double-backward through it:  (sdf, feat, grad) = f(pts; W)  and its vector-Jacobian product.
+ *   nrh_sdf_train_forward : pts [N,3] -> sdf [N], grad [N,3], feat [N,256] (fp32) + `tape`
+ *   nrh_sdf_train_backward: adjoints d_sdf [N], d_feat [N,256], d_grad [N,3] (fp32) -> d_pts [N,3] and the fp16 operand
+ *       dumps gb_l / zb_l in `bwd_out`, all in units of the power-of-two loss scale *loss_scale (device scalar chosen by the
+ *       caller so that |adjoint| * scale stays within fp16 range, e.g. 2^floor(log2(512 / max|adjoint|))).
+ * The weight gradients are point-reductions over the dumps (plain GEMMs, left to the caller / cuBLAS):
+ *       dW_l = (u_l^T gb_l) / (1024 S) + (zb_l^T a_l) / (16 S),   db_l = sum_p zb_l / S        (l = 0: a_0 = PE(3 pts), no 1/16)
+ *       dw_sdf = (sum_p gb_8 / S + d_sdf^T a_8 / 16) / 3,  dW_feat = d_feat^T a_8 / 16
+ * with a_l, u_l from the tape (fp16, x16 / x1024) and gb_l, zb_l from bwd_out; offsets from nrh_sdf_train_layout.
+ * Math: oracle/nrh_oracle.py::sdf_mlp_backward (phase A / phase B).  Workspace: forward nrh_query_workspace_bytes,
+ * backward NrhTrainLayout.bwd_workspace_bytes. */
+typedef struct NrhTrainLayout {
+    int64_t p_pad;                 /* N rounded up to a multiple of 128: row count of every dump                      */
+    uint64_t tape_tiles_off;       /* per-tile packed softplus' / reverse adjoints (opaque to the caller)             */
+    uint64_t tape_act_off;         /* 8 x [p_pad][256] fp16: a_1 .. a_8, x16                                          */
+    uint64_t tape_u_off;           /* 8 x [p_pad][256] fp16: u_0 .. u_7, x1024                                        */
+    uint64_t tape_bytes;
+    uint64_t bwd_gb0_off;          /* [p_pad][64] fp16: gb_0 (39 valid columns)                                       */
+    uint64_t bwd_gb_off;           /* 8 x [p_pad][256] fp16: gb_1 .. gb_8                                             */
+    uint64_t bwd_zb_off;           /* 8 x [p_pad][256] fp16: zb_0 .. zb_7                                             */
+    uint64_t bwd_bytes;
+    uint64_t bwd_workspace_bytes;
+} NrhTrainLayout;
+int nrh_sdf_train_layout(const NrhConfig* cfg, int64_t N, NrhTrainLayout* out);
+int nrh_sdf_train_forward(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N, float* sdf, float* grad,
+                          float* feat, void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream);
+int nrh_sdf_train_backward(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N, const void* tape,
+                           size_t tape_bytes, const float* d_sdf, const float* d_feat, const float* d_grad,
+                           const float* loss_scale, void* bwd_out, size_t bwd_bytes, float* d_pts,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* HashEncoding.pytorch_fwd (fields/encodings.py:306-366; unreachable from the reference's shipped presets, kept as a
  * standalone operator): multi-resolution hash-grid lookup with trilinear interpolation.

@@ -15,10 +15,10 @@ from pathlib import Path
 _CSRC = Path(__file__).resolve().parent / "csrc"
 _LIB_PATH = _CSRC / "libnrhints_b200.so"
 _SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh",
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc",
             "../../include/nrhints_b200.h"]
 
-NRH_ABI_VERSION = 3
+NRH_ABI_VERSION = 4
 NRH_MAX_ROUGHNESS = 4
 NRH_MAX_OUTSIDE = 64
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
@@ -63,6 +63,12 @@ class NrhOutputs(C.Structure):
         "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event")]
 
 
+class NrhTrainLayout(C.Structure):
+    _fields_ = [("p_pad", C.c_int64)] + [(n, C.c_uint64) for n in (
+        "tape_tiles_off", "tape_act_off", "tape_u_off", "tape_bytes", "bwd_gb0_off", "bwd_gb_off", "bwd_zb_off", "bwd_bytes",
+        "bwd_workspace_bytes")]
+
+
 EXPORTS = {
     "nrh_version": (C.c_int, []),
     "nrh_last_error": (C.c_char_p, []),
@@ -78,6 +84,12 @@ EXPORTS = {
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_sphere_trace": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_sdf_train_layout": (C.c_int, [C.POINTER(NrhConfig), C.c_int64, C.POINTER(NrhTrainLayout)]),
+    "nrh_sdf_train_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_sdf_train_backward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_hash_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "nrh_hash_encode_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,

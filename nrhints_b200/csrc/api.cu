@@ -348,6 +348,50 @@ int nrh_sdf_query(const NrhConfig* cfg, const void* packed, const float* pts, in
                    reinterpret_cast<float*>(workspace), workspace_bytes, sms, (cudaStream_t)stream);
 }
 
+int nrh_sdf_train_layout(const NrhConfig* cfg, int64_t N, NrhTrainLayout* out) {
+    if (!cfg || !out || N < 0) { set_error("null argument"); return NRH_ERR_INVALID; }
+    const SdfTrainLayout t = sdf_train_layout(N, sms_or_default());
+    out->p_pad = t.p_pad;
+    out->tape_tiles_off = t.tape_tiles_off; out->tape_act_off = t.tape_act_off; out->tape_u_off = t.tape_u_off; out->tape_bytes = t.tape_bytes;
+    out->bwd_gb0_off = t.bwd_gb0_off; out->bwd_gb_off = t.bwd_gb_off; out->bwd_zb_off = t.bwd_zb_off; out->bwd_bytes = t.bwd_bytes;
+    out->bwd_workspace_bytes = t.bwd_workspace_bytes;
+    return NRH_OK;
+}
+
+int nrh_sdf_train_forward(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N, float* sdf, float* grad,
+                          float* feat, void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = nrh_check_config(cfg); if (rc) return rc;
+    if (resolve_impl(*cfg) != NRH_MLP_TCGEN05) { set_error("nrh_sdf_train_forward needs the tcgen05 engine"); return NRH_ERR_UNSUPPORTED; }
+    if (N == 0) return NRH_OK;
+    if (!packed || !pts || !sdf || !grad || !feat || !tape || !workspace || N < 0) { set_error("null argument"); return NRH_ERR_INVALID; }
+    int sms; if ((rc = device_sms(&sms))) return rc;
+    const SdfTrainLayout t = sdf_train_layout(N, sms);
+    if (tape_bytes < t.tape_bytes) { set_error("tape too small: %zu < %zu", tape_bytes, t.tape_bytes); return NRH_ERR_WORKSPACE; }
+    const PackedLayout L = make_layout(*cfg);
+    return sdf_train_forward_tc(packed, L, pts, N, sdf, grad, feat, tape, reinterpret_cast<float*>(workspace), workspace_bytes, sms,
+                                (cudaStream_t)stream);
+}
+
+int nrh_sdf_train_backward(const NrhConfig* cfg, const void* packed, const float* pts, int64_t N, const void* tape,
+                           size_t tape_bytes, const float* d_sdf, const float* d_feat, const float* d_grad,
+                           const float* loss_scale, void* bwd_out, size_t bwd_bytes, float* d_pts,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = nrh_check_config(cfg); if (rc) return rc;
+    if (resolve_impl(*cfg) != NRH_MLP_TCGEN05) { set_error("nrh_sdf_train_backward needs the tcgen05 engine"); return NRH_ERR_UNSUPPORTED; }
+    if (N == 0) return NRH_OK;
+    if (!packed || !pts || !tape || !d_sdf || !d_feat || !d_grad || !loss_scale || !bwd_out || !d_pts || !workspace || N < 0) {
+        set_error("null argument"); return NRH_ERR_INVALID;
+    }
+    int sms; if ((rc = device_sms(&sms))) return rc;
+    const SdfTrainLayout t = sdf_train_layout(N, sms);
+    if (tape_bytes < t.tape_bytes || bwd_bytes < t.bwd_bytes) { set_error("tape / bwd_out too small"); return NRH_ERR_WORKSPACE; }
+    const PackedLayout L = make_layout(*cfg);
+    return sdf_train_backward_tc(packed, L, pts, N, tape, d_sdf, d_feat, d_grad, loss_scale, bwd_out, d_pts,
+                                 reinterpret_cast<float*>(workspace), workspace_bytes, sms, (cudaStream_t)stream);
+}
+
 int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
                      int max_iterations, float threshold, float far_limit, int check_every,
                      float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream) {

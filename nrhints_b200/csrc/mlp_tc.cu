@@ -55,6 +55,7 @@ struct TcLayout {
     uint32_t col[4];              // reflectance hidden layers: 6 / 4 / 4 / 4 images (single pass)
     uint32_t sdf_bias16;          // [8][256] fp32 biases * ACT_SCALE
     uint32_t col_bias16;          // [4][256] fp32 biases * ACT_SCALE
+    uint32_t feat_rev;            // 8 images of W_feat^T (backward of the feature head)
     uint32_t total;
 };
 __host__ __device__ inline TcLayout tc_layout() {
@@ -66,9 +67,16 @@ __host__ __device__ inline TcLayout tc_layout() {
     for (int l = 0; l < 4; ++l) { t.col[l] = off; off += (l == 0 ? 6 : 4) * IMG; }
     t.sdf_bias16 = off; off += SDF_LAYERS * 256 * 4;
     t.col_bias16 = off; off += 4 * 256 * 4;
+    t.feat_rev = off; off += 8 * IMG;
     t.total = off;
     return t;
 }
+
+// ---- training tape, per 128-point tile (see SdfTape in mlp_tc.cuh) ----
+constexpr uint32_t TAPE_SIG_BYTES = SDF_LAYERS * 128 * TM * 4;        // packed softplus' of the 8 layers  [8][128 col pairs][128 rows]
+constexpr uint32_t TAPE_G_BYTES = (SDF_LAYERS - 1) * 128 * TM * 4;    // packed g_1 .. g_7 (G_SCALE units) [7][128 col pairs][128 rows]
+constexpr uint32_t TAPE_GE_BYTES = PE_PAD * TM * 4;                   // g_e fp32 (G_SCALE units)          [40][128 rows]
+constexpr uint32_t TAPE_TILE_BYTES = TAPE_SIG_BYTES + TAPE_G_BYTES + TAPE_GE_BYTES;
 
 // ---- shared memory map ---------------------------------------------------------------------------------------
 constexpr uint32_t SM_A_HI = 0, SM_A_LO = 65536, SM_B = 131072, SM_MISC = SM_B + NSTAGES * STAGE;    // sdf kernel
@@ -124,6 +132,20 @@ __device__ __forceinline__ float dsig_from_packed(float pk) {
 // split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows (shared addresses)
 __device__ __forceinline__ void store_split8s(uint32_t s_hi, uint32_t s_lo, const float* x) {
     uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    sts128(s_hi, hw[0], hw[1], hw[2], hw[3]);
+    sts128(s_lo, lw[0], lw[1], lw[2], lw[3]);
+}
+// the same, also returning the four packed hi words (training tape: row-major fp16 dump of the published operand)
+__device__ __forceinline__ void store_split8s_hw(uint32_t s_hi, uint32_t s_lo, const float* x, uint32_t (&hw)[4]) {
+    uint32_t lw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
@@ -192,6 +214,11 @@ struct SdfTcParams {
     int feat_image;                    // 1: features leave as fp16 operand images (TC_TILE_FEAT_BYTES per tile)
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
+    // training tape (TRAIN instantiation only; see SdfTape in mlp_tc.cuh)
+    uint8_t* tape_tiles;               // per tile: TAPE_TILE_BYTES (softplus' of the 8 layers, reverse adjoints g_1..g_7, g_e)
+    __half* tape_act;                  // [8][P_pad][256] fp16: a_1 .. a_8 (x ACT_SCALE), row-major
+    __half* tape_u;                    // [8][P_pad][256] fp16: u_0 .. u_7 (x G_SCALE), row-major
+    int64_t p_pad;
 };
 
 // One gemm = `nsub` sub-chunks of 32 K-columns.  Every weight image serves exactly one sub-chunk: its 64 "K" columns are
@@ -222,8 +249,12 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
 // per-thread view of the epilogue: row r of the tile (== TMEM lane), 8-column group gq of every 32-wide sub-chunk.
 // The hand-off unit between the epilogue and the MMA issuer is a SUB-CHUNK of 32 activation columns (2 K-steps, 6 MMAs):
 // the tensor pipe restarts ~0.5K clk after an accumulator completes and idles only ~0.9K clk behind the last publish.
-struct Epi {
+template <bool TRAIN>
+struct EpiT {
     uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;      // a_ready[8]: one per sub-chunk
+    // training tape (TRAIN only): `dump` = row of this thread's point in the row-major fp16 [P][256] dump that receives the
+    // operand published by the CURRENT epilogue (nullptr: none); `gnx` = packed reverse-sweep adjoints of this tile
+    __half* dump; uint32_t* gnx;
     uint32_t* sig;   // [8][128 column pairs][128 rows] packed softplus' of every forward layer: half2 of copysign(exp(-100|x|), x)
     float* pe_s;     // [40][128] fp32 Fourier encoding (final chain)
     float* pk_s;     // [40][128] encoding * ACT_SCALE / sqrt2 (skip concat operand)
@@ -237,13 +268,17 @@ struct Epi {
     // operation of the thread, so callers issue their global loads / stores right AFTER publish(), never before.
     __device__ __forceinline__ void publish(int sc, const float* o) const {
         const uint32_t o8 = (uint32_t)(sc >> 1) * A_CHUNK + off[sc & 1];
-        store_split8s(s_hi + o8, s_lo + o8, o);
+        uint32_t hw[4];
+        if (TRAIN) store_split8s_hw(s_hi + o8, s_lo + o8, o, hw);
+        else store_split8s(s_hi + o8, s_lo + o8, o);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[sc]);
+        if (TRAIN) { if (dump) *reinterpret_cast<uint4*>(dump + sc * 32 + gq * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]); }
     }
 };
+using Epi = EpiT<false>;
 
 __device__ __forceinline__ void ldg8(const float* p, float (&b)[8]) {
     const float4 t0 = __ldg(reinterpret_cast<const float4*>(p)), t1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -267,8 +302,8 @@ constexpr float SP_L = 6.93147181e-3f * ACT_SCALE;
 
 // forward layer epilogue.  LT: 0 = plain, 1 = lin3 (skip concat + 1/sqrt2), 2 = lin7 (sdf head dot).
 // OUT: 0 = no operand for a next gemm, 1 = activations, 2 = reverse seed (w_s/3 * softplus' * G_SCALE)
-template <bool GRAD, int LT, int OUT, class WaitAcc>
-__device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, int l, const float* __restrict__ bias16,
+template <bool GRAD, int LT, int OUT, class EP, class WaitAcc>
+__device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int l, const float* __restrict__ bias16,
                                             const float* __restrict__ head_w, float& dot16) {
     float vA[8], bA[8], vB[8], bB[8];
     float wA[LT == 2 ? 8 : 1], wB[LT == 2 ? 8 : 1], pk[LT == 1 ? 16 : 1];
@@ -347,8 +382,8 @@ __device__ __forceinline__ void epi_forward(const Epi& E, WaitAcc&& wait_acc, in
 }
 
 // feature head epilogue: write feat (fp32 row-major, or the fp16 operand image of the tile) and, with GRAD, seed the reverse sweep
-template <bool GRAD, class WaitAcc>
-__device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
+template <bool GRAD, class EP, class WaitAcc>
+__device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
                                          float* __restrict__ feat_row, uint8_t* __restrict__ feat_tile_img, bool valid) {
     float vA[8], bA[8], vB[8], bB[8];
     const int cq = E.gq * 8;
@@ -395,8 +430,8 @@ __device__ __forceinline__ void epi_feat(const Epi& E, WaitAcc&& wait_acc, const
 
 // reverse layer epilogue (l = 7..1): g_pre_{l-1} = (W_l^T g_pre_l) * softplus'_{l-1}; SKIP = (l == 4).
 // sig holds softplus' / W_SCALE, so acc * sig is already in G_SCALE units.
-template <bool SKIP, class WaitAcc>
-__device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, int l) {
+template <bool SKIP, bool TRAIN, class EP, class WaitAcc>
+__device__ __forceinline__ void epi_reverse(const EP& E, WaitAcc&& wait_acc, int l) {
     const int cq = E.gq * 8;
     const uint32_t* const sig_l = E.sig + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
     float vA[8], vB[8];
@@ -414,19 +449,29 @@ __device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, in
         tmem_wait_ld();
         if (sc < 7) tmem_ld8(acc + (sc + 1) * 32, nv);
         float ge[8];
+        uint32_t gpk[TRAIN ? 4 : 1];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float2 pk = unpack_sig2(sg[i]);
+            float graw[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * i + h, col = sc * 32 + cq + j;
                 const float p1 = h ? pk.y : pk.x;
+                // adjoint of a_l BEFORE the softplus' gate, G_SCALE units (tape: second-order term of the backward)
+                graw[h] = (SKIP && col >= SKIP_H) ? 0.f : v[j] * (SKIP ? OS_R * INV_SQRT2 : OS_R);
                 if (!SKIP) v[j] *= dsig_from_packed(p1);
                 else if (col >= SKIP_H) { ge[j] = v[j] * (OS_R * INV_SQRT2); v[j] = 0.f; }
                 else v[j] = v[j] * INV_SQRT2 * dsig_from_packed(p1);
             }
+            if (TRAIN) gpk[TRAIN ? i : 0] = pack_sig2(graw[0], graw[1]);
         }
         E.publish(sc, v);
+        if (TRAIN) {
+            uint32_t* const g_l = E.gnx + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g_l[(size_t)(sc * 16 + i) * TM] = gpk[TRAIN ? i : 0];
+        }
         if (SKIP) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -446,7 +491,7 @@ __device__ __forceinline__ void epi_reverse(const Epi& E, WaitAcc&& wait_acc, in
     step(vB, sB, vA, 7);
 }
 
-template <bool GRAD, bool FEAT>
+template <bool GRAD, bool FEAT, bool TRAIN = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_out, float* __restrict__ gx,
               float* __restrict__ gy, float* __restrict__ gz, int64_t gstride, float* __restrict__ feat_out,
@@ -567,8 +612,9 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         }
     } else if (warp >= EPI_WARP0) {
         // ======================= epilogue warps =======================
-        Epi E;
+        EpiT<TRAIN> E;
         E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
+        E.dump = nullptr; E.gnx = nullptr;
         const int q = warp & 3;
         E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
@@ -594,6 +640,11 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         for (int64_t tile = tile0; tile < tiles_padded; tile += tstride) {
             const int64_t p = tile * TM + r;
             const bool valid = p < N;
+            if (TRAIN) {                              // softplus' / adjoints of this tile go to the tape instead of the per-CTA scratch
+                uint8_t* const tt = P.tape_tiles + (size_t)tile * TAPE_TILE_BYTES;
+                E.sig = reinterpret_cast<uint32_t*>(tt);
+                E.gnx = reinterpret_cast<uint32_t*>(tt + TAPE_SIG_BYTES);
+            }
             // ---------------- Fourier encoding -> A chunk 0 (hi/lo) + fp32 copy ----------------
             {
                 float x[3];
@@ -643,6 +694,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
                 E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? P.tlog + 256 + l * 32 : nullptr;
+                if (TRAIN) E.dump = P.tape_act + ((size_t)l * P.p_pad + p) * 256;            // this epilogue publishes a_{l+1}
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 tc_fence_before();
@@ -650,6 +702,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             {
                 constexpr int OUT = FEAT ? 1 : (GRAD ? 2 : 0);
                 E.tl = nullptr;
+                if (TRAIN) E.dump = P.tape_act + ((size_t)(SDF_LAYERS - 1) * P.p_pad + p) * 256;   // a_8
                 epi_forward<GRAD, 2, OUT>(E, wait_acc, SDF_LAYERS - 1, P.bias16 + (SDF_LAYERS - 1) * 256, P.head_w, dot);
                 tc_fence_before();
                 // sdf head: combine the four column quarters
@@ -658,6 +711,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                 if (gq == 0 && valid) sdf_out[p] = (((dot + part[r]) + (part[TM + r] + part[2 * TM + r])) * (1.0f / ACT_SCALE) + __ldg(P.head_b)) / SDF_SCALE;
             }
             if (FEAT) {
+                if (TRAIN) E.dump = P.tape_u + ((size_t)(SDF_LAYERS - 1) * P.p_pad + p) * 256;    // reverse seed u_7
                 epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + (valid ? p : 0) * 256,
                                P.feat_image ? reinterpret_cast<uint8_t*>(feat_out) + (size_t)tile * TC_TILE_FEAT_BYTES : nullptr, valid);
                 tc_fence_before();
@@ -665,8 +719,9 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             if (GRAD) {
 #pragma unroll 1
                 for (int l = SDF_LAYERS - 1; l >= 1; --l) {
-                    if (l == SDF_SKIP) epi_reverse<true>(E, wait_acc, l);
-                    else epi_reverse<false>(E, wait_acc, l);
+                    if (TRAIN) E.dump = P.tape_u + ((size_t)(l - 1) * P.p_pad + p) * 256;           // publishes u_{l-1}
+                    if (l == SDF_SKIP) epi_reverse<true, TRAIN>(E, wait_acc, l);
+                    else epi_reverse<false, TRAIN>(E, wait_acc, l);
                     tc_fence_before();
                 }
                 // ---- reverse layer 0 + chain through the encoding (39 columns; quarter 0 warps) ----
@@ -682,6 +737,11 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                         const float a = j < 16 ? v0[j] : (j < 32 ? v1[j - 16] : v2[j - 32]);
                         return fmaf(a, OS_R, E.ge_s[j * TM + r]);
                     };
+                    if (TRAIN) {                      // adjoint of the encoding (G_SCALE units): second derivative term of the backward
+                        float* const ge_t = reinterpret_cast<float*>(P.tape_tiles + (size_t)tile * TAPE_TILE_BYTES + TAPE_SIG_BYTES + TAPE_G_BYTES);
+#pragma unroll
+                        for (int j = 0; j < PE_DIM; ++j) ge_t[j * TM + r] = gcol(j);
+                    }
                     float gsum[3];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
@@ -713,6 +773,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
+
+#include "mlp_tc_bwd.inc"
 
 // ===============================================================================================================
 // Reflectance network (single fp16 pass)
@@ -1043,6 +1105,8 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
         if ((rc = build_matrix(Pf + L.sdf_wt[l], 256, 256, 256, out, 4, true, tcb + T.rev[l], IMG, st))) return rc;
     }
     if ((rc = build_matrix(Pf + L.sdf_wt[0], 256, PE_DIM, 64, 256, 4, true, tcb + T.rev[0], IMG_SMALL, st))) return rc;
+    // feature head transposed (backward): B[n = in][k = out] from the fp32 section's k-major copy
+    if ((rc = build_matrix(Pf + L.feat_wt, 256, 256, 256, 256, 4, true, tcb + T.feat_rev, IMG, st))) return rc;
     // reflectance layer 0: K order = [feat 256 | pts 3, PE(view) 27, n 3, PE(light) 27, PE(vis) 9, PE(spec) 36 | pad]
     const int cin = 316 + (cfg.shadow_hint ? 9 : 0) + (cfg.specular_hint ? 9 * cfg.n_roughness : 0);
     for (int c = 0; c < 4; ++c) {
@@ -1084,6 +1148,7 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
+    P.tape_tiles = nullptr; P.tape_act = nullptr; P.tape_u = nullptr; P.p_pad = 0;
     { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int64_t ntiles = (N + TM - 1) / TM;
@@ -1100,6 +1165,78 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     else if (wfeat) NRH_LAUNCH_TC(false, true);
     else NRH_LAUNCH_TC(false, false);
 #undef NRH_LAUNCH_TC
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+SdfTrainLayout sdf_train_layout(int64_t N, int num_sms) {
+    SdfTrainLayout t;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    t.p_pad = ntiles * TM;
+    const size_t dump = (size_t)SDF_LAYERS * t.p_pad * 256 * sizeof(__half);
+    t.tape_tiles_off = 0;
+    t.tape_act_off = (size_t)ntiles * TAPE_TILE_BYTES;
+    t.tape_u_off = t.tape_act_off + dump;
+    t.tape_bytes = t.tape_u_off + dump;
+    t.bwd_gb0_off = 0;
+    t.bwd_gb_off = (size_t)t.p_pad * 64 * sizeof(__half);
+    t.bwd_zb_off = t.bwd_gb_off + dump;
+    t.bwd_bytes = t.bwd_zb_off + dump;
+    const int64_t grid = ntiles < num_sms ? ntiles : num_sms;
+    t.bwd_workspace_bytes = (size_t)grid * BWD_SCRATCH_FLOATS * sizeof(float);
+    return t;
+}
+
+int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, float* sdf, float* grad, float* feat,
+                         void* tape, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+    if (N <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    const SdfTrainLayout TL = sdf_train_layout(N, num_sms);
+    SdfTcParams P;
+    P.feat_image = 0;
+    P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
+    P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
+    P.dbg = 0; P.tlog = nullptr;
+    uint8_t* tb = reinterpret_cast<uint8_t*>(tape);
+    P.tape_tiles = tb + TL.tape_tiles_off;
+    P.tape_act = reinterpret_cast<__half*>(tb + TL.tape_act_off);
+    P.tape_u = reinterpret_cast<__half*>(tb + TL.tape_u_off);
+    P.p_pad = TL.p_pad;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_train_forward_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
+    Strided3 S3{pts, pts + 1, pts + 2, 3};
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM));
+    sdf_tc_kernel<true, true, true><<<grid, NTHREADS, SDF_SMEM, st>>>(P, S3, N, sdf, grad, grad + 1, grad + 2, 3, feat, scratch);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
+                          const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
+                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+    if (N <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    const SdfTrainLayout TL = sdf_train_layout(N, num_sms);
+    if (scratch_bytes < TL.bwd_workspace_bytes) { set_error("sdf_train_backward_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
+    SdfBwdParams P;
+    P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    P.head_w = Pf + L.head_w;
+    P.scale = scale;
+    P.tape_tiles = reinterpret_cast<const uint8_t*>(tape) + TL.tape_tiles_off;
+    P.d_sdf = d_sdf; P.d_feat = d_feat; P.d_grad = d_grad;
+    uint8_t* ob = reinterpret_cast<uint8_t*>(bwd_out);
+    P.gb0 = reinterpret_cast<__half*>(ob + TL.bwd_gb0_off);
+    P.gb = reinterpret_cast<__half*>(ob + TL.bwd_gb_off);
+    P.zb = reinterpret_cast<__half*>(ob + TL.bwd_zb_off);
+    P.d_pts = d_pts;
+    P.p_pad = TL.p_pad;
+    const int64_t ntiles = (N + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    Strided3 S3{pts, pts + 1, pts + 2, 3};
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM));
+    sdf_bwd_tc_kernel<<<grid, NTHREADS, SDF_SMEM, st>>>(P, S3, N, scratch);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -27,4 +27,24 @@ int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Stride
 // aux_img != nullptr selects the streamed-input path: `feat` holds operand images (see above) and aux_img holds, per
 // block of 128 rays, TC_TILE_AUX_BYTES of operand images of the per-ray inputs (built by k_shade_prep); needs R % 128 == 0.
 
+// ---- training: SDF fine pass with a tape, and its backward (mlp_tc_bwd.inc) -----------------------------------------------
+// Buffer layouts (bytes) for N points; P_pad = N rounded up to 128.
+//   tape    : [tiles]  per 128-point tile: packed softplus' of the 8 layers, packed reverse adjoints g_1..g_7, g_e
+//             [act]    8 x [P_pad][256] fp16, a_1 .. a_8 (x 16), row-major      (layer inputs: dW_l = zb_l^T a_l)
+//             [u]      8 x [P_pad][256] fp16, u_0 .. u_7 (x 1024), row-major    (reverse-sweep signals: dW_l += u_l^T gb_l)
+//   bwd_out : [gb0]    [P_pad][64] fp16 (39 valid), [gb] 8 x [P_pad][256] fp16 gb_1 .. gb_8, [zb] 8 x [P_pad][256] fp16 zb_0 .. zb_7,
+//             all in units of the loss scale S
+struct SdfTrainLayout {
+    int64_t p_pad;
+    size_t tape_tiles_off, tape_act_off, tape_u_off, tape_bytes;
+    size_t bwd_gb0_off, bwd_gb_off, bwd_zb_off, bwd_bytes;
+    size_t bwd_workspace_bytes;
+};
+SdfTrainLayout sdf_train_layout(int64_t N, int num_sms);
+int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, float* sdf, float* grad, float* feat,
+                         void* tape, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);
+int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
+                          const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
+                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);
+
 }  // namespace nrh

@@ -1,0 +1,134 @@
+"""SDF fine pass with a hand-written CUDA backward (training step, BASELINE config #3).
+
+`sdf_fine(renderer, pts, weights)` returns (sdf [N,1], feat [N,256], grad [N,3]) -- what the reference computes with
+`sdf_network(pts)` and `sdf_network.gradient(pts)` (create_graph=True) in render_core / get_alpha
+(/root/reference/models/neus_hint_model.py:504-508, :335-336; /root/reference/fields/sdf_field.py:106-148) -- as ONE
+autograd node:
+
+  forward : nrh_sdf_train_forward  (tcgen05 fused MLP: forward + feature head + reverse sweep, writing a tape)
+  backward: nrh_sdf_train_backward (tcgen05, phase A / phase B chains incl. the second-order terms; csrc/mlp_tc_bwd.inc)
+            -> d_pts and fp16 operand dumps; the weight gradients are point-reductions over the dumps, done here with
+            plain library GEMMs (torch.mm, fp16 operands, fp32 accumulate/out).
+
+The effective (weight-normed) weights enter as autograd inputs so that torch differentiates the weight-norm
+re-parametrisation itself (as in the reference); their VALUES are taken from the renderer's packed weight buffer.
+Math spec: oracle/nrh_oracle.py::sdf_mlp_backward.  CUDA + tcgen05 engine only; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import _lib
+
+_ACT_SCALE = 16.0
+_G_SCALE = 1024.0
+_SDF_SCALE = 3.0
+
+
+def _mm_t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T @ b for fp16 [P,m], [P,n] operands with fp32 accumulation AND fp32 output (the sums run over ~5e5 points)."""
+    try:
+        return torch.mm(a.t(), b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return a.t().float() @ b.float()
+
+
+def _fourier(x: torch.Tensor, n_freq: int) -> torch.Tensor:
+    freqs = 2 ** torch.linspace(0.0, n_freq - 1, n_freq, device=x.device, dtype=x.dtype)
+    s = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
+    return torch.cat([x, torch.sin(torch.cat([s, s + torch.pi / 2.0], dim=-1))], dim=-1)
+
+
+class _SdfFine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, renderer, pts, *weights):
+        lib = _lib.load()
+        device = pts.device
+        packed = renderer._ensure_packed(device)
+        cfg = renderer._c_config()
+        x = pts.detach().to(torch.float32).contiguous()
+        N = x.shape[0]
+        lay = _lib.NrhTrainLayout()
+        _lib.check(lib.nrh_sdf_train_layout(C.byref(cfg), N, C.byref(lay)), "nrh_sdf_train_layout")
+        tape = torch.empty(int(lay.tape_bytes), dtype=torch.uint8, device=device)
+        sdf = torch.empty(N, dtype=torch.float32, device=device)
+        grad = torch.empty(N, 3, dtype=torch.float32, device=device)
+        feat = torch.empty(N, 256, dtype=torch.float32, device=device)
+        ws = renderer._ensure_workspace(lib.nrh_query_workspace_bytes(C.byref(cfg), N), device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.nrh_sdf_train_forward(C.byref(cfg), packed.data_ptr(), x.data_ptr(), N, sdf.data_ptr(), grad.data_ptr(),
+                                                 feat.data_ptr(), tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), stream),
+                       "nrh_sdf_train_forward")
+        ctx.renderer, ctx.lay, ctx.N = renderer, lay, N
+        ctx.packed = packed
+        ctx.save_for_backward(x, tape)
+        return sdf[:, None], feat, grad
+
+    @staticmethod
+    def backward(ctx, d_sdf, d_feat, d_grad):
+        x, tape = ctx.saved_tensors
+        renderer, lay, N = ctx.renderer, ctx.lay, ctx.N
+        lib = _lib.load()
+        device = x.device
+        cfg = renderer._c_config()
+        f32 = dict(dtype=torch.float32, device=device)
+        d_sdf = (d_sdf if d_sdf is not None else torch.zeros(N, 1, **f32)).to(torch.float32).contiguous()
+        d_feat = (d_feat if d_feat is not None else torch.zeros(N, 256, **f32)).to(torch.float32).contiguous()
+        d_grad = (d_grad if d_grad is not None else torch.zeros(N, 3, **f32)).to(torch.float32).contiguous()
+        # power-of-two loss scale, computed on the device (no host sync): largest adjoint -> ~2^9
+        amax = torch.stack([d_sdf.abs().max(), d_feat.abs().max(), d_grad.abs().max() * _SDF_SCALE]).max().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(512.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40).reshape(1).contiguous()
+        bwd = torch.empty(int(lay.bwd_bytes), dtype=torch.uint8, device=device)
+        d_pts = torch.empty(N, 3, **f32)
+        ws = renderer._ensure_workspace(int(lay.bwd_workspace_bytes), device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.nrh_sdf_train_backward(C.byref(cfg), ctx.packed.data_ptr(), x.data_ptr(), N, tape.data_ptr(), tape.numel(),
+                                                  d_sdf.data_ptr(), d_feat.data_ptr(), d_grad.data_ptr(), scale.data_ptr(),
+                                                  bwd.data_ptr(), bwd.numel(), d_pts.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                       "nrh_sdf_train_backward")
+        P = int(lay.p_pad)
+
+        def view(buf, off, n, width=256):
+            return buf[off:off + n * P * width * 2].view(torch.float16).view(n, P, width)
+        act = view(tape, int(lay.tape_act_off), 8)          # a_1 .. a_8, x16
+        u = view(tape, int(lay.tape_u_off), 8)              # u_0 .. u_7, x1024
+        gb0 = view(bwd, int(lay.bwd_gb0_off), 1, 64)[0]     # gb_0 (S units)
+        gb = view(bwd, int(lay.bwd_gb_off), 8)              # gb_1 .. gb_8
+        zb = view(bwd, int(lay.bwd_zb_off), 8)              # zb_0 .. zb_7
+        inv_s = 1.0 / scale
+        grads: List[torch.Tensor] = []
+        for l in range(8):
+            if l == 0:
+                e = torch.zeros(P, 39, **f32)
+                e[:N] = _fourier(x * _SDF_SCALE, 6)
+                dW = _mm_t(u[0], gb0)[:, :39] * (inv_s / _G_SCALE) + (zb[0].float().t() @ e) * inv_s
+            else:
+                dW = _mm_t(u[l], gb[l - 1]) * (inv_s / _G_SCALE) + _mm_t(zb[l], act[l - 1]) * (inv_s / _ACT_SCALE)
+            db = zb[l].sum(0, dtype=torch.float32) * inv_s
+            if l == 3:
+                dW, db = dW[:217], db[:217]
+            grads += [dW, db]
+        a8 = act[7]
+        d_sdf_p = torch.zeros(P, 1, **f32); d_sdf_p[:N] = d_sdf.reshape(N, 1)
+        d_ws = (gb[7].sum(0, dtype=torch.float32) * inv_s + (d_sdf_p.t() @ a8.float()).reshape(-1) / _ACT_SCALE) / _SDF_SCALE
+        d_bs = d_sdf.sum().reshape(1) / _SDF_SCALE
+        d_feat_h = torch.zeros(P, 256, dtype=torch.float16, device=device)
+        d_feat_h[:N] = (d_feat * scale).to(torch.float16)
+        dW_f = _mm_t(d_feat_h, a8) * (inv_s / _ACT_SCALE)
+        db_f = d_feat.sum(0)
+        grads += [d_ws.reshape(1, 256), d_bs, dW_f, db_f]
+        return (None, d_pts) + tuple(grads)
+
+
+def sdf_fine(renderer, pts: torch.Tensor, weights: dict):
+    """weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b) of EFFECTIVE weights (autograd-connected)."""
+    flat = []
+    for l in range(8):
+        flat += [weights["sdf_w"][l], weights["sdf_b"][l]]
+    flat += [weights["sdf_w_head"], weights["sdf_b_head"], weights["feat_w"], weights["feat_b"]]
+    return _SdfFine.apply(renderer, pts, *flat)

@@ -1,0 +1,54 @@
+"""The fused CUDA backward of the SDF fine pass (nrh_sdf_train_forward / _backward behind nrhints_b200.sdf_autograd) against
+torch.autograd through the same network (forward + create_graph input gradient), on the GPU, random adjoints."""
+import pytest
+import torch
+
+import nrh_testlib as T
+import nrhints_b200 as nb
+from nrhints_b200 import autograd_fine, sdf_autograd
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference(m, pts, d_sdf, d_feat, d_grad):
+    w = m._autograd_weights()
+    head = {"sdf_w": w["sdf_w_head"], "sdf_b": w["sdf_b_head"], "feat_w": w["feat_w"], "feat_b": w["feat_b"]}
+    x = pts.clone().requires_grad_(True)
+    out = autograd_fine.sdf_forward(w["sdf_w"], w["sdf_b"], head, x)
+    sdf, feat = out[:, :1], out[:, 1:]
+    grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True)[0]
+    loss = (sdf * d_sdf).sum() + (feat * d_feat).sum() + (grad * d_grad).sum()
+    params = [p for n, p in m.named_parameters() if n.startswith("sdf_network.")]
+    gs = torch.autograd.grad(loss, [x] + params)
+    return sdf.detach(), feat.detach(), grad.detach(), gs[0], dict(zip([n for n, _ in m.named_parameters() if n.startswith("sdf_network.")], gs[1:]))
+
+
+@pytest.mark.parametrize("kind,N", [("init", 1000), ("sharp", 384)])
+def test_fused_sdf_backward_matches_autograd(kind, N):
+    cfg = nb.NeuSModelConfig()
+    m = nb.NeuSHintRenderer(cfg, mlp_impl="tcgen05"); m.load_state_dict(T.make_state(kind, cfg)); m.cuda()
+    g = torch.Generator().manual_seed(N)
+    pts = ((torch.rand(N, 3, generator=g) - 0.5) * 2.0).cuda()
+    d_sdf = (torch.randn(N, 1, generator=g) * 0.3).cuda()
+    d_feat = (torch.randn(N, 256, generator=g) * 0.01).cuda()
+    d_grad = (torch.randn(N, 3, generator=g) * 0.1).cuda()
+    sdf_r, feat_r, grad_r, dpts_r, gp_r = _reference(m, pts, d_sdf, d_feat, d_grad)
+
+    x = pts.clone().requires_grad_(True)
+    sdf, feat, grad = sdf_autograd.sdf_fine(m, x, m._autograd_weights())
+    assert (sdf - sdf_r).abs().max() < 2e-4 and (grad - grad_r).abs().max() < 2e-3
+    assert (feat - feat_r).abs().max() < 2e-3
+    loss = (sdf * d_sdf).sum() + (feat * d_feat).sum() + (grad * d_grad).sum()
+    names = [n for n, _ in m.named_parameters() if n.startswith("sdf_network.")]
+    params = [p for n, p in m.named_parameters() if n.startswith("sdf_network.")]
+    gs = torch.autograd.grad(loss, [x] + params)
+    err = float((gs[0] - dpts_r).abs().max() / dpts_r.abs().max())
+    assert err < 1e-2, ("d_pts", err)
+    worst = 0.0
+    for n, gk in zip(names, gs[1:]):
+        gr = gp_r[n]
+        assert torch.isfinite(gk).all(), n
+        e = float((gk - gr).abs().max() / gr.abs().max().clamp_min(1e-12))
+        worst = max(worst, e)
+        assert e < 2e-2, (n, e)
+    print(kind, N, "d_pts rel err", err, "worst param rel err", worst)
