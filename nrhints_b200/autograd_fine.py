@@ -62,11 +62,14 @@ def attach_coarse_gradient(z_final: Tensor, z_coarse: Tensor) -> Tensor:
 def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
                 sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
                 background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
-                refl_freq: int = 4) -> Dict[str, Tensor]:
+                refl_freq: int = 4, sdf_fn=None) -> Dict[str, Tensor]:
     """render_core's differentiable part (models/neus_hint_model.py:475-651) given the sample positions and hints.
 
     weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b; col_w, col_b: lists of 5).
-    visibilities [R,1] / specular_cue [R,n_rough]: per-ray hint values (no gradient, as in the reference)."""
+    visibilities [R,1] / specular_cue [R,n_rough]: per-ray hint values (no gradient, as in the reference).
+    sdf_fn: optional callable pts [N,3] -> (sdf [N,1], feat [N,256], grad [N,3]) replacing the torch evaluation of the SDF
+    network and its create_graph input gradient by ONE autograd node with a hand-written CUDA forward and backward
+    (nrhints_b200/sdf_autograd.py, the tcgen05 engine)."""
     R, S = z_vals.shape
     dev, dt = z_vals.device, z_vals.dtype
     dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), sample_dist, device=dev, dtype=dt)], -1)
@@ -76,13 +79,16 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
     pls = rays_pl[:, None, :].expand(R, S, 3).reshape(-1, 3)
     head = {"sdf_w": weights["sdf_w_head"], "sdf_b": weights["sdf_b_head"], "feat_w": weights["feat_w"], "feat_b": weights["feat_b"]}
 
-    out = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, pts)
-    feat = out[:, 1:]
-    # get_alpha re-evaluates the SDF and differentiates it w.r.t. the points (:335-336)
-    with torch.enable_grad():
-        x = pts if pts.requires_grad else pts.detach().requires_grad_(True)
-        sdf = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, x)[:, :1]
-        grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
+    if sdf_fn is not None:
+        sdf, feat, grad = sdf_fn(pts)
+    else:
+        out = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, pts)
+        feat = out[:, 1:]
+        # get_alpha re-evaluates the SDF and differentiates it w.r.t. the points (:335-336)
+        with torch.enable_grad():
+            x = pts if pts.requires_grad else pts.detach().requires_grad_(True)
+            sdf = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, x)[:, :1]
+            grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
     true_cos = (dirs * grad).sum(-1, keepdim=True)
     iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
     half = iter_cos * dists.reshape(-1, 1) * 0.5

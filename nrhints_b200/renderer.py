@@ -29,6 +29,7 @@ from torch import nn
 
 from . import _lib
 from . import autograd_fine
+from . import sdf_autograd
 from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig,
                      SDFNetConfig)
 
@@ -614,8 +615,13 @@ class NeuSHintRenderer(nn.Module):
         spec = out["specular_cue"][:, 0, :] if r.specular_hint else None
         bg = background_rgb.to(**f32) if background_rgb is not None else None
         normalized = getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value
-        return autograd_fine.render_fine(self._autograd_weights(), rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
-                                         float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res)
+        w = self._autograd_weights()
+        # tcgen05 engine: the SDF network + its input gradient are one autograd node with a fused CUDA forward AND backward
+        # (sdf_autograd.py / csrc/mlp_tc_bwd.inc); the fp32 engine keeps the torch expression of the same function
+        sdf_fn = (lambda pts: sdf_autograd.sdf_fine(self, pts, w)) if self.mlp_impl in ("auto", "tcgen05") else None
+        return autograd_fine.render_fine(w, rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
+                                         float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res,
+                                         sdf_fn=sdf_fn)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy
