@@ -59,6 +59,43 @@ def attach_coarse_gradient(z_final: Tensor, z_coarse: Tensor) -> Tensor:
     return z_final + torch.zeros_like(z_final).scatter_add(1, idx, z_coarse - zc)
 
 
+class _LinearF16(torch.autograd.Function):
+    """y = x W^T + b with fp16 operands, fp32 accumulation and fp32 results (library GEMMs) in the forward AND in both
+    backward products -- the operand precision of the CUDA reflectance kernel (single fp16 pass; SURVEY.md section 7:
+    the reflectance MLP enters the pixel through a sigmoid and is insensitive to 11-bit operands).  Output adjoints are
+    scaled by a power of two before the cast so that small gradients do not flush to zero in fp16."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xh, wh = x.to(torch.float16), w.to(torch.float16)
+        ctx.save_for_backward(xh, wh)
+        return torch.mm(xh, wh.t(), out_dtype=torch.float32) + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, wh = ctx.saved_tensors
+        amax = dy.abs().max().clamp_min(1e-30)
+        s = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40)
+        dyh = (dy * s).to(torch.float16)
+        inv = 1.0 / s
+        dx = torch.mm(dyh, wh, out_dtype=torch.float32) * inv
+        dw = torch.mm(dyh.t(), xh, out_dtype=torch.float32) * inv
+        return dx, dw, dy.sum(0)
+
+
+def _linear_f16_ok(x: Tensor) -> bool:
+    if not x.is_cuda:
+        return False
+    if not hasattr(_linear_f16_ok, "ok"):
+        try:
+            a = torch.zeros(8, 8, dtype=torch.float16, device=x.device)
+            torch.mm(a, a, out_dtype=torch.float32)
+            _linear_f16_ok.ok = True
+        except (TypeError, RuntimeError):
+            _linear_f16_ok.ok = False
+    return _linear_f16_ok.ok
+
+
 def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
                 sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
                 background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
@@ -108,8 +145,9 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
         parts.append(_fourier(specular_cue[:, None, :].expand(R, S, nr).reshape(-1, nr), refl_freq))
     hcol = torch.cat(parts, dim=-1)
     n_col = len(weights["col_w"])
+    lowp = sdf_fn is not None and _linear_f16_ok(hcol)       # tcgen05 engine: same operand precision as its reflectance kernel
     for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
-        hcol = F.linear(hcol, cw, cb)
+        hcol = _LinearF16.apply(hcol, cw, cb) if lowp else F.linear(hcol, cw, cb)
         if l < n_col - 1:
             hcol = torch.relu(hcol)
     color = torch.sigmoid(hcol).reshape(R, S, 3)
