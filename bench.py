@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement (config #3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -294,6 +295,46 @@ def main():
                                "hbm_algorithmic_gbs": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9,
                                "frac_of_hbm_peak": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
 
+    # ---- BASELINE.json config #3: one training step (forward + loss + backward + Adam) on the same 4096 rays ---------
+    train = None
+    if not args.no_train:
+        torch.set_grad_enabled(True)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        gt = torch.rand(R, 3, device=dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            out = model(dev_rays, is_training=True, background_rgb=bg, global_step=60000)
+            rgb_loss = torch.nn.functional.l1_loss(out.rgb, gt, reduction="sum") / (R + 1e-5)          # pipelines/base_pipeline.py:57-62
+            gerr = (torch.linalg.norm(out.analytic_normals, ord=2, dim=-1) - 1.0) ** 2
+            eik = (out.relax_inside_sphere * gerr).sum() / (out.relax_inside_sphere.sum() + 1e-5)
+            (rgb_loss + 0.1 * eik).backward()
+            if dist is not None:                                   # the one collective of the training loop (flat buffer)
+                from nrhints_b200.grad_sync import allreduce_gradients
+                allreduce_gradients(model)
+            opt.step()
+        for _ in range(2):
+            train_step()
+        torch.cuda.synchronize()
+        tsteps = max(3, min(K, 5))
+        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(tsteps)]
+        if dist is not None:
+            dist.barrier()
+        for a, b in tev:
+            flush.zero_()
+            a.record(); train_step(); b.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev) / tsteps], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+        train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
+                 "what": "BASELINE config #3: forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU, is_training=True (jitter, "
+                         "global_step 60000); fused CUDA SDF backward (tcgen05), torch ops for compositing / reflectance MLP"
+                         + ("; flat-buffer gradient all-reduce" if dist is not None else "")}
+        torch.set_grad_enabled(False)
+        del opt
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference_leg(256, 1)
@@ -309,7 +350,7 @@ def main():
                        "l2": "256 MiB buffer rewritten between timed steps (L2 flush); per-step working set ~0.9 GB > 126 MB L2"},
             "e2e": {"value": world * R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "pinned host RayBundle -> device, forward, full RenderOutput -> pinned host buffers (pipelines/base_pipeline.py:114-120 pattern)"},
-            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train_step": train,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line))
