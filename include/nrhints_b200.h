@@ -13,6 +13,10 @@
  *                                       fields/nerf_density_field.py:66-89  -> inside nrh_render_forward
  *                                       when NrhConfig.use_outside_nerf (off by default in the reference)
  *   HashEncoding.pytorch_fwd            fields/encodings.py:306-366         -> nrh_hash_encode
+ *   RayGenerator.forward (+ autograd)   camera/ray_generator.py:75-150,
+ *                                       camera/lie_groups.py:26-116         -> nrh_raygen_forward / _backward
+ *   get_train_loss_dict (+ autograd)    pipelines/base_pipeline.py:50-69    -> nrh_train_loss
+ *   torch.optim.Adam.step               trainer/trainer.py:99,278-281       -> nrh_adam_step (flat buffer)
  *
  * Conventions
  *  - Every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer.
@@ -38,7 +42,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 4
+#define NRH_ABI_VERSION 5
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -227,6 +231,55 @@ int nrh_hash_encode(const float* pts, int64_t N, const float* table, const float
  * by the caller). */
 int nrh_hash_encode_backward(const float* pts, int64_t N, const float* d_out, const float* host_scalings, int n_levels,
                              int log2_table_size, int features_per_level, float* d_table, void* stream);
+
+/* ---- ray generation in front of the path ---------------------------------------------------------------
+ * RayGenerator.forward (camera/ray_generator.py:75-150): pixel indices + per-ray camera-to-world pose -> RayBundle fields,
+ * with the initial pose / light noise buffers (:62-73,:92-98,:121-122) and the learned per-image deltas
+ * `cam_pose_adjustment` (exp_map_SO3xR3 / exp_map_SE3, camera/lie_groups.py:26-116) and `pl_adjustment` (:124-126) applied
+ * when `img_indices` is given (video views pass NULL and get neither, :103-105).  near/far from the unit sphere when
+ * override_near_far (:133-139), else the camera's zn/zf. */
+#define NRH_CAM_OPT_OFF 0
+#define NRH_CAM_OPT_SO3XR3 1
+#define NRH_CAM_OPT_SE3 2
+typedef struct NrhCamera { float fx, fy, cx, cy, zn, zf; } NrhCamera;      /* CameraModel (camera/camera_model.py:5-24)  */
+typedef struct NrhRayGenInputs {  /* RawPixelBundle (data/data_loader.py:80-89) + the generator's tables                     */
+    const float* w_indices;       /* [R]   pixel column (the reference's [R,1] tensor, as fp32)                              */
+    const float* h_indices;       /* [R]   pixel row                                                                          */
+    const int64_t* img_indices;   /* [R]   nullable: image index of every ray, in [0, n_cameras)                              */
+    const float* poses;           /* [R,4,4] camera-to-world, 16-byte aligned                                                 */
+    const float* pls;             /* [R,3] point-light positions                                                              */
+    const float* cam_pose_noise;  /* [n_cameras,3,4] nullable: buffer `cam_pose_noise`                                        */
+    const float* pl_noise;        /* [n_cameras,3]   nullable: buffer `pl_noise`                                              */
+    const float* cam_pose_adjustment; /* [n_cameras,6] parameter; required when cam_opt_mode != off and img_indices given    */
+    const float* pl_adjustment;   /* [n_cameras,3]   nullable: parameter (pl_opt)                                             */
+    int64_t n_cameras;
+} NrhRayGenInputs;
+int nrh_raygen_forward(const NrhCamera* cam, int cam_opt_mode, int override_near_far, const NrhRayGenInputs* in, int64_t R,
+                       float* origins, float* directions, float* pl_positions, float* nears, float* fars, void* stream);
+/* Vector-Jacobian product of the above w.r.t. the two parameters: d_cam_pose_adjustment [n_cameras,6] and d_pl_adjustment
+ * [n_cameras,3] are ACCUMULATED into (fp32 atomics after an in-warp reduction; zero them first); either may be NULL, and so
+ * may any incoming adjoint (treated as zero).  Index rows that no ray touches are left alone. */
+int nrh_raygen_backward(const NrhCamera* cam, int cam_opt_mode, int override_near_far, const NrhRayGenInputs* in, int64_t R,
+                        const float* d_origins, const float* d_directions, const float* d_pl_positions, const float* d_nears,
+                        const float* d_fars, float* d_cam_pose_adjustment, float* d_pl_adjustment, void* stream);
+
+/* ---- loss and optimiser behind the path ----------------------------------------------------------------
+ * get_train_loss_dict (pipelines/base_pipeline.py:50-69) and its gradient in two launches, no host sync:
+ *   rgb_loss = sum |rgb - rgb_gt| / (R + 1e-5);  eikonal = sum(m (|n| - 1)^2) / (sum m + 1e-5), m = relax_inside_sphere;
+ *   loss = rgb_loss + igr_weight * eikonal;  psnr = 10 log10(1 / mean((rgb - rgb_gt)^2))
+ * stats (device, 8 floats): [loss, rgb_loss, eikonal_loss, psnr, sum m, sum m (|n|-1)^2, sum |d rgb|, sum (d rgb)^2].
+ * d_rgb [R,3] and d_normals [R,S,3] (both nullable) receive d loss / d rgb and d loss / d analytic_normals times
+ * `grad_scale` (a host scalar, e.g. a loss scale; 1 for plain backward). */
+int nrh_train_loss(const float* rgb, const float* rgb_gt, const float* analytic_normals, const float* relax_inside_sphere,
+                   int64_t R, int S, float igr_weight, float grad_scale, float* stats, float* d_rgb, float* d_normals,
+                   void* stream);
+
+/* One torch.optim.Adam step (amsgrad off, weight_decay 0; trainer/trainer.py:99,280) over a FLAT parameter buffer of n floats:
+ *   m <- m + (g - m)(1 - beta1);  v <- beta2 v + (1 - beta2) g g;  p <- p - (lr / (1 - beta1^step)) m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * with g = grad * grad_scale (undo a loss scale or average over ranks), in torch's operation order.  `step` is the 1-based
+ * step count after the increment; the scalar bookkeeping (bias corrections, step size) is done in double like torch's.  lr comes from the caller's scheduler (trainer/trainer.py:101-113). */
+int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, float grad_scale, void* stream);
 
 /* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
 int nrh_last_launch_count(void);

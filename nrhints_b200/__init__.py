@@ -6,9 +6,12 @@ The compute lives in nrhints_b200/csrc (hand-written CUDA behind the C ABI in in
 """
 from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NeuSRendererConfig, NormalComputationType,
                      ReflectanceNetConfig, SDFNetConfig, SingleVarianceNetConfig)
+from .ray_generator import CameraModel, RayGenerator, RayGeneratorConfig
 from .rays import RayBundle
+from .train_ops import FlatAdam, train_loss_dict
 from .renderer import NeuSHintRenderer, ReflectanceNetwork, RenderOutput, SDFNetwork, SingleVarianceNetwork
 
 __all__ = ["NeuSHintRenderer", "RenderOutput", "RayBundle", "NeuSModelConfig", "NeuSRendererConfig", "SDFNetConfig",
            "ReflectanceNetConfig", "SingleVarianceNetConfig", "NeRFConfig", "DepthComputationType", "NormalComputationType",
-           "SDFNetwork", "ReflectanceNetwork", "SingleVarianceNetwork"]
+           "SDFNetwork", "ReflectanceNetwork", "SingleVarianceNetwork", "RayGenerator", "RayGeneratorConfig", "CameraModel",
+           "FlatAdam", "train_loss_dict"]

@@ -14,11 +14,11 @@ from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
 _LIB_PATH = _CSRC / "libnrhints_b200.so"
-_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc",
+_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu"]
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "raygen_math.cuh",
             "../../include/nrhints_b200.h"]
 
-NRH_ABI_VERSION = 4
+NRH_ABI_VERSION = 5
 NRH_MAX_ROUGHNESS = 4
 NRH_MAX_OUTSIDE = 64
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
@@ -69,6 +69,17 @@ class NrhTrainLayout(C.Structure):
         "bwd_workspace_bytes")]
 
 
+class NrhCamera(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "zn", "zf")]
+
+
+class NrhRayGenInputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_indices", "h_indices", "img_indices", "poses", "pls", "cam_pose_noise", "pl_noise",
+                                          "cam_pose_adjustment", "pl_adjustment")] + [("n_cameras", C.c_int64)]
+
+
+CAM_OPT_MODES = {"off": 0, "SO3xR3": 1, "SE3": 2}
+
 EXPORTS = {
     "nrh_version": (C.c_int, []),
     "nrh_last_error": (C.c_char_p, []),
@@ -94,14 +105,26 @@ EXPORTS = {
                                   C.c_void_p, C.c_void_p]),
     "nrh_hash_encode_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p]),
+    "nrh_raygen_forward": (C.c_int, [C.POINTER(NrhCamera), C.c_int, C.c_int, C.POINTER(NrhRayGenInputs), C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_raygen_backward": (C.c_int, [C.POINTER(NrhCamera), C.c_int, C.c_int, C.POINTER(NrhRayGenInputs), C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_train_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                C.c_double, C.c_int64, C.c_float, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 
 
+_OBJ_DIR = _CSRC / "_obj"
+_NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
 def nvcc_command(out: Path = _LIB_PATH):
+    """The one-shot equivalent of build(): every source straight into the shared library."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-shared", "-Xcompiler", "-fPIC", "-o", str(out)] + [str(_CSRC / s) for s in _SOURCES]
+    return [nvcc] + _NVCC_FLAGS + ["-shared", "-o", str(out)] + [str(_CSRC / s) for s in _SOURCES]
 
 
 def needs_build() -> bool:
@@ -112,12 +135,31 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if force or needs_build():
-        cmd = nvcc_command()
-        if verbose:
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.run(cmd, check=True)
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU): one object per source, compiled
+    in parallel and re-used while neither the source nor any header is newer, then linked into libnrhints_b200.so."""
+    if not (force or needs_build()):
+        return _LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    _OBJ_DIR.mkdir(exist_ok=True)
+    hdr_t = max((_CSRC / h).resolve().stat().st_mtime for h in _HEADERS)
+
+    def compile_one(src: str) -> Path:
+        obj = _OBJ_DIR / (src[:-3] + ".o")
+        stale = force or not obj.exists() or obj.stat().st_mtime < max(hdr_t, (_CSRC / src).stat().st_mtime)
+        if stale:
+            cmd = [nvcc] + _NVCC_FLAGS + ["-c", "-o", str(obj), str(_CSRC / src)]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(_SOURCES)) as ex:
+        objs = list(ex.map(compile_one, _SOURCES))
+    cmd = [nvcc, "-shared", "-o", str(_LIB_PATH)] + [str(o) for o in objs]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
     return _LIB_PATH
 
 

@@ -10,7 +10,8 @@ gradients is split exactly where the reference puts its `torch.no_grad()` fences
   * the differentiable remainder -- SDF + feature at the 128 section mid-points, d sdf/dx with create_graph
     (fields/sdf_field.py:136-148), NeuS alpha, weights, reflectance MLP, compositing (:504-525, :583-637) --
     is expressed here with torch ops on the same device, so autograd produces the reference's gradients
-    (parameters, ray origins / directions / light positions, and near/far through the coarse samples).
+    (parameters, ray origins / directions / light positions; near / far only when n_importance == 0, because the
+    reference's up-sampling block re-assigns z_vals under no_grad, :696-713).
 
 This module only uses torch; it never touches the oracle and never runs on the CPU in the product path
 (the renderer rejects CPU tensors).  The CPU test-suite exercises it against the oracle.
@@ -47,8 +48,9 @@ def sdf_forward(sdf_w: List[Tensor], sdf_b: List[Tensor], head: Dict[str, Tensor
 
 
 def attach_coarse_gradient(z_final: Tensor, z_coarse: Tensor) -> Tensor:
-    """The reference's final z_vals are a sort of [coarse (differentiable in near/far), importance (detached)]
-    (models/neus_hint_model.py:321-322): give the coarse entries of the kernel's (detached) z their gradient path."""
+    """Give the coarse entries of the kernel's (detached) z their gradient path to near / far.  Only used when
+    n_importance == 0: with importance sampling the reference's cat_z_vals runs under no_grad (models/neus_hint_model.py:696-713)
+    and the final z_vals are detached altogether."""
     if not z_coarse.requires_grad:
         return z_final
     zc = z_coarse.detach()

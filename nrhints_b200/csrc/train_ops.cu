@@ -1,0 +1,150 @@
+// Loss and optimiser behind the ray-march path.
+//
+//   nrh_train_loss : BaseNRHintPipeline.get_train_loss_dict (/root/reference/pipelines/base_pipeline.py:50-69) and the gradient
+//                    autograd would produce for it, in two launches (reduce, then finalise + gradients).  The reference
+//                    spends ~20 ATen launches on the forward and as many in the backward; all of it is HBM-bound streaming over
+//                    `analytic_normals` [R,S,3] and `relax_inside_sphere` [R,S] (8.4 MB at 4096 x 128).
+//   nrh_adam_step  : torch.optim.Adam.step (/root/reference/trainer/trainer.py:99,280) on a flat buffer -- one launch instead of
+//                    one multi-tensor pass per operation over 46 tensors.
+// Both are bandwidth-trivial next to the MLP kernels; the point is launch count and keeping the step free of host syncs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "nrh_common.cuh"
+
+namespace nrh {
+namespace {
+
+constexpr int TL_THREADS = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// stats[4] += sum m, stats[5] += sum m (|n|-1)^2, stats[6] += sum |rgb - gt|, stats[7] += sum (rgb - gt)^2
+__global__ void __launch_bounds__(TL_THREADS)
+k_loss_reduce(const float* __restrict__ rgb, const float* __restrict__ gt, const float* __restrict__ nrm,
+              const float* __restrict__ mask, int64_t n_rgb, int64_t n_pts, float* __restrict__ stats) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t stride = (int64_t)gridDim.x * TL_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n_pts; i += stride) {
+        const float m = mask[i];
+        const float x = nrm[3 * i], y = nrm[3 * i + 1], z = nrm[3 * i + 2];
+        const float e = sqrtf(x * x + y * y + z * z) - 1.0f;
+        a[0] += m; a[1] += m * (e * e);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n_rgb; i += stride) {
+        const float d = rgb[i] - gt[i];
+        a[2] += fabsf(d); a[3] += d * d;
+    }
+    __shared__ float part[4][TL_THREADS / 32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float v = warp_sum(a[k]);
+        if ((threadIdx.x & 31) == 0) part[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int w = 0; w < TL_THREADS / 32; ++w) v += part[threadIdx.x][w];
+        atomicAdd(stats + 4 + threadIdx.x, v);
+    }
+}
+
+__global__ void __launch_bounds__(TL_THREADS)
+k_loss_finish(const float* __restrict__ rgb, const float* __restrict__ gt, const float* __restrict__ nrm,
+              const float* __restrict__ mask, int64_t R, int64_t n_rgb, int64_t n_pts, float igr_weight, float grad_scale,
+              float* __restrict__ stats, float* __restrict__ d_rgb, float* __restrict__ d_nrm) {
+    const float sum_m = stats[4], sum_e = stats[5], sum_abs = stats[6], sum_sq = stats[7];
+    const float inv_r = 1.0f / ((float)R + 1e-5f), inv_m = 1.0f / (sum_m + 1e-5f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float rgb_loss = sum_abs * inv_r, eik = sum_e * inv_m;
+        stats[0] = rgb_loss + eik * igr_weight;
+        stats[1] = rgb_loss;
+        stats[2] = eik;
+        stats[3] = 10.0f * log10f(1.0f / (sum_sq / (float)n_rgb));          // torchmetrics peak_signal_noise_ratio, data_range 1
+    }
+    const int64_t stride = (int64_t)gridDim.x * TL_THREADS;
+    if (d_nrm) {
+        const float c = 2.0f * igr_weight * inv_m * grad_scale;
+        for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n_pts; i += stride) {
+            const float x = nrm[3 * i], y = nrm[3 * i + 1], z = nrm[3 * i + 2];
+            const float len = sqrtf(x * x + y * y + z * z);
+            const float k = len > 0.0f ? c * mask[i] * (len - 1.0f) / len : 0.0f;      // torch: zero (sub)gradient of the norm at 0
+            d_nrm[3 * i] = k * x; d_nrm[3 * i + 1] = k * y; d_nrm[3 * i + 2] = k * z;
+        }
+    }
+    if (d_rgb) {
+        const float c = inv_r * grad_scale;
+        for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n_rgb; i += stride) {
+            const float d = rgb[i] - gt[i];
+            d_rgb[i] = d > 0.0f ? c : (d < 0.0f ? -c : 0.0f);
+        }
+    }
+}
+
+// torch/optim/adam.py::_single_tensor_adam in its operation order (lerp_, mul_/addcmul_, sqrt/div/add_, addcdiv_)
+__global__ void __launch_bounds__(TL_THREADS)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+       float w1, float beta2, float w2, float bc2_sqrt, float eps, float neg_step_size, float grad_scale) {
+    const int64_t stride = (int64_t)gridDim.x * TL_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        const float mi = __fmaf_rn(w1, gi - m[i], m[i]);
+        const float vi = __fmaf_rn(w2 * gi, gi, v[i] * beta2);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        m[i] = mi; v[i] = vi;
+        p[i] = __fmaf_rn(neg_step_size, mi / denom, p[i]);
+    }
+}
+
+int grid_for(int64_t n) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + TL_THREADS - 1) / TL_THREADS;
+    const int64_t cap = (int64_t)sms * 8;                      // whole waves of 8 resident 256-thread CTAs per SM
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace
+}  // namespace nrh
+
+using namespace nrh;
+
+extern "C" {
+
+int nrh_train_loss(const float* rgb, const float* rgb_gt, const float* analytic_normals, const float* relax_inside_sphere,
+                   int64_t R, int S, float igr_weight, float grad_scale, float* stats, float* d_rgb, float* d_normals,
+                   void* stream) {
+    if (!rgb || !rgb_gt || !analytic_normals || !relax_inside_sphere || !stats || R < 0 || S < 1) {
+        set_error("nrh_train_loss: null argument or bad size"); return NRH_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    NRH_CUDA_CHECK(cudaMemsetAsync(stats, 0, 8 * sizeof(float), st));
+    const int64_t n_pts = R * S, n_rgb = R * 3;
+    const int grid = grid_for(n_pts > n_rgb ? n_pts : n_rgb);
+    k_loss_reduce<<<grid, TL_THREADS, 0, st>>>(rgb, rgb_gt, analytic_normals, relax_inside_sphere, n_rgb, n_pts, stats);
+    NRH_LAUNCH_CHECK();
+    k_loss_finish<<<grid, TL_THREADS, 0, st>>>(rgb, rgb_gt, analytic_normals, relax_inside_sphere, R, n_rgb, n_pts, igr_weight,
+                                                grad_scale, stats, d_rgb, d_normals);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, float grad_scale, void* stream) {
+    if (n == 0) return NRH_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) { set_error("nrh_adam_step: null argument or step < 1"); return NRH_ERR_INVALID; }
+    // scalar bookkeeping in double, as torch does in Python (torch/optim/adam.py)
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const double step_size = lr / bc1;
+    k_adam<<<grid_for(n), TL_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
+                                                                  (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-step_size),
+                                                                  grad_scale);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+}  // extern "C"

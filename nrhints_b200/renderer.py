@@ -610,7 +610,10 @@ class NeuSHintRenderer(nn.Module):
         z_coarse = nears + (fars - nears) * torch.linspace(0.0, 1.0, n, **f32)[None, :]
         if jit_p is not None:
             z_coarse = z_coarse + (jit_p - 0.5) * 2.0 / n
-        z = autograd_fine.attach_coarse_gradient(out["z_vals"], z_coarse)
+        # The reference re-assigns z_vals inside its `with torch.no_grad()` up-sampling block (models/neus_hint_model.py:696-713),
+        # so with n_importance > 0 the final sample positions carry NO gradient (near / far get none); only without importance
+        # sampling do the coarse positions keep their path to near / far.
+        z = out["z_vals"] if r.n_importance_samples > 0 else autograd_fine.attach_coarse_gradient(out["z_vals"], z_coarse)
         vis = out["visibilities"] if r.shadow_hint else None
         spec = out["specular_cue"][:, 0, :] if r.specular_hint else None
         bg = background_rgb.to(**f32) if background_rgb is not None else None

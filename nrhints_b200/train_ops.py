@@ -1,0 +1,164 @@
+"""Loss and optimiser behind the ray-march path on the CUDA operators of csrc/train_ops.cu.
+
+  train_loss_dict  -- BaseNRHintPipeline.get_train_loss_dict (/root/reference/pipelines/base_pipeline.py:50-69): same keys; the
+                      loss tensor is autograd-connected to `rgb` and `analytic_normals` through ONE node whose backward is a
+                      scaled copy of gradients the forward launch already produced.  No host sync ('psnr' stays a device scalar;
+                      the reference's float(...) of it is a sync per step).
+  FlatAdam         -- torch.optim.Adam as the reference configures it (/root/reference/trainer/trainer.py:99: default betas/eps,
+                      no weight decay, one lr per parameter group) over FLAT buffers: parameters, gradients and both moments of
+                      a group live in one allocation each, `p.data` / `p.grad` are views into them, so zero_grad is one memset,
+                      the data-parallel gradient all-reduce is one collective on the buffer itself (no packing copies) and the
+                      step is one kernel launch per group.  state_dict()/load_state_dict() use torch.optim.Adam's layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from . import _lib
+
+
+class _TrainLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, rgb_gt, normals, mask, igr_weight: float):
+        lib = _lib.load()
+        if not rgb.is_cuda:
+            raise RuntimeError("nrhints_b200.train_loss_dict runs on CUDA tensors only (no CPU fallback)")
+        dev = rgb.device
+        c = lambda t: t.detach().to(torch.float32).contiguous()      # noqa: E731
+        rgb_c, gt_c, n_c, m_c = c(rgb), c(rgb_gt), c(normals), c(mask)
+        R, S = m_c.shape[0], m_c.shape[1]
+        stats = torch.empty(8, dtype=torch.float32, device=dev)
+        need_rgb, need_n = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        d_rgb = torch.empty_like(rgb_c) if need_rgb else None
+        d_n = torch.empty_like(n_c) if need_n else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrh_train_loss(rgb_c.data_ptr(), gt_c.data_ptr(), n_c.data_ptr(), m_c.data_ptr(), R, S, float(igr_weight), 1.0,
+                                          stats.data_ptr(), d_rgb.data_ptr() if need_rgb else None, d_n.data_ptr() if need_n else None,
+                                          torch.cuda.current_stream(dev).cuda_stream), "nrh_train_loss")
+        ctx.save_for_backward(d_rgb, d_n)
+        ctx.mark_non_differentiable(stats)
+        return stats[0], stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        d_rgb, d_n = ctx.saved_tensors
+        return (d_rgb * g_loss if d_rgb is not None else None, None, d_n * g_loss if d_n is not None else None, None, None)
+
+
+def train_loss_dict(rendering_res, rgb_gt: torch.Tensor, igr_weight: float) -> Dict[str, torch.Tensor]:
+    """get_train_loss_dict (pipelines/base_pipeline.py:50-69).  `rendering_res` needs .rgb, .analytic_normals,
+    .relax_inside_sphere and .s_val; returns loss / rgb_loss / eikonal_loss / s_val / psnr as 0-d device tensors."""
+    loss, stats = _TrainLossFn.apply(rendering_res.rgb, rgb_gt, rendering_res.analytic_normals, rendering_res.relax_inside_sphere,
+                                     float(igr_weight))
+    return {"loss": loss, "rgb_loss": stats[1], "eikonal_loss": stats[2], "s_val": rendering_res.s_val.mean(), "psnr": stats[3]}
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """Adam over flat per-group buffers (see the module docstring).  Accepts torch.optim.Adam's param-group dicts
+    ({'params': ..., 'lr': ...}); betas / eps / lr can be changed per group like in torch (LambdaLR works unchanged)."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._flat: List[Dict[str, torch.Tensor]] = []
+        for group in self.param_groups:
+            ps = [p for p in group["params"]]
+            if not ps:
+                self._flat.append({})
+                continue
+            dev = ps[0].device
+            if not all(p.is_cuda and p.device == dev and p.dtype == torch.float32 for p in ps):
+                raise RuntimeError("FlatAdam needs every parameter of a group as fp32 on one CUDA device (no CPU fallback)")
+            n = sum(p.numel() for p in ps)
+            buf = {k: torch.zeros(n, dtype=torch.float32, device=dev) for k in ("param", "grad", "exp_avg", "exp_avg_sq")}
+            off = 0
+            with torch.no_grad():
+                for p in ps:
+                    k = p.numel()
+                    buf["param"][off:off + k].copy_(p.detach().reshape(-1))
+                    p.data = buf["param"][off:off + k].view_as(p)
+                    p.grad = buf["grad"][off:off + k].view_as(p)
+                    off += k
+            buf["step"] = 0
+            self._flat.append(buf)
+
+    def flat_grads(self) -> List[torch.Tensor]:
+        """One flat gradient tensor per parameter group: the all-reduce operand (nrhints_b200/grad_sync.py)."""
+        return [b["grad"] for b in self._flat if b]
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset per group.  The gradients must stay views of the flat buffer, so they are never set to None."""
+        for group, buf in zip(self.param_groups, self._flat):
+            if not buf:
+                continue
+            buf["grad"].zero_()
+            off = 0
+            for p in group["params"]:
+                k = p.numel()
+                if p.grad is None or p.grad.data_ptr() != buf["grad"].data_ptr() + 4 * off:
+                    p.grad = buf["grad"][off:off + k].view_as(p)           # someone replaced it: re-attach
+                off += k
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for group, buf in zip(self.param_groups, self._flat):
+            if not buf:
+                continue
+            off = 0
+            for p in group["params"]:                                        # autograd may have re-bound .grad (first backward after set_to_none)
+                k = p.numel()
+                if p.grad is not None and p.grad.data_ptr() != buf["grad"].data_ptr() + 4 * off:
+                    buf["grad"][off:off + k].copy_(p.grad.reshape(-1))
+                    p.grad = buf["grad"][off:off + k].view_as(p)
+                off += k
+            buf["step"] += 1
+            b1, b2 = group["betas"]
+            dev = buf["param"].device
+            with torch.cuda.device(dev):
+                _lib.check(lib.nrh_adam_step(buf["param"].data_ptr(), buf["grad"].data_ptr(), buf["exp_avg"].data_ptr(),
+                                             buf["exp_avg_sq"].data_ptr(), buf["param"].numel(), float(group["lr"]), float(b1), float(b2),
+                                             float(group["eps"]), int(buf["step"]), float(grad_scale),
+                                             torch.cuda.current_stream(dev).cuda_stream), "nrh_adam_step")
+            # the kernel wrote through raw pointers: tell autograd / version-keyed caches (the renderer's packed weights)
+            torch.autograd.graph.increment_version(list(group["params"]))
+        return loss
+
+    # torch.optim.Adam-compatible checkpoints (trainer/trainer.py:156,223)
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        for group, buf in zip(self.param_groups, self._flat):
+            ids, off = [], 0
+            for p in group["params"]:
+                k = p.numel()
+                if buf and buf["step"] > 0:
+                    state[idx] = {"step": torch.tensor(float(buf["step"])),
+                                  "exp_avg": buf["exp_avg"][off:off + k].view_as(p).clone(),
+                                  "exp_avg_sq": buf["exp_avg_sq"][off:off + k].view_as(p).clone()}
+                ids.append(idx); idx += 1; off += k
+            g = {k: v for k, v in group.items() if k != "params"}
+            g["params"] = ids
+            groups.append(g)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        for group, buf, saved in zip(self.param_groups, self._flat, sd["param_groups"]):
+            for k, v in saved.items():
+                if k != "params":
+                    group[k] = v
+            off = 0
+            for p in group["params"]:
+                k = p.numel()
+                st = sd["state"].get(idx)
+                if st is not None:
+                    buf["exp_avg"][off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    buf["exp_avg_sq"][off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    buf["step"] = int(st["step"])
+                idx += 1; off += k

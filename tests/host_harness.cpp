@@ -3,6 +3,7 @@
 // functions the kernels call are unit-tested against the oracle without a GPU.
 // TEST INFRASTRUCTURE ONLY -- never loaded by the product.
 #include "../nrhints_b200/csrc/ray_math.cuh"
+#include "../nrhints_b200/csrc/raygen_math.cuh"
 
 using namespace nrh;
 
@@ -78,6 +79,42 @@ void h_composite_primary_bg(const float* o, const float* d, int S, const float* 
                                             inv_s, cos_anneal, SoA{w, 1}, SoA{inside, 1}, SoA{nx, 1}, SoA{ny, 1}, SoA{nz, 1},
                                             n_out, CSoA{bg_density, 1}, CSoA{bg_dist, 1});
     res[0] = pc.wsum; res[1] = pc.depth; res[2] = pc.nsum[0]; res[3] = pc.nsum[1]; res[4] = pc.nsum[2];
+}
+
+// ---- ray generation (raygen_math.cuh): the loops of k_raygen_forward / k_raygen_backward on the host ---------------------------
+// cam: fx fy cx cy zn zf.  Tables nullable.  img nullable.
+void h_raygen_forward(const float* cam, int mode, int override_nf, long R, const float* w_idx, const float* h_idx, const long* img,
+                      const float* poses, const float* pls, const float* pose_noise, const float* pl_noise, const float* adj,
+                      const float* pl_adj, float* o, float* d, float* pl, float* near, float* far) {
+    const RayGenCamera C{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5]};
+    const RayGenTables T{pose_noise, pl_noise, mode != RAYGEN_OFF ? adj : nullptr, pl_adj};
+    for (long r = 0; r < R; ++r) {
+        float pose[12];
+        for (int i = 0; i < 12; ++i) pose[i] = poses[r * 16 + i];
+        RayGenState S;
+        raygen_forward_one(C, mode, override_nf != 0, w_idx[r], h_idx[r], img ? img[r] : -1, pose, pls + r * 3, T, S, pl + r * 3,
+                           near[r], far[r]);
+        for (int i = 0; i < 3; ++i) { o[r * 3 + i] = S.o[i]; d[r * 3 + i] = S.d[i]; }
+    }
+}
+void h_raygen_backward(const float* cam, int mode, int override_nf, long R, const float* w_idx, const float* h_idx, const long* img,
+                       const float* poses, const float* pose_noise, const float* adj, const float* g_o, const float* g_d,
+                       const float* g_pl, const float* g_near, const float* g_far, float* d_adj, float* d_pl_adj) {
+    const RayGenCamera C{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5]};
+    const RayGenTables T{pose_noise, nullptr, adj, nullptr};
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    for (long r = 0; r < R; ++r) {
+        if (!img || img[r] < 0) continue;
+        if (d_adj) {
+            float pose[12], pl[3], nr, fr, g[6];
+            for (int i = 0; i < 12; ++i) pose[i] = poses[r * 16 + i];
+            RayGenState S;
+            raygen_forward_one(C, mode, override_nf != 0, w_idx[r], h_idx[r], img[r], pose, zero3, T, S, pl, nr, fr);
+            raygen_backward_one(mode, override_nf != 0, S, adj + img[r] * 6, g_o + r * 3, g_d + r * 3, g_near[r], g_far[r], g);
+            for (int i = 0; i < 6; ++i) d_adj[img[r] * 6 + i] += g[i];
+        }
+        if (d_pl_adj) for (int i = 0; i < 3; ++i) d_pl_adj[img[r] * 3 + i] += g_pl[r * 3 + i];
+    }
 }
 
 }  // extern "C"

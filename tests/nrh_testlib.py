@@ -201,3 +201,72 @@ def compare_outputs(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], per_ray_
             stats[k] = m
             assert m < tol, f"{label}: max |d {k}| = {m:.3e} >= {tol}"
     return stats
+
+
+# ---- ray generation: seeded RawPixelBundle-like inputs --------------------------------------------
+RAYGEN_CASES = {
+    # the shipped presets: no optimisation (nr-hints) and SO3xR3 pose refinement (nr-hints-cam-opt, configs/main_config.py:63)
+    "off_same_image": dict(R=96, cam_opt_mode="off", pl_opt=False, noise=False, override_near_far=True, same_image=True, seed=1),
+    "so3xr3_all_images": dict(R=200, cam_opt_mode="SO3xR3", pl_opt=False, noise=False, override_near_far=True, same_image=False, seed=2),
+    "so3xr3_same_image_plopt_noise": dict(R=130, cam_opt_mode="SO3xR3", pl_opt=True, noise=True, override_near_far=True,
+                                          same_image=True, seed=3),
+    # rotations above the clamp of exp_map_SO3xR3 (|w|^2 > 1e-4) and both branches of exp_map_SE3 (theta < / >= 1e-2)
+    "so3xr3_large": dict(R=64, cam_opt_mode="SO3xR3", pl_opt=True, noise=False, override_near_far=True, same_image=False, seed=4,
+                         adj_scale=0.3),
+    "se3_small": dict(R=64, cam_opt_mode="SE3", pl_opt=False, noise=True, override_near_far=True, same_image=False, seed=5),
+    "se3_large": dict(R=64, cam_opt_mode="SE3", pl_opt=True, noise=False, override_near_far=False, same_image=False, seed=6,
+                      adj_scale=0.3),
+    # video views: no image indices -> neither noise nor the learned deltas apply (ray_generator.py:103-105)
+    "video_no_indices": dict(R=40, cam_opt_mode="SO3xR3", pl_opt=True, noise=True, override_near_far=True, same_image=False, seed=7,
+                             no_indices=True),
+}
+
+
+def raygen_inputs(case: dict) -> dict:
+    """Cameras on a radius-4 sphere looking at the origin (camera/video_pose_utils.py:28-34 style poses), 800x800 pinhole."""
+    import math
+    g = torch.Generator().manual_seed(1000 + case["seed"])
+    R, n_cam = case["R"], 12
+    H = W = 800
+    fx = 0.5 * W / math.tan(0.5 * 0.6911)
+    camera = dict(H=H, W=W, cx=W / 2.0, cy=H / 2.0, fx=fx, fy=fx, zn=2.0, zf=6.0)
+    # per-camera poses: random point on the sphere, look-at rotation
+    c = torch.nn.functional.normalize(torch.randn(n_cam, 3, generator=g), dim=-1) * 4.0
+    fwd = -torch.nn.functional.normalize(c, dim=-1)
+    up = torch.tensor([0.0, 1.0, 0.0]).expand(n_cam, 3)
+    right = torch.nn.functional.normalize(torch.cross(fwd, up, dim=-1), dim=-1)
+    upv = torch.cross(right, fwd, dim=-1)
+    c2w = torch.eye(4).repeat(n_cam, 1, 1)
+    c2w[:, :3, 0], c2w[:, :3, 1], c2w[:, :3, 2], c2w[:, :3, 3] = right, upv, -fwd, c
+    if case.get("same_image"):
+        img = torch.full((R,), int(torch.randint(0, n_cam, (1,), generator=g)), dtype=torch.int64)
+    else:
+        img = torch.randint(0, n_cam, (R,), generator=g, dtype=torch.int64)
+    s = case.get("adj_scale", 0.004)
+    out = dict(camera=camera, n_cameras=n_cam, img_indices=None if case.get("no_indices") else img,
+               h_indices=torch.randint(0, H, (R,), generator=g).float(), w_indices=torch.randint(0, W, (R,), generator=g).float(),
+               poses=c2w[img].contiguous(), pls=4.5 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
+               cam_pose_adjustment=s * torch.randn(n_cam, 6, generator=g), pl_adjustment=0.05 * torch.randn(n_cam, 3, generator=g),
+               pl_noise=0.01 * torch.randn(n_cam, 3, generator=g))
+    from oracle import raygen_oracle as rgo
+    out["cam_pose_noise"] = rgo.exp_map_se3(0.01 * torch.randn(n_cam, 6, generator=g)).contiguous()
+    return out
+
+
+def raygen_cotangents(case: dict) -> dict:
+    g = torch.Generator().manual_seed(2000 + case["seed"])
+    R = case["R"]
+    return {"origins": torch.randn(R, 3, generator=g), "directions": torch.randn(R, 3, generator=g),
+            "pl_positions": torch.randn(R, 3, generator=g), "nears": torch.randn(R, 1, generator=g), "fars": torch.randn(R, 1, generator=g)}
+
+
+def raygen_oracle_kwargs(case: dict, inp: dict, dtype=torch.float32) -> dict:
+    """Arguments of oracle.raygen_oracle.raygen_forward for a case (tables the case does not use are None)."""
+    c = lambda t: t.to(dtype) if t is not None else None      # noqa: E731
+    return dict(camera=inp["camera"], cam_opt_mode=case["cam_opt_mode"], override_near_far=case["override_near_far"],
+                w_indices=inp["w_indices"], h_indices=inp["h_indices"], img_indices=inp["img_indices"],
+                poses=c(inp["poses"]), pls=c(inp["pls"]),
+                cam_pose_noise=c(inp["cam_pose_noise"]) if case["noise"] else None,
+                pl_noise=c(inp["pl_noise"]) if case["noise"] else None,
+                cam_pose_adjustment=c(inp["cam_pose_adjustment"]) if case["cam_opt_mode"] != "off" else None,
+                pl_adjustment=c(inp["pl_adjustment"]) if case["pl_opt"] else None)
