@@ -299,20 +299,19 @@ def main():
     train = None
     if not args.no_train:
         torch.set_grad_enabled(True)
-        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        from nrhints_b200.grad_sync import allreduce_flat
+        opt = nb.FlatAdam(model.parameters(), lr=5e-4)           # parameters / gradients / moments re-homed into flat buffers
         gt = torch.rand(R, 3, device=dev)
 
         def train_step():
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad()                                        # one memset
             out = model(dev_rays, is_training=True, background_rgb=bg, global_step=60000)
-            rgb_loss = torch.nn.functional.l1_loss(out.rgb, gt, reduction="sum") / (R + 1e-5)          # pipelines/base_pipeline.py:57-62
-            gerr = (torch.linalg.norm(out.analytic_normals, ord=2, dim=-1) - 1.0) ** 2
-            eik = (out.relax_inside_sphere * gerr).sum() / (out.relax_inside_sphere.sum() + 1e-5)
-            (rgb_loss + 0.1 * eik).backward()
-            if dist is not None:                                   # the one collective of the training loop (flat buffer)
-                from nrhints_b200.grad_sync import allreduce_gradients
-                allreduce_gradients(model)
-            opt.step()
+            loss = nb.train_loss_dict(out, gt, model.config.igr_weight)["loss"]        # pipelines/base_pipeline.py:57-62, 2 launches
+            loss.backward()
+            # the one collective of the training loop: the flat gradient buffer itself (no packing); the mean over ranks is
+            # folded into the Adam launch
+            scale = allreduce_flat(opt.flat_grads()) if dist is not None else 1.0
+            opt.step(grad_scale=scale)
         for _ in range(2):
             train_step()
         torch.cuda.synchronize()
@@ -330,7 +329,8 @@ def main():
         t_ms = float(tt.item())
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
                  "what": "BASELINE config #3: forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU, is_training=True (jitter, "
-                         "global_step 60000); fused CUDA SDF backward (tcgen05), torch ops for compositing / reflectance MLP"
+                         "global_step 60000); fused CUDA SDF forward-with-tape / backward (tcgen05), fused loss (2 launches) and flat-buffer Adam (1 launch); "
+                         "compositing in torch ops, reflectance MLP on fp16 library GEMMs"
                          + ("; flat-buffer gradient all-reduce" if dist is not None else "")}
         torch.set_grad_enabled(False)
         del opt

@@ -281,6 +281,11 @@ int nrh_train_loss(const float* rgb, const float* rgb_gt, const float* analytic_
 int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, int64_t step, float grad_scale, void* stream);
 
+/* Column sums of n_mats row-major fp16 matrices [rows][width] (consecutive matrices `mat_stride` elements apart) -> fp32
+ * out [n_mats][width] = scale * sum over rows: the bias gradients of a training step are such point-reductions over the fp16
+ * adjoint dumps (db_l = sum_p zb_l / S above).  width: multiple of 8 with 256 % (width / 8) == 0; matrices 16-byte aligned. */
+int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_t mat_stride, float scale, float* out, void* stream);
+
 /* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
 int nrh_last_launch_count(void);
 

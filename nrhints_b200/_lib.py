@@ -113,6 +113,7 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrh_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_float, C.c_void_p]),
+    "nrh_colsum_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

@@ -85,6 +85,64 @@ class _LinearF16(torch.autograd.Function):
         return dx, dw, dy.sum(0)
 
 
+class _ReflectanceF16(torch.autograd.Function):
+    """The reflectance MLP (fields/reflectance_network.py:84-96: 4 x (Linear 256, ReLU), Linear 3; the sigmoid stays outside)
+    as ONE autograd node on fp16-operand / fp32-accumulate library GEMMs -- the operand precision of the CUDA reflectance
+    kernel.  Forward: the input is padded to a multiple of 64 columns (361 -> 384: the unaligned K sends cuBLAS to a 6x slower
+    kernel), bias + ReLU run in the GEMM epilogue (torch._addmm_activation) and the hidden activations are kept in fp16.
+    Backward: ONE power-of-two loss scale for the whole chain (chosen on the device from max|dy|), adjoints stay fp16 between
+    layers (they are GEMM operands anyway), ReLU masks come from the saved activations, weight gradients are fp32-output
+    GEMMs and bias gradients one column-sum launch each (nrh_colsum_f16)."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        from .train_ops import colsum_f16  # noqa: F401  (fails loudly here if the CUDA library is missing)
+        n = len(wb) // 2
+        ws, bs = wb[:n], wb[n:]
+        P, K = x.shape
+        Kp = (K + 63) // 64 * 64
+        h16 = torch.zeros(P, Kp, dtype=torch.float16, device=x.device)
+        h16[:, :K] = x
+        acts, w16s = [h16], []
+        for l in range(n - 1):
+            w16 = ws[l].detach().to(torch.float16)
+            if l == 0:
+                w16 = torch.nn.functional.pad(w16, (0, Kp - K))
+            w16s.append(w16)
+            h16 = torch._addmm_activation(bs[l].detach().to(torch.float16), h16, w16.t())
+            acts.append(h16)
+        wl = torch.zeros(8, ws[-1].shape[1], dtype=torch.float16, device=x.device)       # 3 output rows padded to 8
+        wl[:ws[-1].shape[0]] = ws[-1].detach()
+        w16s.append(wl)
+        y = torch.mm(h16, wl.t(), out_dtype=torch.float32)[:, :ws[-1].shape[0]] + bs[-1].detach()
+        ctx.save_for_backward(*acts, *w16s)
+        ctx.n, ctx.K = n, K
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .train_ops import colsum_f16
+        n, K = ctx.n, ctx.K
+        acts, w16s = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        P = dy.shape[0]
+        amax = dy.abs().max().clamp_min(1e-30)
+        s = torch.exp2(torch.floor(torch.log2(256.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40)
+        inv = 1.0 / s
+        dz = torch.zeros(P, 8, dtype=torch.float16, device=dy.device)
+        dz[:, :dy.shape[1]] = dy * s
+        dws, dbs = [None] * n, [None] * n
+        dws[n - 1] = torch.mm(dz.t(), acts[n - 1], out_dtype=torch.float32)[:dy.shape[1]] * inv
+        dbs[n - 1] = dy.sum(0)
+        for l in range(n - 2, -1, -1):
+            dh = torch.mm(dz, w16s[l + 1])                                   # fp16 out, fp32 accumulate: the next operand
+            dz = torch.ops.aten.threshold_backward(dh, acts[l + 1], 0.0)     # ReLU mask from the saved activation
+            dw = torch.mm(dz.t(), acts[l], out_dtype=torch.float32) * inv
+            dws[l] = dw[:, :K] if l == 0 else dw
+            dbs[l] = colsum_f16(dz) * inv
+        dx = torch.mm(dz, w16s[0])[:, :K].float() * inv
+        return (dx,) + tuple(dws) + tuple(dbs)
+
+
 def _linear_f16_ok(x: Tensor) -> bool:
     if not x.is_cuda:
         return False
@@ -148,10 +206,13 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
     hcol = torch.cat(parts, dim=-1)
     n_col = len(weights["col_w"])
     lowp = sdf_fn is not None and _linear_f16_ok(hcol)       # tcgen05 engine: same operand precision as its reflectance kernel
-    for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
-        hcol = _LinearF16.apply(hcol, cw, cb) if lowp else F.linear(hcol, cw, cb)
-        if l < n_col - 1:
-            hcol = torch.relu(hcol)
+    if lowp:
+        hcol = _ReflectanceF16.apply(hcol, *weights["col_w"], *weights["col_b"])
+    else:
+        for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
+            hcol = F.linear(hcol, cw, cb)
+            if l < n_col - 1:
+                hcol = torch.relu(hcol)
     color = torch.sigmoid(hcol).reshape(R, S, 3)
     rgb = (color * w[..., None]).sum(1)
     if background_rgb is not None:

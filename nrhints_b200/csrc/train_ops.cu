@@ -7,6 +7,7 @@
 //   nrh_adam_step  : torch.optim.Adam.step (/root/reference/trainer/trainer.py:99,280) on a flat buffer -- one launch instead of
 //                    one multi-tensor pass per operation over 46 tensors.
 // Both are bandwidth-trivial next to the MLP kernels; the point is launch count and keeping the step free of host syncs.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -100,6 +101,39 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     }
 }
 
+// column sums of `n_mats` row-major fp16 matrices [rows][width] -> fp32 [n_mats][width] (bias gradients = point-reductions over
+// the fp16 adjoint dumps).  One pass at HBM speed: a thread owns 8 consecutive columns (one 16-byte load per row), a CTA walks a
+// contiguous slab of rows, partial sums meet in shared memory and leave as one atomicAdd per column and CTA.
+constexpr int CS_THREADS = 256;
+__global__ void __launch_bounds__(CS_THREADS)
+k_colsum_f16(const __half* __restrict__ mats, int64_t rows, int width, int64_t mat_stride, int slabs_per_mat, float scale,
+             float* __restrict__ out) {
+    const int mat = blockIdx.x / slabs_per_mat, slab = blockIdx.x % slabs_per_mat;
+    const int groups = width >> 3;                          // 8-column groups per row
+    const int rows_per_pass = CS_THREADS / groups;          // rows covered by the CTA per iteration
+    const int g = threadIdx.x % groups, rslot = threadIdx.x / groups;
+    const int64_t r0 = rows * slab / slabs_per_mat, r1 = rows * (slab + 1) / slabs_per_mat;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rslot < rows_per_pass) {
+        const __half* base = mats + (size_t)mat * mat_stride + g * 8;
+        for (int64_t r = r0 + rslot; r < r1; r += rows_per_pass) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + r * width));
+            const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
+    }
+    __shared__ float part[CS_THREADS * 8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[(rslot * groups + g) * 8 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < width; c += CS_THREADS) {
+        float v = 0.f;
+        for (int rs = 0; rs < rows_per_pass; ++rs) v += part[(rs * groups + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(out + (size_t)mat * width + c, v * scale);
+    }
+}
+
 int grid_for(int64_t n) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -143,6 +177,27 @@ int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
     k_adam<<<grid_for(n), TL_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
                                                                   (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-step_size),
                                                                   grad_scale);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_t mat_stride, float scale, float* out, void* stream) {
+    if (n_mats == 0 || rows == 0) return NRH_OK;
+    if (!mats || !out || n_mats < 0 || rows < 0 || width < 8 || width > 2048 || (width & 7) || (CS_THREADS % (width >> 3)) != 0 ||
+        (mat_stride & 7) || (reinterpret_cast<uintptr_t>(mats) & 15)) {
+        set_error("nrh_colsum_f16: need 16-byte aligned fp16 matrices, width a multiple of 8 with 256 %% (width / 8) == 0");
+        return NRH_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    NRH_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)n_mats * width * sizeof(float), st));
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int slabs = (sms * 8 + n_mats - 1) / n_mats;                       // ~8 CTAs per SM over all matrices
+    const int64_t max_slabs = (rows + 63) / 64;
+    if (slabs > max_slabs) slabs = (int)max_slabs;
+    if (slabs < 1) slabs = 1;
+    k_colsum_f16<<<(unsigned)(n_mats * slabs), CS_THREADS, 0, st>>>(static_cast<const __half*>(mats), rows, width, mat_stride, slabs,
+                                                                     scale, out);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -71,3 +71,14 @@ def allreduce_gradients(module: torch.nn.Module, group: Optional[dist.ProcessGro
         sync = FlatGradSync(module.parameters(), group=group, average=average)
         module._flat_grad_sync = sync
     return sync.sync()
+
+
+def allreduce_flat(flat_grads, group: Optional[dist.ProcessGroup] = None) -> float:
+    """All-reduce (sum) the flat gradient buffers of a FlatAdam optimiser IN PLACE -- the parameters' `.grad` are views of them,
+    so there is nothing to pack or unpack -- and return the factor that turns the sum into the mean over ranks (hand it to
+    FlatAdam.step(grad_scale=...), which folds it into the optimiser launch)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1.0
+    for g in flat_grads:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / dist.get_world_size(group)

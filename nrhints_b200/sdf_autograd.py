@@ -22,6 +22,7 @@ from typing import List
 import torch
 
 from . import _lib
+from .train_ops import colsum_f16
 
 _ACT_SCALE = 16.0
 _G_SCALE = 1024.0
@@ -102,24 +103,30 @@ class _SdfFine(torch.autograd.Function):
         zb = view(bwd, int(lay.bwd_zb_off), 8)              # zb_0 .. zb_7
         inv_s = 1.0 / scale
         grads: List[torch.Tensor] = []
+        # bias gradients: column sums of the fp16 dumps, all eight layers in ONE launch (nrh_colsum_f16) + the sdf head's
+        db_all = colsum_f16(zb) * inv_s                      # [8,256]
+        gb8_sum = colsum_f16(gb[7]) * inv_s                  # [256]
         for l in range(8):
             if l == 0:
-                e = torch.zeros(P, 39, **f32)
-                e[:N] = _fourier(x * _SDF_SCALE, 6)
-                dW = _mm_t(u[0], gb0)[:, :39] * (inv_s / _G_SCALE) + (zb[0].float().t() @ e) * inv_s
+                # a_0 = PE(3 pts) enters as an fp16 operand like every other activation (|PE| <= 1.5: no scaling needed)
+                e = torch.zeros(P, 64, dtype=torch.float16, device=device)
+                e[:N, :39] = _fourier(x * _SDF_SCALE, 6).to(torch.float16)
+                dW = _mm_t(u[0], gb0)[:, :39] * (inv_s / _G_SCALE) + _mm_t(zb[0], e)[:, :39] * inv_s
             else:
                 dW = _mm_t(u[l], gb[l - 1]) * (inv_s / _G_SCALE) + _mm_t(zb[l], act[l - 1]) * (inv_s / _ACT_SCALE)
-            db = zb[l].sum(0, dtype=torch.float32) * inv_s
+            db = db_all[l]
             if l == 3:
                 dW, db = dW[:217], db[:217]
             grads += [dW, db]
         a8 = act[7]
-        d_sdf_p = torch.zeros(P, 1, **f32); d_sdf_p[:N] = d_sdf.reshape(N, 1)
-        d_ws = (gb[7].sum(0, dtype=torch.float32) * inv_s + (d_sdf_p.t() @ a8.float()).reshape(-1) / _ACT_SCALE) / _SDF_SCALE
+        # head operands [d_sdf | d_feat] * scale as ONE fp16 matrix [P, 264] -> one GEMM against a_8 gives dw_sdf's second term and dW_feat
+        dh = torch.zeros(P, 264, dtype=torch.float16, device=device)
+        dh[:N, :256] = (d_feat * scale).to(torch.float16)
+        dh[:N, 256] = (d_sdf.reshape(N) * scale).to(torch.float16)
+        head = _mm_t(dh, a8) * (inv_s / _ACT_SCALE)          # [264,256]
+        d_ws = (gb8_sum + head[256]) / _SDF_SCALE
         d_bs = d_sdf.sum().reshape(1) / _SDF_SCALE
-        d_feat_h = torch.zeros(P, 256, dtype=torch.float16, device=device)
-        d_feat_h[:N] = (d_feat * scale).to(torch.float16)
-        dW_f = _mm_t(d_feat_h, a8) * (inv_s / _ACT_SCALE)
+        dW_f = head[:256]
         db_f = d_feat.sum(0)
         grads += [d_ws.reshape(1, 256), d_bs, dW_f, db_f]
         return (None, d_pts) + tuple(grads)

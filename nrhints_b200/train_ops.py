@@ -20,6 +20,20 @@ import torch
 from . import _lib
 
 
+def colsum_f16(mats: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """fp32 column sums of fp16 matrices: [n,P,W] (or [P,W]) -> [n,W] ([W]) = scale * sum over P, one launch (nrh_colsum_f16)."""
+    lib = _lib.load()
+    if not (mats.is_cuda and mats.dtype == torch.float16 and mats.is_contiguous()):
+        raise RuntimeError("colsum_f16 needs a contiguous CUDA fp16 tensor (no CPU fallback)")
+    m3 = mats if mats.dim() == 3 else mats[None]
+    n, P, W = m3.shape
+    out = torch.empty(n, W, dtype=torch.float32, device=mats.device)
+    with torch.cuda.device(mats.device):
+        _lib.check(lib.nrh_colsum_f16(m3.data_ptr(), n, P, W, P * W, float(scale), out.data_ptr(),
+                                      torch.cuda.current_stream(mats.device).cuda_stream), "nrh_colsum_f16")
+    return out if mats.dim() == 3 else out[0]
+
+
 class _TrainLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgb, rgb_gt, normals, mask, igr_weight: float):
