@@ -117,6 +117,21 @@ typedef struct NrhRays {          /* RayBundle fields (camera/ray_utils.py:214-2
     const float* hit_depths;      /* [R,1] nullable: required when depth_type == NRH_DEPTH_SPHERE_TRACE */
 } NrhRays;
 
+/* Training capture (tcgen05 engine, no outside NeRF): when NrhOutputs.train_capture is set, the primary fine pass of
+ * nrh_render_forward IS the training forward of nrh_sdf_train_forward -- it writes the tape the hand-written backward needs
+ * and hands its results to the caller, so a training step evaluates the 128 fine samples of every ray once instead of twice.
+ * Point order is the pipeline's: SAMPLE-major, point p = j * R + r (sample j of ray r), N = S * R points.
+ * In this mode the reflectance network and the final compositing are left to the caller's differentiable path:
+ * NrhOutputs.rgb / sampled_color / normal maps are NOT produced (depth, visibilities, the per-sample geometry block,
+ * specular cue and z_vals are). */
+typedef struct NrhTrainCapture {
+    void* tape; size_t tape_bytes;   /* nrh_sdf_train_layout(cfg, S * R).tape_bytes                         */
+    float* sdf;                      /* [N]                                                                 */
+    float* grad_soa;                 /* [3][N]  d sdf / d x, one plane per coordinate                       */
+    float* feat;                     /* [N,256] fp32 feature head output                                    */
+    float* pts_soa;                  /* [3][N]  the section mid-points the kernels evaluated                */
+} NrhTrainCapture;
+
 typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance;
                                    * with the outside NeRF `weights` and `sampled_color` have S + n_outside entries per ray
                                    * (the reference returns the concatenated weights, :521-524,:640) */
@@ -143,6 +158,7 @@ typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model
      * the shadow march and the reflectance network run, so that a caller that moves the result to the host
      * (pipelines/base_pipeline.py:120) can overlap that copy with the rest of the render on a second stream. */
     void* early_event;
+    const NrhTrainCapture* train_capture;   /* nullable: see NrhTrainCapture */
 } NrhOutputs;
 
 int nrh_version(void);

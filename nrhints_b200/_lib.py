@@ -60,7 +60,12 @@ class NrhOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "weights", "inside_sphere", "analytic_normals", "normalized_normals",
         "visibilities", "specular_cue", "inv_s", "z_vals", "z_shadow", "sampled_color",
-        "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event")]
+        "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event", "train_capture")]
+
+
+class NrhTrainCapture(C.Structure):
+    _fields_ = [("tape", C.c_void_p), ("tape_bytes", C.c_size_t), ("sdf", C.c_void_p), ("grad_soa", C.c_void_p),
+                ("feat", C.c_void_p), ("pts_soa", C.c_void_p)]
 
 
 class NrhTrainLayout(C.Structure):

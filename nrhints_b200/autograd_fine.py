@@ -159,21 +159,28 @@ def _linear_f16_ok(x: Tensor) -> bool:
 def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
                 sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
                 background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
-                refl_freq: int = 4, sdf_fn=None) -> Dict[str, Tensor]:
+                refl_freq: int = 4, sdf_fn=None, sample_major: bool = False) -> Dict[str, Tensor]:
     """render_core's differentiable part (models/neus_hint_model.py:475-651) given the sample positions and hints.
 
     weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b; col_w, col_b: lists of 5).
     visibilities [R,1] / specular_cue [R,n_rough]: per-ray hint values (no gradient, as in the reference).
     sdf_fn: optional callable pts [N,3] -> (sdf [N,1], feat [N,256], grad [N,3]) replacing the torch evaluation of the SDF
     network and its create_graph input gradient by ONE autograd node with a hand-written CUDA forward and backward
-    (nrhints_b200/sdf_autograd.py, the tcgen05 engine)."""
+    (nrhints_b200/sdf_autograd.py, the tcgen05 engine).
+    sample_major: evaluate the points in the render pipeline's order (p = j * R + r instead of r * S + j), so that a tape captured
+    by nrh_render_forward (NrhTrainCapture) lines up with them; results are returned ray-major either way."""
     R, S = z_vals.shape
     dev, dt = z_vals.device, z_vals.dtype
     dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), sample_dist, device=dev, dtype=dt)], -1)
     mid_z = z_vals + dists * 0.5
-    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., None]).reshape(-1, 3)
-    dirs = rays_d[:, None, :].expand(R, S, 3).reshape(-1, 3)
-    pls = rays_pl[:, None, :].expand(R, S, 3).reshape(-1, 3)
+    def per_point(t):                  # [R,S,...] -> one row per point in evaluation order
+        return (t.transpose(0, 1) if sample_major else t).reshape(R * S, *t.shape[2:])
+
+    def per_ray(t):                    # rows in evaluation order -> [R,S,...]
+        return t.reshape(S, R, *t.shape[1:]).transpose(0, 1) if sample_major else t.reshape(R, S, *t.shape[1:])
+    pts = per_point(rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., None])
+    dirs = per_point(rays_d[:, None, :].expand(R, S, 3))
+    pls = per_point(rays_pl[:, None, :].expand(R, S, 3))
     head = {"sdf_w": weights["sdf_w_head"], "sdf_b": weights["sdf_b_head"], "feat_w": weights["feat_w"], "feat_b": weights["feat_b"]}
 
     if sdf_fn is not None:
@@ -188,10 +195,10 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
             grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
     true_cos = (dirs * grad).sum(-1, keepdim=True)
     iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
-    half = iter_cos * dists.reshape(-1, 1) * 0.5
+    half = iter_cos * per_point(dists[..., None]) * 0.5
     prev_cdf = torch.sigmoid((sdf - half) * inv_s)
     next_cdf = torch.sigmoid((sdf + half) * inv_s)
-    alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1).reshape(R, S)
+    alpha = per_ray(((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1))[..., 0]
     trans = torch.cumprod(torch.cat([torch.ones((R, 1), device=dev, dtype=dt), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
     w = alpha * trans
     wsum = w.sum(-1, keepdim=True)
@@ -199,10 +206,10 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
     n_hat = F.normalize(grad, dim=-1, p=2)
     parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
     if visibilities is not None:
-        parts.append(_fourier(visibilities[:, None, :].expand(R, S, 1).reshape(-1, 1), refl_freq))
+        parts.append(_fourier(per_point(visibilities[:, None, :].expand(R, S, 1)), refl_freq))
     if specular_cue is not None:
         nr = specular_cue.shape[-1]
-        parts.append(_fourier(specular_cue[:, None, :].expand(R, S, nr).reshape(-1, nr), refl_freq))
+        parts.append(_fourier(per_point(specular_cue[:, None, :].expand(R, S, nr)), refl_freq))
     hcol = torch.cat(parts, dim=-1)
     n_col = len(weights["col_w"])
     lowp = sdf_fn is not None and _linear_f16_ok(hcol)       # tcgen05 engine: same operand precision as its reflectance kernel
@@ -213,9 +220,9 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
             hcol = F.linear(hcol, cw, cb)
             if l < n_col - 1:
                 hcol = torch.relu(hcol)
-    color = torch.sigmoid(hcol).reshape(R, S, 3)
+    color = per_ray(torch.sigmoid(hcol))
     rgb = (color * w[..., None]).sum(1)
     if background_rgb is not None:
         rgb = rgb + background_rgb * (1.0 - wsum)
-    return {"rgb": rgb, "weights": w, "analytic_normals": grad.reshape(R, S, 3),
-            "normalized_analytic_normals": n_hat.reshape(R, S, 3), "sampled_color": color}
+    return {"rgb": rgb, "weights": w, "analytic_normals": per_ray(grad),
+            "normalized_analytic_normals": per_ray(n_hat), "sampled_color": color}

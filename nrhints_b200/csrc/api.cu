@@ -460,9 +460,27 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     Strided3 P{w.prim.px, w.prim.py, w.prim.pz, 1};
     // tcgen05 engine with whole 128-ray blocks: features and per-ray inputs travel as fp16 operand images that the
     // reflectance kernel streams straight into its A operand (no conversion pass, half the feature bytes)
-    const bool streamed = resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
-    if ((rc = run_sdf(*cfg, packed, L, P, (int64_t)S * R, w.fine.sdf, w.fine.gx, w.fine.gy, w.fine.gz, 1, w.feat,
-                      w.mlp_scratch, w.mlp_scratch_bytes, sms, st, streamed))) return rc;
+    const NrhTrainCapture* cap = out->train_capture;
+    if (cap) {
+        if (resolve_impl(*cfg) != NRH_MLP_TCGEN05 || cfg->use_outside_nerf) { set_error("train_capture needs the tcgen05 engine without the outside NeRF"); return NRH_ERR_UNSUPPORTED; }
+        if (!cap->tape || !cap->sdf || !cap->grad_soa || !cap->feat || !cap->pts_soa) { set_error("train_capture: null buffer"); return NRH_ERR_INVALID; }
+        if (cap->tape_bytes < sdf_train_layout((int64_t)S * R, sms).tape_bytes) { set_error("train_capture: tape too small"); return NRH_ERR_WORKSPACE; }
+    }
+    const bool streamed = !cap && resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
+    if (cap) {
+        // the training forward (same arithmetic + tape) straight into the caller's buffers; the compositor reads them there
+        const int64_t N = (int64_t)S * R;
+        if ((rc = sdf_train_forward_tc_strided(packed, L, P, N, cap->sdf, cap->grad_soa, cap->grad_soa + N, cap->grad_soa + 2 * N, 1,
+                                               cap->feat, cap->tape, w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
+        NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.sdf, cap->sdf, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.gx, cap->grad_soa, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.gy, cap->grad_soa + N, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.gz, cap->grad_soa + 2 * N, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(cap->pts_soa, w.prim.px, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(cap->pts_soa + N, w.prim.py, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        NRH_CUDA_CHECK(cudaMemcpyAsync(cap->pts_soa + 2 * N, w.prim.pz, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = run_sdf(*cfg, packed, L, P, (int64_t)S * R, w.fine.sdf, w.fine.gx, w.fine.gy, w.fine.gz, 1, w.feat,
+                             w.mlp_scratch, w.mlp_scratch_bytes, sms, st, streamed))) return rc;
     // ---- outside NeRF on the merged sample set (render_outside, :716-724): background alpha / colour per section ----
     const int n_out = cfg->use_outside_nerf ? cfg->n_outside : 0;
     const int St = S + n_out;
@@ -512,8 +530,12 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
                                 streamed ? reinterpret_cast<unsigned char*>(w.aux_img) : nullptr, st))) return rc;
     // ---- reflectance + composite ----------------------------------------------------------------------------
     Strided3 Nrm = cfg->normalized_normals ? Strided3{w.fine.nx, w.fine.ny, w.fine.nz, 1} : Strided3{w.fine.gx, w.fine.gy, w.fine.gz, 1};
-    if ((rc = run_color(*cfg, packed, L, P, Nrm, w.feat, w.rayfeat, streamed ? w.aux_img : nullptr, R, (int64_t)S * R, w.cr, w.cg, w.cb,
-                        w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
+    if (cap) {            // training capture: reflectance + compositing belong to the caller's differentiable path
+        NRH_CUDA_CHECK(cudaMemsetAsync(w.cr, 0, sizeof(float) * (size_t)St * R, st));
+        NRH_CUDA_CHECK(cudaMemsetAsync(w.cg, 0, sizeof(float) * (size_t)St * R, st));
+        NRH_CUDA_CHECK(cudaMemsetAsync(w.cb, 0, sizeof(float) * (size_t)St * R, st));
+    } else if ((rc = run_color(*cfg, packed, L, P, Nrm, w.feat, w.rayfeat, streamed ? w.aux_img : nullptr, R, (int64_t)S * R, w.cr, w.cg, w.cb,
+                               w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
     if ((rc = launch_final_rgb(R, S, w.fine, w.rs, w.cr, w.cg, w.cb, bg_rgb, out->rgb, out->depth,
                                cfg->shadow_hint ? out->visibilities : nullptr, out->normal_map, out->normalized_normal_map,
                                cfg->specular_hint ? out->specular_cue_ray : nullptr, cfg->n_roughness, n_out, w.ob, st))) return rc;

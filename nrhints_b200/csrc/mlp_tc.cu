@@ -1187,8 +1187,9 @@ SdfTrainLayout sdf_train_layout(int64_t N, int num_sms) {
     return t;
 }
 
-int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, float* sdf, float* grad, float* feat,
-                         void* tape, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf, float* gx, float* gy,
+                                 float* gz, int64_t gstride, float* feat, void* tape, float* scratch, size_t scratch_bytes, int num_sms,
+                                 cudaStream_t st) {
     if (N <= 0) return NRH_OK;
     const float* Pf = reinterpret_cast<const float*>(packed);
     const SdfTrainLayout TL = sdf_train_layout(N, num_sms);
@@ -1206,11 +1207,16 @@ int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float*
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_train_forward_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
-    Strided3 S3{pts, pts + 1, pts + 2, 3};
     NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM));
-    sdf_tc_kernel<true, true, true><<<grid, NTHREADS, SDF_SMEM, st>>>(P, S3, N, sdf, grad, grad + 1, grad + 2, 3, feat, scratch);
+    sdf_tc_kernel<true, true, true><<<grid, NTHREADS, SDF_SMEM, st>>>(P, pts, N, sdf, gx, gy, gz, gstride, feat, scratch);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
+}
+
+int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, float* sdf, float* grad, float* feat,
+                         void* tape, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+    return sdf_train_forward_tc_strided(packed, L, Strided3{pts, pts + 1, pts + 2, 3}, N, sdf, grad, grad + 1, grad + 2, 3, feat, tape,
+                                        scratch, scratch_bytes, num_sms, st);
 }
 
 int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,

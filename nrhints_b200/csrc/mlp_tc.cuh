@@ -43,6 +43,10 @@ struct SdfTrainLayout {
 SdfTrainLayout sdf_train_layout(int64_t N, int num_sms);
 int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, float* sdf, float* grad, float* feat,
                          void* tape, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);
+// the same for points / gradients given as strided coordinate arrays (the render pipeline's sample-major SoA buffers)
+int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf, float* gx, float* gy,
+                                 float* gz, int64_t gstride, float* feat, void* tape, float* scratch, size_t scratch_bytes, int num_sms,
+                                 cudaStream_t st);
 int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
                           const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
                           float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);

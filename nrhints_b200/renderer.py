@@ -561,6 +561,18 @@ class NeuSHintRenderer(nn.Module):
         c_out = _lib.NrhOutputs(**{k: (v.data_ptr() if v is not None else None) for k, v in out.items()})
         if _early_event is not None:
             c_out.early_event = _early_event.cuda_event
+        # training capture (tcgen05 engine): the primary fine pass of the render call doubles as the forward of the SDF autograd
+        # node (it writes the tape), so the 128 fine samples per ray are evaluated once per step instead of twice
+        captured = c_cap = None
+        if needs_grad and R > 0 and self.mlp_impl in ("auto", "tcgen05") and not self.has_outside_nerf:
+            N = R * S
+            lay = _lib.NrhTrainLayout()
+            _lib.check(lib.nrh_sdf_train_layout(C.byref(cfg), N, C.byref(lay)), "nrh_sdf_train_layout")
+            captured = dict(tape=torch.empty(int(lay.tape_bytes), dtype=torch.uint8, device=device), sdf=torch.empty(N, **f32),
+                            grad_soa=torch.empty(3, N, **f32), feat=torch.empty(N, 256, **f32), pts_soa=torch.empty(3, N, **f32))
+            c_cap = _lib.NrhTrainCapture(captured["tape"].data_ptr(), captured["tape"].numel(), captured["sdf"].data_ptr(),
+                                         captured["grad_soa"].data_ptr(), captured["feat"].data_ptr(), captured["pts_soa"].data_ptr())
+            c_out.train_capture = C.addressof(c_cap)
         wsb = lib.nrh_workspace_bytes(C.byref(cfg), R)
         ws = self._ensure_workspace(wsb, device)
         if R > 0:
@@ -579,7 +591,7 @@ class NeuSHintRenderer(nn.Module):
         if needs_grad and R > 0:
             # interim autograd backend (nrhints_b200/autograd_fine.py): the no_grad parts of the reference ran in the
             # CUDA kernels above; the differentiable fine pass is re-expressed with torch ops on the same device
-            fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32)
+            fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured)
             out["rgb"], out["weights"] = fine["rgb"], fine["weights"]
             out["analytic_normals"], out["normalized_normals"] = fine["analytic_normals"], fine["normalized_analytic_normals"]
             if out["sampled_color"] is not None:
@@ -603,7 +615,7 @@ class NeuSHintRenderer(nn.Module):
             "col_b": [getattr(cn, f"lin{l}").bias for l in range(5)],
         }
 
-    def _differentiable_fine(self, ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32):
+    def _differentiable_fine(self, ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured=None):
         r = self.config.renderer
         rays_o, rays_d, rays_pl, nears, fars = (t.to(**f32) for t in ray_fields)
         n = r.n_samples
@@ -621,10 +633,14 @@ class NeuSHintRenderer(nn.Module):
         w = self._autograd_weights()
         # tcgen05 engine: the SDF network + its input gradient are one autograd node with a fused CUDA forward AND backward
         # (sdf_autograd.py / csrc/mlp_tc_bwd.inc); the fp32 engine keeps the torch expression of the same function
-        sdf_fn = (lambda pts: sdf_autograd.sdf_fine(self, pts, w)) if self.mlp_impl in ("auto", "tcgen05") else None
+        cap = None
+        if captured is not None:
+            cap = dict(tape=captured["tape"], sdf=captured["sdf"], feat=captured["feat"], grad=captured["grad_soa"].t().contiguous(),
+                       pts=captured["pts_soa"].t().contiguous())
+        sdf_fn = (lambda pts: sdf_autograd.sdf_fine(self, pts, w, cap)) if self.mlp_impl in ("auto", "tcgen05") else None
         return autograd_fine.render_fine(w, rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
                                          float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res,
-                                         sdf_fn=sdf_fn)
+                                         sdf_fn=sdf_fn, sample_major=captured is not None)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy

@@ -45,7 +45,7 @@ def _fourier(x: torch.Tensor, n_freq: int) -> torch.Tensor:
 
 class _SdfFine(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, renderer, pts, *weights):
+    def forward(ctx, renderer, pts, captured, *weights):
         lib = _lib.load()
         device = pts.device
         packed = renderer._ensure_packed(device)
@@ -54,16 +54,22 @@ class _SdfFine(torch.autograd.Function):
         N = x.shape[0]
         lay = _lib.NrhTrainLayout()
         _lib.check(lib.nrh_sdf_train_layout(C.byref(cfg), N, C.byref(lay)), "nrh_sdf_train_layout")
-        tape = torch.empty(int(lay.tape_bytes), dtype=torch.uint8, device=device)
-        sdf = torch.empty(N, dtype=torch.float32, device=device)
-        grad = torch.empty(N, 3, dtype=torch.float32, device=device)
-        feat = torch.empty(N, 256, dtype=torch.float32, device=device)
-        ws = renderer._ensure_workspace(lib.nrh_query_workspace_bytes(C.byref(cfg), N), device)
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(lib.nrh_sdf_train_forward(C.byref(cfg), packed.data_ptr(), x.data_ptr(), N, sdf.data_ptr(), grad.data_ptr(),
-                                                 feat.data_ptr(), tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), stream),
-                       "nrh_sdf_train_forward")
+        if captured is not None:
+            # nrh_render_forward already ran this forward as its primary fine pass (NrhTrainCapture): adopt tape and results
+            tape, sdf, grad, feat = captured["tape"], captured["sdf"], captured["grad"], captured["feat"]
+            assert tape.numel() >= int(lay.tape_bytes) and sdf.numel() == N
+            x = captured["pts"]                                # exactly the points the forward kernel evaluated
+        else:
+            tape = torch.empty(int(lay.tape_bytes), dtype=torch.uint8, device=device)
+            sdf = torch.empty(N, dtype=torch.float32, device=device)
+            grad = torch.empty(N, 3, dtype=torch.float32, device=device)
+            feat = torch.empty(N, 256, dtype=torch.float32, device=device)
+            ws = renderer._ensure_workspace(lib.nrh_query_workspace_bytes(C.byref(cfg), N), device)
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(lib.nrh_sdf_train_forward(C.byref(cfg), packed.data_ptr(), x.data_ptr(), N, sdf.data_ptr(), grad.data_ptr(),
+                                                     feat.data_ptr(), tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), stream),
+                           "nrh_sdf_train_forward")
         ctx.renderer, ctx.lay, ctx.N = renderer, lay, N
         ctx.packed = packed
         ctx.save_for_backward(x, tape)
@@ -129,13 +135,15 @@ class _SdfFine(torch.autograd.Function):
         dW_f = head[:256]
         db_f = d_feat.sum(0)
         grads += [d_ws.reshape(1, 256), d_bs, dW_f, db_f]
-        return (None, d_pts) + tuple(grads)
+        return (None, d_pts, None) + tuple(grads)
 
 
-def sdf_fine(renderer, pts: torch.Tensor, weights: dict):
-    """weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b) of EFFECTIVE weights (autograd-connected)."""
+def sdf_fine(renderer, pts: torch.Tensor, weights: dict, captured=None):
+    """weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b) of EFFECTIVE weights (autograd-connected).
+    captured: dict(tape, sdf [N], grad [N,3], feat [N,256]) from a nrh_render_forward call with NrhTrainCapture over the SAME
+    points in the same order -- the forward kernel is then not launched again."""
     flat = []
     for l in range(8):
         flat += [weights["sdf_w"][l], weights["sdf_b"][l]]
     flat += [weights["sdf_w_head"], weights["sdf_b_head"], weights["feat_w"], weights["feat_b"]]
-    return _SdfFine.apply(renderer, pts, *flat)
+    return _SdfFine.apply(renderer, pts, captured, *flat)

@@ -5,17 +5,14 @@ from nrhints_b200.workload import synthetic_rays
 dev = torch.device("cuda", 0)
 torch.manual_seed(3407)
 m = nb.NeuSHintRenderer(nb.NeuSModelConfig()).to(dev)
-opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+opt = nb.FlatAdam(m.parameters(), lr=5e-4)
 R = 4096
 rays = nb.RayBundle(**synthetic_rays(R, seed=3407)).to(dev)
 bg = torch.ones(1, 3, device=dev); gt = torch.rand(R, 3, device=dev)
 def step():
-    opt.zero_grad(set_to_none=True)
+    opt.zero_grad()
     out = m(rays, is_training=True, background_rgb=bg, global_step=60000)
-    rgb_loss = torch.nn.functional.l1_loss(out.rgb, gt, reduction="sum") / (R + 1e-5)
-    gerr = (torch.linalg.norm(out.analytic_normals, ord=2, dim=-1) - 1.0) ** 2
-    eik = (out.relax_inside_sphere * gerr).sum() / (out.relax_inside_sphere.sum() + 1e-5)
-    (rgb_loss + 0.1 * eik).backward()
+    nb.train_loss_dict(out, gt, 0.1)["loss"].backward()
     opt.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
