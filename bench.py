@@ -159,10 +159,29 @@ def run_reference_arm(args):
             "config": {"workload": "NRHints forward render, 64+64 samples, shadow 64+64, both hints, 800x800 synthetic scene, "
                                    f"bounded sample of {n_rays} rays per step on host CPU", "rays_per_step": n_rays},
             "cpu_baseline": base, "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to fd 1 from every
+    rank), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -353,7 +372,7 @@ def main():
             "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train_step": train,
             "wall_s_timed_region": wall,
         }
-        print(json.dumps(line))
+        _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

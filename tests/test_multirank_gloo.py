@@ -117,3 +117,36 @@ def test_two_rank_gradient_allreduce_is_one_flat_collective():
         assert p.exitcode == 0
     assert calls == [nparams] and nflat == nparams, (calls, nflat, nparams)
     assert err < 1e-4, err
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(T.ROOT))
+    from nrhints_b200.grad_sync import allreduce_flat
+    g0 = torch.arange(10, dtype=torch.float32) * (rank + 1)          # group 0 flat gradient buffer of this rank
+    g1 = torch.full((4,), float(rank))                               # group 1 (ray-generator parameters)
+    views = [g0[2:6].view(2, 2), g1[1:3]]                            # what `p.grad` are: views into the flat buffers
+    scale = allreduce_flat([g0, g1])
+    if rank == 0:
+        q.put((scale, g0.tolist(), g1.tolist(), views[0].tolist(), views[1].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_buffer_allreduce_in_place():
+    """FlatAdam's gradient buffers are reduced in place (the parameters' .grad are views of them: nothing is packed or
+    unpacked) and the mean is returned as a scale for the optimiser launch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    scale, g0, g1, v0, v1 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert scale == 0.5
+    assert g0 == [3.0 * i for i in range(10)] and g1 == [1.0] * 4
+    assert v0 == [[6.0, 9.0], [12.0, 15.0]] and v1 == [1.0, 1.0]
