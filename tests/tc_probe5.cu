@@ -126,8 +126,11 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// (c) publish cost, 512 threads (16 warps), `iters` publishes of 8 values per thread
-__global__ void __launch_bounds__(512, 1) publish_kernel(int mode, int iters, long long* clk, uint32_t* sink) {
+// (c) publish cost, 512 threads (16 warps), `iters` publishes of 8 values per thread with `work` rounds of 8 independent FMAs
+//     of "epilogue math" per publish.  mode 0: math, st.shared x2, fence.proxy.async, arrive (the engine's current order);
+//     mode 1: math, tcgen05.st x2, tcgen05.wait::st, arrive; mode 2: DEFERRED hand-off -- st.shared x2 of step i, then the math
+//     of step i+1, then fence.proxy.async + arrive for step i (the fence no longer waits for stores issued just before it).
+__global__ void __launch_bounds__(512, 1) publish_kernel(int mode, int iters, int work, long long* clk, uint32_t* sink) {
     __shared__ __align__(1024) uint8_t buf[32768];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
@@ -137,28 +140,49 @@ __global__ void __launch_bounds__(512, 1) publish_kernel(int mode, int iters, lo
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t taddr = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 8;
     const uint32_t sa = smem_u32(buf) + tid * 16;
-    float acc = tid;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = tid + j;
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
-        uint32_t w[8];
+        const bool odd = (mode == 3) && ((warp >> 2) & 1);      // mode 3: half of the warps hand off in the MIDDLE of their math
+        for (int w = 0; w < work; ++w) {
+            if (odd && w == work / 2 && i > 0) {
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar);
+            }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc = acc * 1.0001f + j; w[j] = __float_as_uint(acc); }     // a little math between publishes
-        if (mode == 0) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16384), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            for (int j = 0; j < 8; ++j) a[j] = a[j] * 1.0001f + 0.5f;
+        }
+        uint32_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w8[j] = __float_as_uint(a[j]);
+        if (mode == 2 && i > 0) {                      // hand off the PREVIOUS step: its stores are long done
             fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar);
+        }
+        if (mode == 0 || mode == 2 || mode == 3) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(w8[0]), "r"(w8[1]), "r"(w8[2]), "r"(w8[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16384), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7]) : "memory");
+            if (mode == 0 || (mode == 3 && !odd)) fence_proxy_async_smem();
         } else {
-            tmem_st4(taddr + (i & 7) * 32, w[0], w[1], w[2], w[3]);
-            tmem_st4(taddr + (i & 7) * 32 + 4, w[4], w[5], w[6], w[7]);
+            tmem_st4(taddr + (i & 7) * 32, w8[0], w8[1], w8[2], w8[3]);
+            tmem_st4(taddr + (i & 7) * 32 + 4, w8[4], w8[5], w8[6], w8[7]);
             tmem_wait_st();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar);
+        if (mode != 2 && !odd) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar);
+        }
     }
     const long long t1 = clock64();
     if (tid == 0) clk[0] = t1 - t0;
-    sink[tid] = __float_as_uint(acc);
+    sink[tid] = __float_as_uint(a[0] + a[7]);
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(slot, 512);
 }
@@ -200,12 +224,15 @@ int main() {
     }
     printf("PROBE5 %s: SS mismatches %d, TS (A in TMEM, in place) mismatches %d of %d\n", (bad1 | bad2) ? "FAIL" : "PASS", bad1, bad2, M * N);
     printf("PROBE5 480 MMAs M128 N256 K16: SS %lld clk (%.1f / MMA), TS %lld clk (%.1f / MMA)\n", clk[0], clk[0] / 480.0, clk[1], clk[1] / 480.0);
-    for (int mode = 0; mode < 2; ++mode) {
-        publish_kernel<<<1, 512>>>(mode, 256, dclk, dsink);
-        e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("PROBE5 publish CUDA ERROR: %s\n", cudaGetErrorString(e)); return 2; }
-        cudaMemcpy(clk, dclk, 8, cudaMemcpyDeviceToHost);
-        printf("PROBE5 publish mode %d (%s): %.1f clk per publish (16 warps)\n", mode, mode ? "tcgen05.st + wait::st" : "st.shared + fence.proxy.async", clk[0] / 256.0);
-    }
+    const char* names[4] = {"st.shared + fence.proxy.async", "tcgen05.st + wait::st", "st.shared, fence deferred by one step",
+                            "st.shared, half of the warps fence in the middle of their math"};
+    for (int work = 0; work <= 12; work += 6)
+        for (int mode = 0; mode < 4; ++mode) {
+            publish_kernel<<<1, 512>>>(mode, 256, work, dclk, dsink);
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("PROBE5 publish CUDA ERROR: %s\n", cudaGetErrorString(e)); return 2; }
+            cudaMemcpy(clk, dclk, 8, cudaMemcpyDeviceToHost);
+            printf("PROBE5 publish, %3d FMAs of math per step, mode %d (%s): %.1f clk per step (16 warps)\n", work * 8, mode, names[mode], clk[0] / 256.0);
+        }
     return (bad1 | bad2) ? 1 : 0;
 }
