@@ -44,6 +44,7 @@ constexpr float W_SCALE = TC_W_SCALE;
 constexpr float ACT_SCALE = TC_ACT_SCALE;
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
 constexpr float INV_SQRT2 = 0.70710678f;
+constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed off on its own
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
 constexpr float OS_R = 1.0f / W_SCALE;                 // accumulator -> reverse signal (stays in G_SCALE units)
 
@@ -213,6 +214,7 @@ struct SdfTcParams {
     const float* head_w; const float* head_b; const float* feat_b;
     int feat_image;                    // 1: features leave as fp16 operand images (TC_TILE_FEAT_BYTES per tile)
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
+    uint32_t fmask;                    // hand-off steps of the epilogue (EpiT::fence_mask)
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
     // training tape (TRAIN instantiation only; see SdfTape in mlp_tc.cuh)
     uint8_t* tape_tiles;               // per tile: TAPE_TILE_BYTES (softplus' of the 8 layers, reverse adjoints g_1..g_7, g_e)
@@ -266,15 +268,25 @@ struct EpiT {
     // 8 values -> sub-chunk sc of the A operand (hi/lo split), then signal the MMA issuer (one arrival per warp).
     // NOTE: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it drains every outstanding memory
     // operation of the thread, so callers issue their global loads / stores right AFTER publish(), never before.
+    // Hand-offs are batched: the proxy fence costs every warp ~20 clk of a CTA-wide serialised resource (16 warps x 8 sub-chunks
+    // = 128 fences per layer, tests/tc_probe5.cu), so only the steps in `fence_mask` fence and they signal every sub-chunk stored
+    // since the previous hand-off.  Sub-chunks 0 and 7 are always handed off on their own (they bound the pipeline bubble at both
+    // ends of a layer).
+    uint32_t fence_mask;
     __device__ __forceinline__ void publish(int sc, const float* o) const {
         const uint32_t o8 = (uint32_t)(sc >> 1) * A_CHUNK + off[sc & 1];
         uint32_t hw[4];
         if (TRAIN) store_split8s_hw(s_hi + o8, s_lo + o8, o, hw);
         else store_split8s(s_hi + o8, s_lo + o8, o);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[sc]);
+        if ((fence_mask >> sc) & 1u) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_ready[sc]);
+                for (int s = sc - 1; s >= 0 && !((fence_mask >> s) & 1u); --s) mbar_arrive(&a_ready[s]);
+            }
+        }
         if (TRAIN) { if (dump) *reinterpret_cast<uint4*>(dump + sc * 32 + gq * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]); }
     }
 };
@@ -614,7 +626,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         // ======================= epilogue warps =======================
         EpiT<TRAIN> E;
         E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
-        E.dump = nullptr; E.gnx = nullptr;
+        E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask;
         const int q = warp & 3;
         E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
@@ -1137,6 +1149,13 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     return NRH_OK;
 }
 
+// epilogue hand-off steps (bit sc = fence after sub-chunk sc); developer override NRH_TC_FMASK (bits 0 and 7 are forced)
+static uint32_t tc_fence_mask() {
+    const char* e = getenv("NRH_TC_FMASK");
+    const uint32_t m = e ? (uint32_t)strtoul(e, nullptr, 0) : TC_FENCE_MASK_DEFAULT;
+    return (m & 0xFFu) | 0x81u;
+}
+
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
                float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat, bool feat_as_image,
                float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
@@ -1151,6 +1170,7 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     P.tape_tiles = nullptr; P.tape_act = nullptr; P.tape_u = nullptr; P.p_pad = 0;
     { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+    P.fmask = tc_fence_mask();
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
@@ -1198,7 +1218,7 @@ int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Stri
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
-    P.dbg = 0; P.tlog = nullptr;
+    P.dbg = 0; P.tlog = nullptr; P.fmask = tc_fence_mask();
     uint8_t* tb = reinterpret_cast<uint8_t*>(tape);
     P.tape_tiles = tb + TL.tape_tiles_off;
     P.tape_act = reinterpret_cast<__half*>(tb + TL.tape_act_off);
@@ -1237,7 +1257,7 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
     P.gb = reinterpret_cast<__half*>(ob + TL.bwd_gb_off);
     P.zb = reinterpret_cast<__half*>(ob + TL.bwd_zb_off);
     P.d_pts = d_pts;
-    P.p_pad = TL.p_pad;
+    P.p_pad = TL.p_pad; P.fmask = tc_fence_mask();
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     Strided3 S3{pts, pts + 1, pts + 2, 3};
