@@ -15,7 +15,7 @@ from pathlib import Path
 _CSRC = Path(__file__).resolve().parent / "csrc"
 _LIB_PATH = _CSRC / "libnrhints_b200.so"
 _SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "raygen_math.cuh",
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "raygen_math.cuh",
             "../../include/nrhints_b200.h"]
 
 NRH_ABI_VERSION = 5

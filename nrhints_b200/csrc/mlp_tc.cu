@@ -44,6 +44,7 @@ constexpr float W_SCALE = TC_W_SCALE;
 constexpr float ACT_SCALE = TC_ACT_SCALE;
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
 constexpr float INV_SQRT2 = 0.70710678f;
+constexpr int TC_GENERATION_DEFAULT = 1;
 constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed off on its own
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
 constexpr float OS_R = 1.0f / W_SCALE;                 // accumulator -> reverse signal (stays in G_SCALE units)
@@ -579,7 +580,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        {   // the whole warp runs this loop in lockstep (uniform operands); one elected lane issues inside the *_w primitives:
+            // a single lane of a diverged warp pays an elect + R2UR.BROADCAST waterfall loop (12 SASS instructions) per MMA
             uint32_t it = 0, gc = 0, ready_seen = 0;
             const uint32_t a_hi_lo = desc_lo(smem_u32(A_hi)), a_lo_lo = desc_lo(smem_u32(A_lo)), b_lo0 = desc_lo(smem_u32(Bst));
             const uint32_t ready_s = smem_u32(ready);
@@ -590,7 +592,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
                     const int lgi = (P.dbg == 9) ? gi - 8 : gi;
-                    const bool lg = P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
+                    const bool lg = lane == 0 && P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
                     for (int sc = 0; sc < G.nsub; ++sc, ++it) {
                         if (lg) P.tlog[lgi * 32 + sc * 3 + 0] = clock64();
                         if (ready_seen <= it) {
@@ -600,6 +602,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                                 if (ready_seen > it) break;
                                 if (++spins > (1u << 27)) asm volatile("trap;");
                             }
+                            __syncwarp();
                             tc_fence_after();
                         }
                         if (lg) P.tlog[lgi * 32 + sc * 3 + 1] = clock64();
@@ -608,17 +611,17 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                             // A: K-steps 2 sc, 2 sc + 1 of the 64-wide chunk sc / 2 (32 B per K-step inside the swizzled rows)
                             const uint32_t ko = (uint32_t)(sc >> 1) * (A_CHUNK >> 4) + (uint32_t)(sc & 1) * 4;
                             const uint32_t ah = a_hi_lo + ko, al = a_lo_lo + ko, bl = b_lo0 + s * (STAGE >> 4);
-                            umma_f16_lo(acc, ah, bl, idesc, (uint32_t)(sc != 0));        // A_hi * W_hi
-                            umma_f16_lo(acc, ah + 2, bl + 2, idesc, 1u);
-                            umma_f16_lo(acc, al, bl, idesc, 1u);                          // A_lo * W_hi
-                            umma_f16_lo(acc, al + 2, bl + 2, idesc, 1u);
-                            umma_f16_lo(acc, ah, bl + 4, idesc, 1u);                      // A_hi * W_lo
-                            umma_f16_lo(acc, ah + 2, bl + 6, idesc, 1u);
+                            umma_f16_lo_w(acc, ah, bl, idesc, (uint32_t)(sc != 0));        // A_hi * W_hi
+                            umma_f16_lo_w(acc, ah + 2, bl + 2, idesc, 1u);
+                            umma_f16_lo_w(acc, al, bl, idesc, 1u);                          // A_lo * W_hi
+                            umma_f16_lo_w(acc, al + 2, bl + 2, idesc, 1u);
+                            umma_f16_lo_w(acc, ah, bl + 4, idesc, 1u);                      // A_hi * W_lo
+                            umma_f16_lo_w(acc, ah + 2, bl + 6, idesc, 1u);
                         }
-                        umma_commit(&b_empty[s]);
+                        umma_commit_w(&b_empty[s]);
                         if (lg) P.tlog[lgi * 32 + sc * 3 + 2] = clock64();
                     }
-                    umma_commit(&acc_full[gc & 1]);
+                    umma_commit_w(&acc_full[gc & 1]);
                     if (lg) P.tlog[lgi * 32 + 24] = clock64();
                 }
         }
@@ -787,6 +790,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
 }
 
 #include "mlp_tc_bwd.inc"
+#include "mlp_tc2.inc"
 
 // ===============================================================================================================
 // Reflectance network (single fp16 pass)
@@ -1156,6 +1160,12 @@ static uint32_t tc_fence_mask() {
     return (m & 0xFFu) | 0x81u;
 }
 
+// engine generation for the passes generation 2 covers (developer override NRH_TC_GEN=1|2)
+static int tc_generation() {
+    const char* e = getenv("NRH_TC_GEN");
+    return e ? atoi(e) : TC_GENERATION_DEFAULT;
+}
+
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
                float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat, bool feat_as_image,
                float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
@@ -1175,6 +1185,12 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
     const bool grad = gx != nullptr, wfeat = feat != nullptr;
+    if (!grad && !wfeat && tc_generation() == 2) {          // second-generation engine (mlp_tc2.inc): sdf-only passes
+        NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF2_SMEM));
+        sdf_tc2_kernel<false, false><<<grid, NTHREADS, SDF2_SMEM, st>>>(P, pts, N, sdf, scratch);
+        NRH_LAUNCH_CHECK();
+        return NRH_OK;
+    }
 #define NRH_LAUNCH_TC(G, F)                                                                                        \
     do {                                                                                                           \
         NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM)); \

@@ -17,16 +17,6 @@ constexpr int M = 128, N = 256, K = 128, KC = 64;
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-        "mov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
-}
-
 __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__ A, const __half* __restrict__ Bimg, float* __restrict__ D,
                                                         long long* __restrict__ clk) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -106,19 +96,59 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     }
     tc_fence_before();
     __syncthreads();
-    // ---- (b) timing: 480 MMAs, SS then TS
+    // ---- (b) timing: 480 MMAs, SS then TS, for N = 256, 128, 64 (clk[2 * n + mode])
     if (tid == 0) {
         tc_fence_after();
         uint32_t par = 1;
-        for (int mode = 0; mode < 2; ++mode) {
+        for (int n = 0; n < 3; ++n) {
+            const uint32_t idn = make_idesc_f16(M, 256 >> n);
+            for (int mode = 0; mode < 2; ++mode) {
+                const long long t0 = clock64();
+                for (int i = 0; i < 480; ++i) {
+                    if (mode == 0) umma_f16_lo(tmem_base + 256, desc_lo(smem_u32(a_tile)) + (i & 3) * 2, b_lo0 + (i & 3) * 2, idn, 1u);
+                    else umma_f16_ts(tmem_base + 256, tmem_base + (i & 7) * 8, b_lo0 + (i & 3) * 2, idn, 1u);
+                }
+                umma_commit(&bars[2]);
+                mbar_wait(&bars[2], par); par ^= 1;
+                clk[2 * n + mode] = clock64() - t0;
+            }
+        }
+    }
+    // ---- (b2) the MMA sequence of one MLP layer, 10 layers back to back, accumulator regions alternating:
+    //      mode 0: generation 1 (48 x N256, operand from shared memory); 1: the same with the operand in tensor memory;
+    //      2: generation 2 (24 x N256 + 2 x 24 x N128, operand in tensor memory); 3: all 96 x N128 from tensor memory
+    if (tid == 0) {
+        uint32_t par = 1;
+        const uint32_t idf = make_idesc_f16(M, 256), idh = make_idesc_f16(M, 128), a_s = desc_lo(smem_u32(a_tile));
+        for (int mode = 0; mode < 4; ++mode) {
             const long long t0 = clock64();
-            for (int i = 0; i < 480; ++i) {
-                if (mode == 0) umma_f16_lo(tmem_base + 256, desc_lo(smem_u32(a_tile)) + (i & 3) * 2, b_lo0 + (i & 3) * 2, idesc, 1u);
-                else umma_f16_ts(tmem_base + 256, tmem_base + (i & 7) * 8, b_lo0 + (i & 3) * 2, idesc, 1u);
+            for (int layer = 0; layer < 10; ++layer) {
+                const uint32_t D = tmem_base + (layer & 1) * 256, X = tmem_base + ((layer & 1) ^ 1) * 256;
+                auto group = [&](int sc, uint32_t d, uint32_t idesc, bool ts) {
+                    const uint32_t a0 = X + 32u * sc, s0 = a_s + (sc & 1) * 4, bl = b_lo0 + (sc & 1) * 2048;
+                    if (ts) {
+                        umma_f16_ts(d, a0, bl, idesc, (uint32_t)(sc != 0)); umma_f16_ts(d, a0 + 16, bl + 2, idesc, 1u);
+                        umma_f16_ts(d, a0 + 8, bl, idesc, 1u); umma_f16_ts(d, a0 + 24, bl + 2, idesc, 1u);
+                        umma_f16_ts(d, a0, bl + 4, idesc, 1u); umma_f16_ts(d, a0 + 16, bl + 6, idesc, 1u);
+                    } else {
+                        umma_f16_lo(d, s0, bl, idesc, (uint32_t)(sc != 0)); umma_f16_lo(d, s0 + 2, bl + 2, idesc, 1u);
+                        umma_f16_lo(d, s0, bl, idesc, 1u); umma_f16_lo(d, s0 + 2, bl + 2, idesc, 1u);
+                        umma_f16_lo(d, s0, bl + 4, idesc, 1u); umma_f16_lo(d, s0 + 2, bl + 6, idesc, 1u);
+                    }
+                    umma_commit(&bars[3]);                 // stage release, as in the engine (nobody waits on it here)
+                };
+                if (mode <= 1) { for (int sc = 0; sc < 8; ++sc) group(sc, D, idf, mode == 1); }
+                else if (mode == 2) {
+                    for (int sc = 0; sc < 4; ++sc) group(sc, D, idf, true);
+                    for (int sc = 4; sc < 8; ++sc) group(sc, D, idh, true);
+                    for (int sc = 4; sc < 8; ++sc) group(sc, D + 128, idh, true);
+                } else {
+                    for (int h = 0; h < 2; ++h) for (int sc = 0; sc < 8; ++sc) group(sc, D + 128 * h, idh, true);
+                }
             }
             umma_commit(&bars[2]);
             mbar_wait(&bars[2], par); par ^= 1;
-            clk[mode] = clock64() - t0;
+            clk[8 + mode] = clock64() - t0;
         }
     }
     tc_fence_before();
@@ -204,7 +234,7 @@ int main() {
             for (int k = 0; k < KC; ++k)
                 Bimg[((size_t)c * 32768 + sw128_offset(n, k)) / 2] = __float2half(B[n * K + c * KC + k]);
     float *dA, *dD; __half* dB; long long* dclk; uint32_t* dsink;
-    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, Bimg.size() * 2); cudaMalloc(&dD, 2 * M * N * 4); cudaMalloc(&dclk, 64); cudaMalloc(&dsink, 4096);
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, Bimg.size() * 2); cudaMalloc(&dD, 2 * M * N * 4); cudaMalloc(&dclk, 128); cudaMalloc(&dsink, 4096);
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, Bimg.data(), Bimg.size() * 2, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0xff, 2 * M * N * 4);
@@ -214,16 +244,23 @@ int main() {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("PROBE5 CUDA ERROR: %s\n", cudaGetErrorString(e)); return 2; }
     std::vector<float> D(2 * M * N);
-    long long clk[2];
+    long long clk[16];
     cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(clk, dclk, 16, cudaMemcpyDeviceToHost);
+    cudaMemcpy(clk, dclk, 96, cudaMemcpyDeviceToHost);
     int bad1 = 0, bad2 = 0;
     for (int i = 0; i < M * N; ++i) {
         if (D[i] != Dref[i]) { if (bad1 < 5) printf("SS mismatch m=%d n=%d got %f want %f\n", i / N, i % N, D[i], Dref[i]); ++bad1; }
         if (D[M * N + i] != Dref[i]) { if (bad2 < 5) printf("TS mismatch m=%d n=%d got %f want %f\n", i / N, i % N, D[M * N + i], Dref[i]); ++bad2; }
     }
     printf("PROBE5 %s: SS mismatches %d, TS (A in TMEM, in place) mismatches %d of %d\n", (bad1 | bad2) ? "FAIL" : "PASS", bad1, bad2, M * N);
-    printf("PROBE5 480 MMAs M128 N256 K16: SS %lld clk (%.1f / MMA), TS %lld clk (%.1f / MMA)\n", clk[0], clk[0] / 480.0, clk[1], clk[1] / 480.0);
+    for (int n = 0; n < 3; ++n)
+        printf("PROBE5 480 MMAs M128 N%d K16: SS %lld clk (%.1f / MMA), TS %lld clk (%.1f / MMA)\n", 256 >> n, clk[2 * n], clk[2 * n] / 480.0,
+               clk[2 * n + 1], clk[2 * n + 1] / 480.0);
+    {
+        const char* ln[4] = {"gen 1: 48 x N256, operand in shared memory", "48 x N256, operand in tensor memory",
+                             "gen 2: 24 x N256 + 48 x N128, operand in tensor memory", "96 x N128, operand in tensor memory"};
+        for (int mode = 0; mode < 4; ++mode) printf("PROBE5 layer MMA sequence (%s): %.0f clk per layer\n", ln[mode], clk[8 + mode] / 10.0);
+    }
     const char* names[4] = {"st.shared + fence.proxy.async", "tcgen05.st + wait::st", "st.shared, fence deferred by one step",
                             "st.shared, half of the warps fence in the middle of their math"};
     for (int work = 0; work <= 12; work += 6)

@@ -290,3 +290,19 @@ def test_render_image_equals_chunked_render_maps():
             assert torch.allclose(got[k], v.cpu(), atol=1e-5), k         # chunk composition changes nothing (rays are independent)
     dev = m.render_image(rays, background_rgb=bg, chunk_rays=384, to_host=False)
     assert dev["rgb"].is_cuda and torch.allclose(dev["rgb"].cpu(), want["rgb"].cpu(), atol=1e-5)
+
+
+def test_generation2_engine_matches_generation1(monkeypatch):
+    """The experimental second-generation tcgen05 engine (csrc/mlp_tc2.inc: N-split accumulators, next-layer operand written
+    in place into tensor memory; sdf-only passes, NRH_TC_GEN=2) against generation 1 and the fp64 oracle, ragged point count."""
+    case = T.CASES["sharp_32x128"]
+    m, cfg, sd = build_module(case, "tcgen05")
+    g = torch.Generator().manual_seed(4)
+    pts = torch.cat([(torch.rand(1000, 3, generator=g) - 0.5) * 2.6, 4.5 * torch.nn.functional.normalize(torch.randn(77, 3, generator=g), dim=-1)])
+    want = orc.sdf_mlp(orc.effective_weights(sd, torch.float64), pts.double(), orc.OracleConfig.from_model_config(cfg))["sdf"][:, 0]
+    got = {}
+    for gen in ("1", "2"):
+        monkeypatch.setenv("NRH_TC_GEN", gen)
+        got[gen] = m.sdf_query(pts.cuda())[0].cpu()
+    assert float((got["2"].double() - want).abs().max()) < 1e-4
+    assert float((got["2"] - got["1"]).abs().max()) < 5e-5
