@@ -95,14 +95,25 @@ class _ReflectanceF16(torch.autograd.Function):
     GEMMs and bias gradients one column-sum launch each (nrh_colsum_f16)."""
 
     @staticmethod
-    def forward(ctx, x, *wb):
+    def forward(ctx, n_parts, *args):
+        """args = the n_parts column blocks of the input ([P, k_i] fp32, concatenated in order) followed by 5 weights and 5
+        biases.  The blocks are written straight into the padded fp16 operand (no fp32 concatenation pass) and receive their
+        gradients block by block, only where needed."""
         from .train_ops import colsum_f16  # noqa: F401  (fails loudly here if the CUDA library is missing)
+        parts, wb = args[:n_parts], args[n_parts:]
         n = len(wb) // 2
         ws, bs = wb[:n], wb[n:]
-        P, K = x.shape
+        P = parts[0].shape[0]
+        widths = [int(t.shape[1]) for t in parts]
+        K = sum(widths)
         Kp = (K + 63) // 64 * 64
-        h16 = torch.zeros(P, Kp, dtype=torch.float16, device=x.device)
-        h16[:, :K] = x
+        h16 = torch.empty(P, Kp, dtype=torch.float16, device=parts[0].device)
+        off = 0
+        for t, k in zip(parts, widths):
+            h16[:, off:off + k] = t
+            off += k
+        if Kp > K:
+            h16[:, K:] = 0
         acts, w16s = [h16], []
         for l in range(n - 1):
             w16 = ws[l].detach().to(torch.float16)
@@ -111,12 +122,12 @@ class _ReflectanceF16(torch.autograd.Function):
             w16s.append(w16)
             h16 = torch._addmm_activation(bs[l].detach().to(torch.float16), h16, w16.t())
             acts.append(h16)
-        wl = torch.zeros(8, ws[-1].shape[1], dtype=torch.float16, device=x.device)       # 3 output rows padded to 8
+        wl = torch.zeros(8, ws[-1].shape[1], dtype=torch.float16, device=h16.device)       # 3 output rows padded to 8
         wl[:ws[-1].shape[0]] = ws[-1].detach()
         w16s.append(wl)
         y = torch.mm(h16, wl.t(), out_dtype=torch.float32)[:, :ws[-1].shape[0]] + bs[-1].detach()
         ctx.save_for_backward(*acts, *w16s)
-        ctx.n, ctx.K = n, K
+        ctx.n, ctx.K, ctx.widths = n, K, widths
         return y
 
     @staticmethod
@@ -139,8 +150,12 @@ class _ReflectanceF16(torch.autograd.Function):
             dw = torch.mm(dz.t(), acts[l], out_dtype=torch.float32) * inv
             dws[l] = dw[:, :K] if l == 0 else dw
             dbs[l] = colsum_f16(dz) * inv
-        dx = torch.mm(dz, w16s[0])[:, :K].float() * inv
-        return (dx,) + tuple(dws) + tuple(dbs)
+        dx16 = torch.mm(dz, w16s[0])                                         # [P, Kp] fp16, loss-scaled
+        dparts, off = [], 0
+        for i, k in enumerate(ctx.widths):
+            dparts.append(dx16[:, off:off + k].float() * inv if ctx.needs_input_grad[1 + i] else None)
+            off += k
+        return (None,) + tuple(dparts) + tuple(dws) + tuple(dbs)
 
 
 def _linear_f16_ok(x: Tensor) -> bool:
@@ -210,12 +225,12 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
     if specular_cue is not None:
         nr = specular_cue.shape[-1]
         parts.append(_fourier(per_point(specular_cue[:, None, :].expand(R, S, nr)), refl_freq))
-    hcol = torch.cat(parts, dim=-1)
     n_col = len(weights["col_w"])
-    lowp = sdf_fn is not None and _linear_f16_ok(hcol)       # tcgen05 engine: same operand precision as its reflectance kernel
+    lowp = sdf_fn is not None and _linear_f16_ok(pts)        # tcgen05 engine: same operand precision as its reflectance kernel
     if lowp:
-        hcol = _ReflectanceF16.apply(hcol, *weights["col_w"], *weights["col_b"])
+        hcol = _ReflectanceF16.apply(len(parts), *parts, *weights["col_w"], *weights["col_b"])
     else:
+        hcol = torch.cat(parts, dim=-1)
         for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
             hcol = F.linear(hcol, cw, cb)
             if l < n_col - 1:
