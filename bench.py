@@ -318,14 +318,22 @@ def main():
     train = None
     if not args.no_train:
         torch.set_grad_enabled(True)
+        from types import SimpleNamespace
         from nrhints_b200.grad_sync import allreduce_flat
-        opt = nb.FlatAdam(model.parameters(), lr=5e-4)           # parameters / gradients / moments re-homed into flat buffers
-        gt = torch.rand(R, 3, device=dev)
+        from nrhints_b200.workload import synthetic_pixel_bundle
+        # the reference's train_iter (trainer/trainer.py:269-283) on the composed pipeline: pixel bundle -> ray generation ->
+        # render -> loss dict -> backward -> Adam; the renderer is the one measured above (same weights)
+        pb, cam = synthetic_pixel_bundle(R, seed=3407 + rank)
+        pipe = nb.NRHintPipeline(cfg, nb.RayGeneratorConfig(), nb.CameraModel(**cam), 64, mlp_impl=args.mlp)
+        pipe.renderer = model
+        pipe = pipe.to(dev)
+        pixels = SimpleNamespace(**{k: v.to(dev) for k, v in vars(pb).items()})
+        opt = pipe.make_optimizer()                              # parameters / gradients / moments re-homed into flat buffers
 
         def train_step():
             opt.zero_grad()                                        # one memset
-            out = model(dev_rays, is_training=True, background_rgb=bg, global_step=60000)
-            loss = nb.train_loss_dict(out, gt, model.config.igr_weight)["loss"]        # pipelines/base_pipeline.py:57-62, 2 launches
+            res = pipe(pixels, global_step=60000)
+            loss = pipe.get_train_loss_dict(res, pixels)["loss"]  # pipelines/base_pipeline.py:57-62, 2 launches
             loss.backward()
             # the one collective of the training loop: the flat gradient buffer itself (no packing); the mean over ranks is
             # folded into the Adam launch
@@ -347,7 +355,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms = float(tt.item())
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
-                 "what": "BASELINE config #3: forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU, is_training=True (jitter, "
+                 "what": "BASELINE config #3: ray generation + forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU (the reference's train_iter), is_training=True (jitter, "
                          "global_step 60000); fused CUDA SDF forward-with-tape / backward (tcgen05), fused loss (2 launches) and flat-buffer Adam (1 launch); "
                          "compositing in torch ops, reflectance MLP on fp16 library GEMMs"
                          + ("; flat-buffer gradient all-reduce" if dist is not None else "")}

@@ -9,9 +9,10 @@ from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NeuSRend
 from .ray_generator import CameraModel, RayGenerator, RayGeneratorConfig
 from .rays import RayBundle
 from .train_ops import FlatAdam, train_loss_dict
+from .pipeline import NRHintPipeline
 from .renderer import NeuSHintRenderer, ReflectanceNetwork, RenderOutput, SDFNetwork, SingleVarianceNetwork
 
 __all__ = ["NeuSHintRenderer", "RenderOutput", "RayBundle", "NeuSModelConfig", "NeuSRendererConfig", "SDFNetConfig",
            "ReflectanceNetConfig", "SingleVarianceNetConfig", "NeRFConfig", "DepthComputationType", "NormalComputationType",
            "SDFNetwork", "ReflectanceNetwork", "SingleVarianceNetwork", "RayGenerator", "RayGeneratorConfig", "CameraModel",
-           "FlatAdam", "train_loss_dict"]
+           "FlatAdam", "train_loss_dict", "NRHintPipeline"]

@@ -46,3 +46,31 @@ def shard_rays(rays: dict, rank: int, world: int) -> dict:
     lo = rank * per
     hi = R if rank == world - 1 else lo + per
     return {k: v[lo:hi] for k, v in rays.items()}
+
+
+def synthetic_pixel_bundle(R: int, seed: int = 3407, n_cameras: int = 64, H: int = 800):
+    """The same synthetic scene as synthetic_rays, one level up: a RawPixelBundle-like batch (pixel indices, per-ray
+    camera-to-world pose, light position, image index, ground-truth colour; /root/reference/data/data_loader.py:80-89) of an
+    ALL_IMAGES sampler (trainer/trainer.py:118-125) over `n_cameras` views on the radius-4 sphere at -30 deg elevation
+    (camera/video_pose_utils.py:28-34 style poses), plus the camera intrinsics.  Returns (fields dict, camera dict)."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(seed)
+    fx = 0.5 * H / math.tan(0.5 * 0.6911)
+    theta = rng.uniform(-180.0, 180.0, n_cameras) / 180.0 * math.pi
+    phi = -30.0 / 180.0 * math.pi
+    cp, sp = math.cos(phi), math.sin(phi)
+    cam = np.stack([4.0 * cp * np.sin(theta), np.full(n_cameras, -4.0 * sp), 4.0 * cp * np.cos(theta)], -1)
+    fwd = -cam / np.linalg.norm(cam, axis=-1, keepdims=True)
+    up = np.tile(np.array([0.0, 1.0, 0.0]), (n_cameras, 1))
+    right = np.cross(fwd, up); right /= np.linalg.norm(right, axis=-1, keepdims=True)
+    upv = np.cross(right, fwd)
+    c2w = np.tile(np.eye(4), (n_cameras, 1, 1))
+    c2w[:, :3, 0], c2w[:, :3, 1], c2w[:, :3, 2], c2w[:, :3, 3] = right, upv, -fwd, cam
+    pl_cam = rng.normal(size=(n_cameras, 3)); pl_cam = 4.5 * pl_cam / np.linalg.norm(pl_cam, axis=-1, keepdims=True)
+    img = rng.integers(0, n_cameras, R)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)        # noqa: E731
+    fields = dict(img_indices=torch.tensor(img, dtype=torch.int64)[:, None], h_indices=f32(rng.integers(0, H, R))[:, None],
+                  w_indices=f32(rng.integers(0, H, R))[:, None], poses=f32(c2w[img]), pls=f32(pl_cam[img]),
+                  rgb_gt=f32(rng.uniform(0.0, 1.0, (R, 3))))
+    camera = dict(H=H, W=H, cx=H / 2.0, cy=H / 2.0, fx=fx, fy=fx, zn=2.0, zf=6.0)
+    return SimpleNamespace(**fields), camera
