@@ -1,18 +1,19 @@
 import sys, torch
+from types import SimpleNamespace
 sys.path.insert(0, "/root/repo")
 import nrhints_b200 as nb
-from nrhints_b200.workload import synthetic_rays
+from nrhints_b200.workload import synthetic_pixel_bundle
 dev = torch.device("cuda", 0)
 torch.manual_seed(3407)
-m = nb.NeuSHintRenderer(nb.NeuSModelConfig()).to(dev)
-opt = nb.FlatAdam(m.parameters(), lr=5e-4)
 R = 4096
-rays = nb.RayBundle(**synthetic_rays(R, seed=3407)).to(dev)
-bg = torch.ones(1, 3, device=dev); gt = torch.rand(R, 3, device=dev)
+pb, cam = synthetic_pixel_bundle(R, seed=3407)
+pipe = nb.NRHintPipeline(nb.NeuSModelConfig(), nb.RayGeneratorConfig(), nb.CameraModel(**cam), 64).to(dev)
+pixels = SimpleNamespace(**{k: v.to(dev) for k, v in vars(pb).items()})
+opt = pipe.make_optimizer()
 def step():
     opt.zero_grad()
-    out = m(rays, is_training=True, background_rgb=bg, global_step=60000)
-    nb.train_loss_dict(out, gt, 0.1)["loss"].backward()
+    res = pipe(pixels, global_step=60000)
+    pipe.get_train_loss_dict(res, pixels)["loss"].backward()
     opt.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
