@@ -387,8 +387,8 @@ def main():
 
 def _ncu_traffic(engine):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-    (profiles/r2c_traffic.json, written from profiles/r2c_tc_fine_kernel_ncu.txt); None if there is no capture for this engine."""
-    p = ROOT / "profiles" / "r2c_traffic.json"
+    (profiles/r1x_traffic.json, written from profiles/r1x_tc_fine_kernel_ncu.txt); None if there is no capture for this engine."""
+    p = ROOT / "profiles" / "r1x_traffic.json"
     if not p.exists():
         return None
     d = json.loads(p.read_text()).get(engine)

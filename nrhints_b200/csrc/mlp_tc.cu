@@ -114,24 +114,6 @@ __device__ __forceinline__ float softplus100(float x, float& dsig) {
     return fmaf(lg2_approx(1.0f + e), 6.93147181e-3f, fmaxf(x, 0.0f));
 }
 
-// L2 residency hints.  The packed softplus' scratch is written and re-read by the same CTA for every tile (86 MB over all CTAs,
-// it fits the 126 MB L2) while the kernel streams ~0.3 GB of results through the same cache: without hints the streaming
-// stores evict the scratch lines and every tile's 512 KB of scratch is written back to DRAM (2.3 GB per launch, ncu).  Scratch
-// traffic is therefore tagged evict_last, result stores evict_first (__stcs).
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void st_keep(uint32_t* p, uint32_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_keep(const uint32_t* p, uint64_t pol) {
-    uint32_t v;
-    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -208,16 +190,6 @@ __device__ __forceinline__ void store_half8(uint8_t* a, uint32_t off, const floa
         hw[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(a + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-}
-// the same to GLOBAL memory with a streaming (evict-first) store: the fp16 feature image of the fine pass
-__device__ __forceinline__ void store_half8_stream(uint8_t* a, uint32_t off, const float* x) {
-    uint32_t hw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    __stcs(reinterpret_cast<uint4*>(a + off), make_uint4(hw[0], hw[1], hw[2], hw[3]));
 }
 __device__ __forceinline__ void put_split1(uint8_t* a_hi, uint8_t* a_lo, uint32_t row, uint32_t col, float x) {
     const __half h = __float2half_rn(x);
@@ -302,7 +274,6 @@ struct EpiT {
     // since the previous hand-off.  Sub-chunks 0 and 7 are always handed off on their own (they bound the pipeline bubble at both
     // ends of a layer).
     uint32_t fence_mask;
-    uint64_t keep;                         // L2 evict_last policy for the per-CTA scratch (inference; the training tape streams)
     __device__ __forceinline__ void publish(int sc, const float* o) const {
         const uint32_t o8 = (uint32_t)(sc >> 1) * A_CHUNK + off[sc & 1];
         uint32_t hw[4];
@@ -406,7 +377,7 @@ __device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int
         // global traffic goes after the fence inside publish(): softplus' stores, bias of the sub-chunk after next
         if (GRAD) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) st_keep(&sig_l[(size_t)(sc * 16 + i) * TM], pack_sig2(s[2 * i], s[2 * i + 1]), E.keep);
+            for (int i = 0; i < 4; ++i) sig_l[(size_t)(sc * 16 + i) * TM] = pack_sig2(s[2 * i], s[2 * i + 1]);
         }
         if (sc < 6) {
             ldg8(bias16 + cq + (sc + 2) * 32, b);
@@ -440,7 +411,7 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
         if (GRAD) {
             ldg8(head_w + cq + sc * 32, w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 t2 = unpack_sig2(ld_keep(&sig_l[(size_t)(sc * 16 + i) * TM], E.keep)); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
+            for (int i = 0; i < 4; ++i) { const float2 t2 = unpack_sig2(sig_l[(size_t)(sc * 16 + i) * TM]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
@@ -448,11 +419,11 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
             float t16[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) t16[i] = valid ? v[i] * ACT_SCALE : 0.f;
-            store_half8_stream(feat_tile_img + (sc >> 1) * A_CHUNK, E.off[sc & 1], t16);
+            store_half8(feat_tile_img + (sc >> 1) * A_CHUNK, E.off[sc & 1], t16);
         } else if (valid) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-                __stcs(reinterpret_cast<float4*>(feat_row + cq + sc * 32 + 4 * i), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                *reinterpret_cast<float4*>(feat_row + cq + sc * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         if (GRAD) {
 #pragma unroll
@@ -481,7 +452,7 @@ __device__ __forceinline__ void epi_reverse(const EP& E, WaitAcc&& wait_acc, int
     auto load_sig = [&](uint32_t (&sg)[4], const int sc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            sg[i] = (!SKIP || sc * 32 + cq + 2 * i < SKIP_H) ? ld_keep(&sig_l[(size_t)(sc * 16 + i) * TM], E.keep) : 0u;
+            sg[i] = (!SKIP || sc * 32 + cq + 2 * i < SKIP_H) ? sig_l[(size_t)(sc * 16 + i) * TM] : 0u;
     };
     load_sig(sA, 0);
     load_sig(sB, 1);
@@ -658,7 +629,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         // ======================= epilogue warps =======================
         EpiT<TRAIN> E;
         E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
-        E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask; E.keep = l2_policy_evict_last();
+        E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask;
         const int q = warp & 3;
         E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
