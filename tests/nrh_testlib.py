@@ -216,6 +216,12 @@ RAYGEN_CASES = {
     "se3_small": dict(R=64, cam_opt_mode="SE3", pl_opt=False, noise=True, override_near_far=True, same_image=False, seed=5),
     "se3_large": dict(R=64, cam_opt_mode="SE3", pl_opt=True, noise=False, override_near_far=False, same_image=False, seed=6,
                       adj_scale=0.3),
+    # the state every run starts from: all adjustments exactly zero (torch.zeros parameters, ray_generator.py:53,58) -- the clamp
+    # branch of SO3xR3 and the theta = 0 corner of SE3 (zero sub-gradient of the norm)
+    "so3xr3_zero_init": dict(R=48, cam_opt_mode="SO3xR3", pl_opt=True, noise=False, override_near_far=True, same_image=False, seed=8,
+                             adj_scale=0.0, pl_scale=0.0),
+    "se3_zero_init": dict(R=48, cam_opt_mode="SE3", pl_opt=True, noise=True, override_near_far=True, same_image=True, seed=9,
+                          adj_scale=0.0, pl_scale=0.0),
     # video views: no image indices -> neither noise nor the learned deltas apply (ray_generator.py:103-105)
     "video_no_indices": dict(R=40, cam_opt_mode="SO3xR3", pl_opt=True, noise=True, override_near_far=True, same_image=False, seed=7,
                              no_indices=True),
@@ -246,7 +252,8 @@ def raygen_inputs(case: dict) -> dict:
     out = dict(camera=camera, n_cameras=n_cam, img_indices=None if case.get("no_indices") else img,
                h_indices=torch.randint(0, H, (R,), generator=g).float(), w_indices=torch.randint(0, W, (R,), generator=g).float(),
                poses=c2w[img].contiguous(), pls=4.5 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
-               cam_pose_adjustment=s * torch.randn(n_cam, 6, generator=g), pl_adjustment=0.05 * torch.randn(n_cam, 3, generator=g),
+               cam_pose_adjustment=s * torch.randn(n_cam, 6, generator=g),
+               pl_adjustment=case.get("pl_scale", 0.05) * torch.randn(n_cam, 3, generator=g),
                pl_noise=0.01 * torch.randn(n_cam, 3, generator=g))
     from oracle import raygen_oracle as rgo
     out["cam_pose_noise"] = rgo.exp_map_se3(0.01 * torch.randn(n_cam, 6, generator=g)).contiguous()
