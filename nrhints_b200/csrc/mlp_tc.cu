@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "mlp_tc.cuh"
 #include "tc_primitives.cuh"
 
@@ -44,6 +45,7 @@ constexpr float W_SCALE = TC_W_SCALE;
 constexpr float ACT_SCALE = TC_ACT_SCALE;
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
 constexpr float INV_SQRT2 = 0.70710678f;
+constexpr int TC_MAX_JOBS = 192;                     // operand images per weight set (156 today)
 constexpr int TC_GENERATION_DEFAULT = 1;
 constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed off on its own
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
@@ -1045,7 +1047,13 @@ struct ImgJob {
     __half* dst;
 };
 
-__global__ void k_build_image(ImgJob J) {
+// every operand image of a weight set in ONE launch (blockIdx.y = job); the job table travels as a kernel parameter (20 KB; sm_70+
+// accept 32 KB of parameters since CUDA 12.1), so nothing is staged through device memory and the stream is never synchronised.
+// The packing pass of a training step (weights change every step) was 156 launches of the single-image kernel.
+struct JobTable { ImgJob j[TC_MAX_JOBS]; };
+static_assert(sizeof(JobTable) <= 32000, "job table exceeds the kernel parameter space");
+__global__ void k_build_images(const __grid_constant__ JobTable Tb) {
+    const ImgJob& J = Tb.j[blockIdx.y];
     const int total = J.nrows_img * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i >> 6, k = i & 63;
@@ -1067,13 +1075,26 @@ __global__ void k_scale_copy(const float* __restrict__ src, float* __restrict__ 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i] * scale;
 }
 
+// jobs are collected on the host and flushed by tc_pack in one launch
+struct JobList { JobTable t; int n; };
+thread_local JobList* g_jobs = nullptr;
+
 int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
                 uint8_t* dst, cudaStream_t st) {
-    ImgJob J; J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
+    (void)st;
+    if (!g_jobs || g_jobs->n >= TC_MAX_JOBS) { set_error("image job table overflow"); return NRH_ERR_INVALID; }
+    ImgJob& J = g_jobs->t.j[g_jobs->n++];
+    J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
     for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0, 0};
     J.lo = lo; J.scale = W_SCALE; J.dst = reinterpret_cast<__half*>(dst);
-    k_build_image<<<(nrows_img * 64 + 255) / 256, 256, 0, st>>>(J);
+    return NRH_OK;
+}
+
+int flush_image_jobs(cudaStream_t st) {
+    if (!g_jobs || g_jobs->n == 0) return NRH_OK;
+    k_build_images<<<dim3(64, (unsigned)g_jobs->n), 256, 0, st>>>(g_jobs->t);
     NRH_LAUNCH_CHECK();
+    g_jobs->n = 0;
     return NRH_OK;
 }
 
@@ -1109,6 +1130,10 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     const float* Pf = reinterpret_cast<const float*>(packed);
     const TcLayout T = tc_layout();
     int rc;
+    static thread_local JobList jobs;              // 20 KB: kept off the stack
+    jobs.n = 0;
+    g_jobs = &jobs;
+    struct Reset { ~Reset() { g_jobs = nullptr; } } reset_on_exit;
     // forward: B[n = out][k = in] = W native [out][in]
     for (int l = 0; l < SDF_LAYERS; ++l) {
         const int in = (l == 0) ? PE_DIM : 256, out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
@@ -1140,6 +1165,7 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     }
     for (int l = 1; l < 4; ++l)
         if ((rc = build_matrix(raw.col_W[l], 256, 256, 256, 256, 4, false, tcb + T.col[l], IMG, st))) return rc;
+    if ((rc = flush_image_jobs(st))) return rc;
     // biases pre-multiplied by ACT_SCALE (the forward epilogues work in x16 units)
     for (int l = 0; l < SDF_LAYERS; ++l) {
         const int out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
