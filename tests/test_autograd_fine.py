@@ -70,3 +70,44 @@ def test_coarse_sample_gradient_path():
     zs2, _ = torch.sort(torch.cat([zc2, extra], -1), -1)
     (zs2 * torch.arange(1, z.shape[1] + 1)[None, :]).sum().backward()
     assert torch.allclose(near.grad, near2.grad, atol=1e-5)
+
+
+def test_reflectance_node_chain_rule(monkeypatch):
+    """autograd_fine._ReflectanceF16 (block inputs, padded fp16 operand, one loss scale, fp16 adjoints between layers) against
+    torch.autograd through the same network with the same fp16 operand roundings.  The library calls it makes on the GPU
+    (fp16 GEMMs with fp32 accumulation, bias+ReLU epilogue, nrh_colsum_f16) are replaced by fp32 stand-ins with identical
+    rounding points, so the chain rule itself is checked without a GPU."""
+    import nrhints_b200.train_ops as train_ops
+    orig_mm = torch.mm
+
+    def mm(a, b, out_dtype=None):
+        r = orig_mm(a.float(), b.float())
+        return r if out_dtype == torch.float32 else r.half()
+    monkeypatch.setattr(torch, "mm", mm)
+    monkeypatch.setattr(torch, "_addmm_activation", lambda b, x, w: torch.relu(orig_mm(x.float(), w.float()) + b.float()).half())
+    monkeypatch.setattr(train_ops, "colsum_f16", lambda m, scale=1.0: m.float().sum(0) * scale)
+    g = torch.Generator().manual_seed(0)
+    P, widths = 160, [3, 27, 3, 27, 256, 9, 36]                       # the 361-wide input of the nr-hints preset
+    parts = [torch.randn(P, k, generator=g) for k in widths]
+    for i in (0, 2, 4):                                                # position, normal, feature carry gradients; the PE blocks do not
+        parts[i].requires_grad_(True)
+    ws = [torch.randn(256, 361, generator=g) * 0.05] + [torch.randn(256, 256, generator=g) * 0.08 for _ in range(3)] + \
+         [torch.randn(3, 256, generator=g) * 0.1]
+    bs = [torch.randn(256, generator=g) * 0.1 for _ in range(4)] + [torch.randn(3, generator=g) * 0.1]
+    ws, bs = [w.requires_grad_(True) for w in ws], [b.requires_grad_(True) for b in bs]
+    y = autograd_fine._ReflectanceF16.apply(len(parts), *parts, *ws, *bs)
+    cot = torch.randn(P, 3, generator=g) * 1e-3
+    leaves = [parts[0], parts[2], parts[4]] + ws + bs
+    got = torch.autograd.grad((y * cot).sum(), leaves)
+
+    def q(t):                                                          # value rounded to fp16, gradient passed straight through
+        return t + (t.detach().half().float() - t.detach())
+    h = torch.cat(parts, -1)
+    for l in range(5):
+        h = torch.nn.functional.linear(q(h), q(ws[l]), q(bs[l]) if l < 4 else bs[l])
+        if l < 4:
+            h = torch.relu(h)
+    want = torch.autograd.grad((h * cot).sum(), leaves)
+    assert float((y - h).abs().max()) < 1e-6
+    for a, b in zip(got, want):
+        assert float((a - b).abs().max()) < 2e-3 * float(b.abs().max()), (tuple(a.shape), float((a - b).abs().max() / b.abs().max()))
