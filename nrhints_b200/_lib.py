@@ -145,9 +145,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     in parallel and re-used while neither the source nor any header is newer, then linked into libnrhints_b200.so."""
     if not (force or needs_build()):
         return _LIB_PATH
+    import fcntl
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     _OBJ_DIR.mkdir(exist_ok=True)
+    # one builder at a time: the ranks of a torchrun launch may all find the library stale at once
+    lock = open(_OBJ_DIR / ".build.lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():            # another process built it while we waited
+            return _LIB_PATH
+        return _build_locked(nvcc, force, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, force: bool, verbose: bool) -> Path:
+    from concurrent.futures import ThreadPoolExecutor
     hdr_t = max((_CSRC / h).resolve().stat().st_mtime for h in _HEADERS)
 
     def compile_one(src: str) -> Path:
@@ -162,10 +177,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(_SOURCES)) as ex:
         objs = list(ex.map(compile_one, _SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(_LIB_PATH)] + [str(o) for o in objs]
+    tmp = _LIB_PATH.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp)] + [str(o) for o in objs]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+    os.replace(tmp, _LIB_PATH)                          # readers never see a half-written library
     return _LIB_PATH
 
 
