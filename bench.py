@@ -362,7 +362,7 @@ def main():
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
                  "what": "BASELINE config #3: ray generation + forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU (the reference's train_iter), is_training=True (jitter, "
                          "global_step 60000); fused CUDA SDF forward-with-tape / backward (tcgen05), fused loss (2 launches) and flat-buffer Adam (1 launch); "
-                         "compositing in torch ops, reflectance MLP on fp16 library GEMMs"
+                         "CUDA compositing node (forward + hand-derived backward), reflectance MLP on fp16 library GEMMs"
                          + ("; flat-buffer gradient all-reduce" if dist is not None else "")}
         torch.set_grad_enabled(False)
         del opt

@@ -17,6 +17,8 @@
  *                                       camera/lie_groups.py:26-116         -> nrh_raygen_forward / _backward
  *   get_train_loss_dict (+ autograd)    pipelines/base_pipeline.py:50-69    -> nrh_train_loss
  *   torch.optim.Adam.step               trainer/trainer.py:99,278-281       -> nrh_adam_step (flat buffer)
+ *   get_alpha / weights / compositing   models/neus_hint_model.py:339-356,
+ *   (+ autograd), training step         :521-526,:635-637                   -> nrh_composite_train_forward / _backward
  *
  * Conventions
  *  - Every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer.
@@ -301,6 +303,21 @@ int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * out [n_mats][width] = scale * sum over rows: the bias gradients of a training step are such point-reductions over the fp16
  * adjoint dumps (db_l = sum_p zb_l / S above).  width: multiple of 8 with 256 % (width / 8) == 0; matrices 16-byte aligned. */
 int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_t mat_stride, float scale, float* out, void* stream);
+
+/* Differentiable compositing of the primary ray for a training step: get_alpha (models/neus_hint_model.py:339-356), the
+ * transmittance scan / weights (:521-526) and rgb = sum_j w_j c_j + bg (1 - sum_j w_j) (:635-637), and the vector-Jacobian
+ * product torch autograd derives for them.  Per-point inputs sdf [N], grad [N,3], color [N,3] (N = R*S) are addressed as
+ * point(r, j) = r * point_stride_ray + j * point_stride_sample, so both the ray-major (S, 1) and the pipeline's sample-major
+ * (1, R) orders are accepted; dists [R,S] and weights [R,S] are ray-major, dirs [R,3], inv_s a device scalar, bg_rgb [3] or NULL.
+ * Backward: d_rgb [R,3], d_weights [R,S] (nullable) -> d_sdf / d_grad / d_color in the inputs' point order, d_dirs [R,3], and the
+ * scalar *d_inv_s (ACCUMULATED: zero it first).  One thread per ray, no tape: the scan is recomputed. */
+int nrh_composite_train_forward(const float* sdf, const float* grad, const float* color, int64_t point_stride_ray,
+                                int64_t point_stride_sample, const float* dists, const float* dirs, const float* inv_s,
+                                float cos_anneal, const float* bg_rgb, int64_t R, int S, float* weights, float* rgb, void* stream);
+int nrh_composite_train_backward(const float* sdf, const float* grad, const float* color, int64_t point_stride_ray,
+                                 int64_t point_stride_sample, const float* dists, const float* dirs, const float* inv_s,
+                                 float cos_anneal, const float* bg_rgb, int64_t R, int S, const float* d_rgb, const float* d_weights,
+                                 float* d_sdf, float* d_grad, float* d_color, float* d_dirs, float* d_inv_s, void* stream);
 
 /* Kernel launches issued by the last nrh_render_forward / nrh_sdf_query call on this thread. */
 int nrh_last_launch_count(void);

@@ -19,6 +19,7 @@ This module only uses torch; it never touches the oracle and never runs on the C
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -158,6 +159,58 @@ class _ReflectanceF16(torch.autograd.Function):
         return (None,) + tuple(dparts) + tuple(dws) + tuple(dbs)
 
 
+class _CompositeTrain(torch.autograd.Function):
+    """NeuS alpha, transmittance scan / weights and colour compositing of the primary ray (models/neus_hint_model.py:339-356,
+    :521-526,:635-637) as ONE autograd node on the CUDA operators nrh_composite_train_forward / _backward (one thread per ray,
+    hand-derived backward, the scan is recomputed instead of taped; csrc/composite_train_math.cuh) -- it replaces ~60 small torch
+    launches per step.  Inputs per point in evaluation order: sdf [N,1], grad [N,3], color [N,3]; dists [R,S] (no gradient:
+    the sample positions are detached), dirs [R,3], inv_s (1 element), bg [1,3] or None.  Returns (rgb [R,3], weights [R,S])."""
+
+    @staticmethod
+    def forward(ctx, sdf, grad, color, dirs, inv_s, dists, bg, cos_anneal: float, sample_major: bool):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        dev = sdf.device
+        R, S = dists.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        c = lambda t: t.detach().to(torch.float32).contiguous()          # noqa: E731
+        sdf_c, g_c, col_c, dirs_c, dist_c = c(sdf).reshape(-1), c(grad), c(color), c(dirs), c(dists)
+        s_c = c(inv_s).reshape(1)
+        bg_c = c(bg).reshape(-1) if bg is not None else None
+        pr, pj = (1, R) if sample_major else (S, 1)
+        w, rgb = torch.empty(R, S, **f32), torch.empty(R, 3, **f32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrh_composite_train_forward(sdf_c.data_ptr(), g_c.data_ptr(), col_c.data_ptr(), pr, pj, dist_c.data_ptr(),
+                                                       dirs_c.data_ptr(), s_c.data_ptr(), float(cos_anneal),
+                                                       bg_c.data_ptr() if bg_c is not None else None, R, S, w.data_ptr(), rgb.data_ptr(),
+                                                       torch.cuda.current_stream(dev).cuda_stream), "nrh_composite_train_forward")
+        ctx.save_for_backward(sdf_c, g_c, col_c, dirs_c, dist_c, s_c, bg_c)
+        ctx.meta = (R, S, pr, pj, float(cos_anneal), tuple(sdf.shape), tuple(inv_s.shape))
+        return rgb, w
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_w):
+        from . import _lib
+        lib = _lib.load()
+        sdf_c, g_c, col_c, dirs_c, dist_c, s_c, bg_c = ctx.saved_tensors
+        R, S, pr, pj, cos_anneal, sdf_shape, s_shape = ctx.meta
+        dev = sdf_c.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_rgb = (d_rgb if d_rgb is not None else torch.zeros(R, 3, **f32)).to(torch.float32).contiguous()
+        d_w = d_w.to(torch.float32).contiguous() if d_w is not None else None
+        d_sdf, d_g, d_c = torch.empty_like(sdf_c), torch.empty_like(g_c), torch.empty_like(col_c)
+        d_dirs, d_s = torch.empty(R, 3, **f32), torch.zeros(1, **f32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrh_composite_train_backward(sdf_c.data_ptr(), g_c.data_ptr(), col_c.data_ptr(), pr, pj, dist_c.data_ptr(),
+                                                        dirs_c.data_ptr(), s_c.data_ptr(), cos_anneal,
+                                                        bg_c.data_ptr() if bg_c is not None else None, R, S, d_rgb.data_ptr(),
+                                                        d_w.data_ptr() if d_w is not None else None, d_sdf.data_ptr(), d_g.data_ptr(),
+                                                        d_c.data_ptr(), d_dirs.data_ptr(), d_s.data_ptr(),
+                                                        torch.cuda.current_stream(dev).cuda_stream), "nrh_composite_train_backward")
+        return d_sdf.reshape(sdf_shape), d_g, d_c, d_dirs, d_s.reshape(s_shape), None, None, None, None
+
+
 def _linear_f16_ok(x: Tensor) -> bool:
     if not x.is_cuda:
         return False
@@ -208,15 +261,21 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
             x = pts if pts.requires_grad else pts.detach().requires_grad_(True)
             sdf = sdf_forward(weights["sdf_w"], weights["sdf_b"], head, x)[:, :1]
             grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
-    true_cos = (dirs * grad).sum(-1, keepdim=True)
-    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
-    half = iter_cos * per_point(dists[..., None]) * 0.5
-    prev_cdf = torch.sigmoid((sdf - half) * inv_s)
-    next_cdf = torch.sigmoid((sdf + half) * inv_s)
-    alpha = per_ray(((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1))[..., 0]
-    trans = torch.cumprod(torch.cat([torch.ones((R, 1), device=dev, dtype=dt), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
-    w = alpha * trans
-    wsum = w.sum(-1, keepdim=True)
+    # compositing: ONE CUDA autograd node on the tcgen05 path (the sample positions carry no gradient there: importance sampling
+    # detaches them, so `dists` is data), the torch expression otherwise (fp32 engine, CPU tests, n_importance == 0)
+    fused_composite = (sdf_fn is not None and pts.is_cuda and not dists.requires_grad and S <= 128
+                       and os.environ.get("NRH_COMPOSITE", "cuda") != "torch")
+    w = wsum = None
+    if not fused_composite:
+        true_cos = (dirs * grad).sum(-1, keepdim=True)
+        iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
+        half = iter_cos * per_point(dists[..., None]) * 0.5
+        prev_cdf = torch.sigmoid((sdf - half) * inv_s)
+        next_cdf = torch.sigmoid((sdf + half) * inv_s)
+        alpha = per_ray(((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1))[..., 0]
+        trans = torch.cumprod(torch.cat([torch.ones((R, 1), device=dev, dtype=dt), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+        w = alpha * trans
+        wsum = w.sum(-1, keepdim=True)
 
     n_hat = F.normalize(grad, dim=-1, p=2)
     parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
@@ -235,9 +294,13 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
             hcol = F.linear(hcol, cw, cb)
             if l < n_col - 1:
                 hcol = torch.relu(hcol)
-    color = per_ray(torch.sigmoid(hcol))
-    rgb = (color * w[..., None]).sum(1)
-    if background_rgb is not None:
-        rgb = rgb + background_rgb * (1.0 - wsum)
+    color_pt = torch.sigmoid(hcol)
+    color = per_ray(color_pt)
+    if fused_composite:
+        rgb, w = _CompositeTrain.apply(sdf, grad, color_pt, rays_d, inv_s, dists, background_rgb, float(cos_anneal), bool(sample_major))
+    else:
+        rgb = (color * w[..., None]).sum(1)
+        if background_rgb is not None:
+            rgb = rgb + background_rgb * (1.0 - wsum)
     return {"rgb": rgb, "weights": w, "analytic_normals": per_ray(grad),
             "normalized_analytic_normals": per_ray(n_hat), "sampled_color": color}

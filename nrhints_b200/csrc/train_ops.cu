@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "nrh_common.cuh"
+#include "composite_train_math.cuh"
 
 namespace nrh {
 namespace {
@@ -134,6 +135,52 @@ k_colsum_f16(const __half* __restrict__ mats, int64_t rows, int width, int64_t m
     }
 }
 
+// ---- differentiable compositing of the primary ray (composite_train_math.cuh), one thread per ray ---------------------------
+struct CtArgs {
+    const float* sdf; const float* grad; const float* color;      // per point: [N], [N,3], [N,3]; point (r, j) = r * pr + j * pj
+    int64_t pr, pj;
+    const float* dists; const float* dirs; const float* inv_s; const float* bg;   // [R,S], [R,3], device scalar, nullable [3]
+    float cos_anneal; int64_t R; int S;
+};
+__device__ __forceinline__ CtRay ct_ray(const CtArgs& A, int64_t r) {
+    CtRay Y;
+    Y.S = A.S;
+    Y.sdf = A.sdf + r * A.pr; Y.sdf_st = A.pj;
+    Y.g = A.grad + r * A.pr * 3; Y.g_st = A.pj * 3;
+    Y.c = A.color + r * A.pr * 3; Y.c_st = A.pj * 3;
+    Y.dist = A.dists + r * A.S; Y.dist_st = 1;
+    Y.d[0] = A.dirs[r * 3]; Y.d[1] = A.dirs[r * 3 + 1]; Y.d[2] = A.dirs[r * 3 + 2];
+    Y.inv_s = *A.inv_s; Y.cos_anneal = A.cos_anneal;
+    Y.has_bg = A.bg != nullptr;
+    for (int k = 0; k < 3; ++k) Y.bg[k] = A.bg ? A.bg[k] : 0.f;
+    return Y;
+}
+__global__ void __launch_bounds__(128)
+k_composite_train_fwd(CtArgs A, float* __restrict__ w, float* __restrict__ rgb) {
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (r >= A.R) return;
+    const CtRay Y = ct_ray(A, r);
+    float c3[3];
+    composite_train_forward(Y, w + r * A.S, 1, c3);
+    rgb[r * 3] = c3[0]; rgb[r * 3 + 1] = c3[1]; rgb[r * 3 + 2] = c3[2];
+}
+__global__ void __launch_bounds__(128)
+k_composite_train_bwd(CtArgs A, const float* __restrict__ d_rgb, const float* __restrict__ d_w, float* __restrict__ d_sdf,
+                      float* __restrict__ d_grad, float* __restrict__ d_color, float* __restrict__ d_dirs, float* __restrict__ d_inv_s) {
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    float ds = 0.f;
+    if (r < A.R) {
+        const CtRay Y = ct_ray(A, r);
+        float alpha_s[CT_MAX_S], T_s[CT_MAX_S], dd[3];
+        const float g3[3] = {d_rgb[r * 3], d_rgb[r * 3 + 1], d_rgb[r * 3 + 2]};
+        ds = composite_train_backward(Y, g3, d_w ? d_w + r * A.S : nullptr, 1, d_sdf + r * A.pr, d_grad + r * A.pr * 3, d_color + r * A.pr * 3,
+                                      dd, alpha_s, T_s);
+        d_dirs[r * 3] = dd[0]; d_dirs[r * 3 + 1] = dd[1]; d_dirs[r * 3 + 2] = dd[2];
+    }
+    ds = warp_sum(ds);
+    if ((threadIdx.x & 31) == 0 && ds != 0.f) atomicAdd(d_inv_s, ds);
+}
+
 int grid_for(int64_t n) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -198,6 +245,40 @@ int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_
     if (slabs < 1) slabs = 1;
     k_colsum_f16<<<(unsigned)(n_mats * slabs), CS_THREADS, 0, st>>>(static_cast<const __half*>(mats), rows, width, mat_stride, slabs,
                                                                      scale, out);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+static int ct_fill(CtArgs& A, const float* sdf, const float* grad, const float* color, int64_t pr, int64_t pj, const float* dists,
+                   const float* dirs, const float* inv_s, float cos_anneal, const float* bg, int64_t R, int S, const char* who) {
+    if (!sdf || !grad || !color || !dists || !dirs || !inv_s || R < 0 || S < 1 || S > CT_MAX_S) {
+        set_error("%s: null argument or S outside [1, %d]", who, CT_MAX_S); return NRH_ERR_INVALID;
+    }
+    A = CtArgs{sdf, grad, color, pr, pj, dists, dirs, inv_s, bg, cos_anneal, R, S};
+    return NRH_OK;
+}
+
+int nrh_composite_train_forward(const float* sdf, const float* grad, const float* color, int64_t point_stride_ray,
+                                int64_t point_stride_sample, const float* dists, const float* dirs, const float* inv_s,
+                                float cos_anneal, const float* bg_rgb, int64_t R, int S, float* weights, float* rgb, void* stream) {
+    if (R == 0) return NRH_OK;
+    CtArgs A; int rc = ct_fill(A, sdf, grad, color, point_stride_ray, point_stride_sample, dists, dirs, inv_s, cos_anneal, bg_rgb, R, S,
+                               "nrh_composite_train_forward"); if (rc) return rc;
+    if (!weights || !rgb) { set_error("nrh_composite_train_forward: null output"); return NRH_ERR_INVALID; }
+    k_composite_train_fwd<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, weights, rgb);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int nrh_composite_train_backward(const float* sdf, const float* grad, const float* color, int64_t point_stride_ray,
+                                 int64_t point_stride_sample, const float* dists, const float* dirs, const float* inv_s,
+                                 float cos_anneal, const float* bg_rgb, int64_t R, int S, const float* d_rgb, const float* d_weights,
+                                 float* d_sdf, float* d_grad, float* d_color, float* d_dirs, float* d_inv_s, void* stream) {
+    if (R == 0) return NRH_OK;
+    CtArgs A; int rc = ct_fill(A, sdf, grad, color, point_stride_ray, point_stride_sample, dists, dirs, inv_s, cos_anneal, bg_rgb, R, S,
+                               "nrh_composite_train_backward"); if (rc) return rc;
+    if (!d_rgb || !d_sdf || !d_grad || !d_color || !d_dirs || !d_inv_s) { set_error("nrh_composite_train_backward: null argument"); return NRH_ERR_INVALID; }
+    k_composite_train_bwd<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, d_rgb, d_weights, d_sdf, d_grad, d_color, d_dirs, d_inv_s);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -4,6 +4,7 @@
 // TEST INFRASTRUCTURE ONLY -- never loaded by the product.
 #include "../nrhints_b200/csrc/ray_math.cuh"
 #include "../nrhints_b200/csrc/raygen_math.cuh"
+#include "../nrhints_b200/csrc/composite_train_math.cuh"
 
 using namespace nrh;
 
@@ -115,6 +116,25 @@ void h_raygen_backward(const float* cam, int mode, int override_nf, long R, cons
         }
         if (d_pl_adj) for (int i = 0; i < 3; ++i) d_pl_adj[img[r] * 3 + i] += g_pl[r * 3 + i];
     }
+}
+
+// ---- differentiable compositing (composite_train_math.cuh): one ray, contiguous arrays ------------------------------------
+static CtRay make_ct(int S, const float* sdf, const float* g, const float* c, const float* dist, const float* d, float inv_s,
+                     float cos_anneal, const float* bg) {
+    CtRay Y; Y.S = S; Y.sdf = sdf; Y.sdf_st = 1; Y.g = g; Y.g_st = 3; Y.c = c; Y.c_st = 3; Y.dist = dist; Y.dist_st = 1;
+    for (int k = 0; k < 3; ++k) { Y.d[k] = d[k]; Y.bg[k] = bg ? bg[k] : 0.f; }
+    Y.inv_s = inv_s; Y.cos_anneal = cos_anneal; Y.has_bg = bg != nullptr;
+    return Y;
+}
+void h_composite_train_forward(int S, const float* sdf, const float* g, const float* c, const float* dist, const float* d, float inv_s,
+                               float cos_anneal, const float* bg, float* w, float* rgb) {
+    composite_train_forward(make_ct(S, sdf, g, c, dist, d, inv_s, cos_anneal, bg), w, 1, rgb);
+}
+float h_composite_train_backward(int S, const float* sdf, const float* g, const float* c, const float* dist, const float* d, float inv_s,
+                                 float cos_anneal, const float* bg, const float* d_rgb, const float* d_w, float* d_sdf, float* d_g,
+                                 float* d_c, float* d_dir) {
+    float alpha_s[CT_MAX_S], T_s[CT_MAX_S];
+    return composite_train_backward(make_ct(S, sdf, g, c, dist, d, inv_s, cos_anneal, bg), d_rgb, d_w, 1, d_sdf, d_g, d_c, d_dir, alpha_s, T_s);
 }
 
 }  // extern "C"
