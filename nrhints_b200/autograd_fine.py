@@ -96,22 +96,31 @@ class _ReflectanceF16(torch.autograd.Function):
     GEMMs and bias gradients one column-sum launch each (nrh_colsum_f16)."""
 
     @staticmethod
-    def forward(ctx, n_parts, *args):
-        """args = the n_parts column blocks of the input ([P, k_i] fp32, concatenated in order) followed by 5 weights and 5
-        biases.  The blocks are written straight into the padded fp16 operand (no fp32 concatenation pass) and receive their
-        gradients block by block, only where needed."""
+    def forward(ctx, n_parts, ray_dims, *args):
+        """args = the n_parts column blocks of the input (concatenated in order) followed by 5 weights and 5 biases.  A block is
+        either per point ([P, k_i] fp32) or per RAY ([R, k_i]: view / light / hint encodings are the same for all samples of a
+        ray); ray_dims = (G0, G1, ray_axis) says how the P points factor into [G0, G1] and which axis is the ray.  The blocks are
+        written straight into the padded fp16 operand (no fp32 concatenation pass, per-ray blocks by a broadcast copy) and
+        receive their gradients block by block, only where needed (per-ray blocks: summed over the samples)."""
         from .train_ops import colsum_f16  # noqa: F401  (fails loudly here if the CUDA library is missing)
         parts, wb = args[:n_parts], args[n_parts:]
         n = len(wb) // 2
         ws, bs = wb[:n], wb[n:]
-        P = parts[0].shape[0]
+        G0, G1, ray_axis = ray_dims
+        P, n_rays = G0 * G1, (G0, G1)[ray_axis]
         widths = [int(t.shape[1]) for t in parts]
+        per_ray = [t.shape[0] != P for t in parts]
+        assert all(t.shape[0] == (n_rays if pr else P) for t, pr in zip(parts, per_ray))
         K = sum(widths)
         Kp = (K + 63) // 64 * 64
         h16 = torch.empty(P, Kp, dtype=torch.float16, device=parts[0].device)
+        h3 = h16.view(G0, G1, Kp)
         off = 0
-        for t, k in zip(parts, widths):
-            h16[:, off:off + k] = t
+        for t, k, pr in zip(parts, widths, per_ray):
+            if pr:
+                h3[:, :, off:off + k] = t.unsqueeze(1 - ray_axis)            # broadcast over the sample axis
+            else:
+                h16[:, off:off + k] = t
             off += k
         if Kp > K:
             h16[:, K:] = 0
@@ -128,7 +137,7 @@ class _ReflectanceF16(torch.autograd.Function):
         w16s.append(wl)
         y = torch.mm(h16, wl.t(), out_dtype=torch.float32)[:, :ws[-1].shape[0]] + bs[-1].detach()
         ctx.save_for_backward(*acts, *w16s)
-        ctx.n, ctx.K, ctx.widths = n, K, widths
+        ctx.n, ctx.K, ctx.widths, ctx.per_ray, ctx.ray_dims = n, K, widths, per_ray, ray_dims
         return y
 
     @staticmethod
@@ -152,11 +161,17 @@ class _ReflectanceF16(torch.autograd.Function):
             dws[l] = dw[:, :K] if l == 0 else dw
             dbs[l] = colsum_f16(dz) * inv
         dx16 = torch.mm(dz, w16s[0])                                         # [P, Kp] fp16, loss-scaled
+        G0, G1, ray_axis = ctx.ray_dims
         dparts, off = [], 0
         for i, k in enumerate(ctx.widths):
-            dparts.append(dx16[:, off:off + k].float() * inv if ctx.needs_input_grad[1 + i] else None)
+            if not ctx.needs_input_grad[2 + i]:
+                dparts.append(None)
+            elif ctx.per_ray[i]:
+                dparts.append(dx16.view(G0, G1, -1)[:, :, off:off + k].sum(1 - ray_axis, dtype=torch.float32) * inv)
+            else:
+                dparts.append(dx16[:, off:off + k].float() * inv)
             off += k
-        return (None,) + tuple(dparts) + tuple(dws) + tuple(dbs)
+        return (None, None) + tuple(dparts) + tuple(dws) + tuple(dbs)
 
 
 class _CompositeTrain(torch.autograd.Function):
@@ -278,17 +293,24 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
         wsum = w.sum(-1, keepdim=True)
 
     n_hat = F.normalize(grad, dim=-1, p=2)
-    parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
-    if visibilities is not None:
-        parts.append(_fourier(per_point(visibilities[:, None, :].expand(R, S, 1)), refl_freq))
-    if specular_cue is not None:
-        nr = specular_cue.shape[-1]
-        parts.append(_fourier(per_point(specular_cue[:, None, :].expand(R, S, nr)), refl_freq))
     n_col = len(weights["col_w"])
     lowp = sdf_fn is not None and _linear_f16_ok(pts)        # tcgen05 engine: same operand precision as its reflectance kernel
     if lowp:
-        hcol = _ReflectanceF16.apply(len(parts), *parts, *weights["col_w"], *weights["col_b"])
+        # view / light / hint encodings are per-RAY quantities: encoded once per ray and broadcast into the operand by the node
+        parts = [pts, _fourier(rays_d, refl_freq), n_hat if normalized_normals else grad, _fourier(rays_pl, refl_freq), feat]
+        if visibilities is not None:
+            parts.append(_fourier(visibilities, refl_freq))
+        if specular_cue is not None:
+            parts.append(_fourier(specular_cue, refl_freq))
+        ray_dims = (S, R, 1) if sample_major else (R, S, 0)
+        hcol = _ReflectanceF16.apply(len(parts), ray_dims, *parts, *weights["col_w"], *weights["col_b"])
     else:
+        parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
+        if visibilities is not None:
+            parts.append(_fourier(per_point(visibilities[:, None, :].expand(R, S, 1)), refl_freq))
+        if specular_cue is not None:
+            nr = specular_cue.shape[-1]
+            parts.append(_fourier(per_point(specular_cue[:, None, :].expand(R, S, nr)), refl_freq))
         hcol = torch.cat(parts, dim=-1)
         for l, (cw, cb) in enumerate(zip(weights["col_w"], weights["col_b"])):
             hcol = F.linear(hcol, cw, cb)

@@ -87,27 +87,37 @@ def test_reflectance_node_chain_rule(monkeypatch):
     monkeypatch.setattr(torch, "_addmm_activation", lambda b, x, w: torch.relu(orig_mm(x.float(), w.float()) + b.float()).half())
     monkeypatch.setattr(train_ops, "colsum_f16", lambda m, scale=1.0: m.float().sum(0) * scale)
     g = torch.Generator().manual_seed(0)
-    P, widths = 160, [3, 27, 3, 27, 256, 9, 36]                       # the 361-wide input of the nr-hints preset
-    parts = [torch.randn(P, k, generator=g) for k in widths]
-    for i in (0, 2, 4):                                                # position, normal, feature carry gradients; the PE blocks do not
-        parts[i].requires_grad_(True)
+    R, S, widths = 8, 20, [3, 27, 3, 27, 256, 9, 36]                   # the 361-wide input of the nr-hints preset
+    P = R * S
+    ray_block = [False, True, False, True, False, True, True]        # view / light / hint encodings are per ray
     ws = [torch.randn(256, 361, generator=g) * 0.05] + [torch.randn(256, 256, generator=g) * 0.08 for _ in range(3)] + \
          [torch.randn(3, 256, generator=g) * 0.1]
     bs = [torch.randn(256, generator=g) * 0.1 for _ in range(4)] + [torch.randn(3, generator=g) * 0.1]
     ws, bs = [w.requires_grad_(True) for w in ws], [b.requires_grad_(True) for b in bs]
-    y = autograd_fine._ReflectanceF16.apply(len(parts), *parts, *ws, *bs)
-    cot = torch.randn(P, 3, generator=g) * 1e-3
-    leaves = [parts[0], parts[2], parts[4]] + ws + bs
-    got = torch.autograd.grad((y * cot).sum(), leaves)
+    for sample_major in (False, True):
+        parts = [torch.randn(R if rb else P, k, generator=g) for k, rb in zip(widths, ray_block)]
+        for i in (0, 1, 2, 3, 4):                                      # position, view, normal, light, feature carry gradients
+            parts[i].requires_grad_(True)
+        ray_dims = (S, R, 1) if sample_major else (R, S, 0)
+        y = autograd_fine._ReflectanceF16.apply(len(parts), ray_dims, *parts, *ws, *bs)
+        cot = torch.randn(P, 3, generator=g) * 1e-3
+        leaves = parts[:5] + ws + bs
+        got = torch.autograd.grad((y * cot).sum(), leaves)
 
-    def q(t):                                                          # value rounded to fp16, gradient passed straight through
-        return t + (t.detach().half().float() - t.detach())
-    h = torch.cat(parts, -1)
-    for l in range(5):
-        h = torch.nn.functional.linear(q(h), q(ws[l]), q(bs[l]) if l < 4 else bs[l])
-        if l < 4:
-            h = torch.relu(h)
-    want = torch.autograd.grad((h * cot).sum(), leaves)
-    assert float((y - h).abs().max()) < 1e-6
-    for a, b in zip(got, want):
-        assert float((a - b).abs().max()) < 2e-3 * float(b.abs().max()), (tuple(a.shape), float((a - b).abs().max() / b.abs().max()))
+        def q(t):                                                      # value rounded to fp16, gradient passed straight through
+            return t + (t.detach().half().float() - t.detach())
+
+        def per_point(t, rb):                                          # expand a per-ray block to the evaluation order
+            if not rb:
+                return t
+            return (t[None, :, :].expand(S, R, -1) if sample_major else t[:, None, :].expand(R, S, -1)).reshape(P, -1)
+        h = torch.cat([per_point(t, rb) for t, rb in zip(parts, ray_block)], -1)
+        for l in range(5):
+            h = torch.nn.functional.linear(q(h), q(ws[l]), q(bs[l]) if l < 4 else bs[l])
+            if l < 4:
+                h = torch.relu(h)
+        want = torch.autograd.grad((h * cot).sum(), leaves)
+        assert float((y - h).abs().max()) < 1e-6
+        for a, b in zip(got, want):
+            # per-ray gradients are sums of fp16-rounded per-point adjoints: a slightly wider band
+            assert float((a - b).abs().max()) < 4e-3 * float(b.abs().max()), (sample_major, tuple(a.shape), float((a - b).abs().max() / b.abs().max()))
