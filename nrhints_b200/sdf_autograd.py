@@ -87,7 +87,9 @@ class _SdfFine(torch.autograd.Function):
         d_feat = (d_feat if d_feat is not None else torch.zeros(N, 256, **f32)).to(torch.float32).contiguous()
         d_grad = (d_grad if d_grad is not None else torch.zeros(N, 3, **f32)).to(torch.float32).contiguous()
         # power-of-two loss scale, computed on the device (no host sync): largest adjoint -> ~2^9
-        amax = torch.stack([d_sdf.abs().max(), d_feat.abs().max(), d_grad.abs().max() * _SDF_SCALE]).max().clamp_min(1e-30)
+        inf = float("inf")                                     # max |x| in one reduction pass, without the 512 MB |d_feat| temporary
+        amax = torch.stack([torch.linalg.vector_norm(d_sdf, ord=inf), torch.linalg.vector_norm(d_feat, ord=inf),
+                            torch.linalg.vector_norm(d_grad, ord=inf) * _SDF_SCALE]).max().clamp_min(1e-30)
         scale = torch.exp2(torch.floor(torch.log2(512.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40).reshape(1).contiguous()
         bwd = torch.empty(int(lay.bwd_bytes), dtype=torch.uint8, device=device)
         d_pts = torch.empty(N, 3, **f32)
