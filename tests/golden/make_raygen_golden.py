@@ -73,6 +73,14 @@ def main():
         for n, g in grads.items():
             store[f"{name}.grad_{n}"] = g.numpy()
         print(name, "ok;", {n: float(g.abs().max()) for n, g in grads.items()})
+    # the constructor's RNG draws (ray_generator.py:62-73): noise buffers for a fixed seed, and the state_dict layout
+    torch.manual_seed(123)
+    gen = RayGenerator(CameraModel(H=8, W=8, cx=4.0, cy=4.0, fx=10.0, fy=10.0, zn=0.1, zf=10.0), 5,
+                       RayGeneratorConfig(cam_opt_mode="SE3", pl_opt=True, cam_position_noise_std=0.02, cam_orientation_noise_std=0.01,
+                                          pl_position_noise_std=0.03))
+    for k, v in gen.state_dict().items():
+        store[f"ctor_seed123.{k}"] = v.detach().numpy()
+    store["ctor_seed123.keys"] = np.array(list(gen.state_dict().keys()))
     np.savez_compressed(HERE / "raygen.npz", **store)
     print("written", HERE / "raygen.npz")
 

@@ -190,3 +190,22 @@ def test_cuda_raygen_feeds_the_renderer_and_reaches_the_pose_parameters():
         want = want if want is not None else torch.zeros_like(got.cpu())
         scale = max(float(want.abs().max()), 1e-6)
         assert float((got.cpu() - want).abs().max()) < 3e-2 * scale + 1e-6, (got.cpu(), want)
+
+
+def test_constructor_matches_the_reference_state_dict_and_rng_draws():
+    """Same state_dict keys / shapes as the reference RayGenerator and, for the same torch seed, bit-identical noise buffers
+    (the constructor draws torch.normal in the reference's order, camera/ray_generator.py:62-73)."""
+    import nrhints_b200 as nb
+    torch.manual_seed(123)
+    gen = nb.RayGenerator(nb.CameraModel(H=8, W=8, cx=4.0, cy=4.0, fx=10.0, fy=10.0, zn=0.1, zf=10.0), 5,
+                          nb.RayGeneratorConfig(cam_opt_mode="SE3", pl_opt=True, cam_position_noise_std=0.02,
+                                                cam_orientation_noise_std=0.01, pl_position_noise_std=0.03))
+    sd = gen.state_dict()
+    assert list(sd.keys()) == [str(k) for k in GOLD["ctor_seed123.keys"]]
+    for k, v in sd.items():
+        ref = GOLD[f"ctor_seed123.{k}"]
+        assert tuple(v.shape) == ref.shape, k
+        if k == "pl_noise":
+            np.testing.assert_array_equal(v.numpy(), ref)                      # a plain torch.normal draw
+        else:
+            np.testing.assert_allclose(v.numpy(), ref, rtol=0, atol=1e-7, err_msg=k)   # exp_map_SE3 of the draw
