@@ -13,7 +13,7 @@
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, List
 
 import torch
 
