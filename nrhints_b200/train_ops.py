@@ -12,7 +12,6 @@
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, List
 
 import torch
