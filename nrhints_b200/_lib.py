@@ -13,7 +13,11 @@ import sys
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-_LIB_PATH = _CSRC / "libnrhints_b200.so"
+# NRH_DEV_LIB=1 (developer tools under tests/tc_*.py only) selects the developer build: the same sources compiled with -DNRH_DEV,
+# which adds kernel timelines / ablation switches behind the explicit nrh_dev_configure() call.  The production library has no
+# such hooks and reads nothing from the environment.
+DEV_BUILD = os.environ.get("NRH_DEV_LIB", "0") == "1"
+_LIB_PATH = _CSRC / ("libnrhints_b200_dev.so" if DEV_BUILD else "libnrhints_b200.so")
 _SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu"]
 _HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "raygen_math.cuh", "composite_train_math.cuh",
             "../../include/nrhints_b200.h"]
@@ -128,8 +132,9 @@ EXPORTS = {
 }
 
 
-_OBJ_DIR = _CSRC / "_obj"
-_NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+_OBJ_DIR = _CSRC / ("_obj_dev" if DEV_BUILD else "_obj")
+_NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + (
+    ["-DNRH_DEV"] if DEV_BUILD else [])
 
 
 def nvcc_command(out: Path = _LIB_PATH):
@@ -210,6 +215,9 @@ def load():
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)          # AttributeError here = ABI drift: fail loudly
         fn.restype, fn.argtypes = res, args
+    if DEV_BUILD:
+        lib.nrh_dev_configure.restype = C.c_int
+        lib.nrh_dev_configure.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
     _lib = lib
     return lib
 

@@ -19,8 +19,6 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
-#include <stdlib.h>
-#include <string.h>
 #include "mlp_tc.cuh"
 #include "tc_primitives.cuh"
 
@@ -51,6 +49,22 @@ constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed 
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
 constexpr float OS_R = 1.0f / W_SCALE;                 // accumulator -> reverse signal (stays in G_SCALE units)
 
+// Developer hooks (kernel timelines, ablations that switch the MMAs / weight loads off, hand-off batching, engine generation).
+// They exist ONLY in the developer build of the library (-DNRH_DEV -> libnrhints_b200_dev.so, used by tests/tc_*.py) and are set
+// through the explicit nrh_dev_configure() call; the production library compiles them out (the macros below fold to constants)
+// and reads nothing from the environment.
+struct DevOptions { int gen; int dbg; uint32_t fmask; long long* tlog; };
+#ifdef NRH_DEV
+#define NRH_DBG(P) ((P).dbg)
+#define NRH_TLOG(P) ((P).tlog)
+DevOptions g_dev = {TC_GENERATION_DEFAULT, 0, TC_FENCE_MASK_DEFAULT, nullptr};
+inline DevOptions dev_options() { return g_dev; }
+#else
+#define NRH_DBG(P) 0
+#define NRH_TLOG(P) (static_cast<long long*>(nullptr))
+inline DevOptions dev_options() { return DevOptions{TC_GENERATION_DEFAULT, 0, TC_FENCE_MASK_DEFAULT, nullptr}; }
+#endif
+
 // ---- tensor-core section of the packed weight buffer (byte offsets from the section start) ----------------
 struct TcLayout {
     uint32_t fwd[SDF_LAYERS];     // l = 0: 2 images (hi, lo); l >= 1: 4 chunks x (hi, lo)
@@ -77,8 +91,8 @@ __host__ __device__ inline TcLayout tc_layout() {
 }
 
 // ---- training tape, per 128-point tile (see SdfTape in mlp_tc.cuh) ----
-constexpr uint32_t TAPE_SIG_BYTES = SDF_LAYERS * 128 * TM * 4;        // packed softplus' of the 8 layers  [8][128 col pairs][128 rows]
-constexpr uint32_t TAPE_G_BYTES = (SDF_LAYERS - 1) * 128 * TM * 4;    // packed g_1 .. g_7 (G_SCALE units) [7][128 col pairs][128 rows]
+constexpr uint32_t TAPE_SIG_BYTES = SDF_LAYERS * 128 * TM * 4;        // packed softplus' of the 8 layers  [8][8 sc][4 gq][128 rows] x uint4 (pk_index)
+constexpr uint32_t TAPE_G_BYTES = (SDF_LAYERS - 1) * 128 * TM * 4;    // packed g_1 .. g_7 (G_SCALE units) [7][8 sc][4 gq][128 rows] x uint4
 constexpr uint32_t TAPE_GE_BYTES = PE_PAD * TM * 4;                   // g_e fp32 (G_SCALE units)          [40][128 rows]
 constexpr uint32_t TAPE_TILE_BYTES = TAPE_SIG_BYTES + TAPE_G_BYTES + TAPE_GE_BYTES;
 
@@ -132,6 +146,24 @@ __device__ __forceinline__ float dsig_from_packed(float pk) {
     const float e = fabsf(pk);
     const float rr = rcp_approx(1.0f + e);
     return (__float_as_int(pk) >= 0 ? rr : e * rr) * OS_R;      // sign BIT: e underflows to +-0 for |100 x| > 87
+}
+// Packed per-tile arrays (softplus' of the forward layers, reverse adjoints g_1..g_7): one uint4 = the 8 columns
+// [32 sc + 8 gq, +8) of row r as four half2 words, stored [layer][sub-chunk][column group][row] -- exactly the unit an epilogue
+// thread produces / consumes per step, so every access is ONE 16-byte LDG / STG and a warp touches 512 contiguous bytes
+// (it was four strided 4-byte accesses per step; the fence of the hand-off drains them, so fewer is faster).
+__device__ __forceinline__ size_t pk_index(int l, int sc, int gq, int r) { return (((size_t)l * 8 + sc) * 4 + gq) * TM + r; }
+__device__ __forceinline__ void pk_load(const uint32_t* base, int l, int sc, int gq, int r, uint32_t (&w)[4]) {
+    const uint4 t = reinterpret_cast<const uint4*>(base)[pk_index(l, sc, gq, r)];
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+}
+// The inference kernels keep softplus' in a per-CTA global scratch that is written once and read once per tile.  After its
+// single read the data is dead: `discard.global.L2` drops the (dirty) lines from L2 instead of letting them be written back to
+// DRAM on eviction (2.3 GB of write-back per fine pass otherwise).  One lane per 128-byte line.
+__device__ __forceinline__ void pk_discard(const uint32_t* base, int l, int sc, int gq, int r) {
+    if ((r & 7) == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const uint4*>(base) + pk_index(l, sc, gq, r)) : "memory");
+}
+__device__ __forceinline__ void pk_store(uint32_t* base, int l, int sc, int gq, int r, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    reinterpret_cast<uint4*>(base)[pk_index(l, sc, gq, r)] = make_uint4(a, b, c, d);
 }
 // split 8 fp32 values into fp16 hi / lo (value ~= hi + lo) and store both as 16-byte swizzled rows (shared addresses)
 __device__ __forceinline__ void store_split8s(uint32_t s_hi, uint32_t s_lo, const float* x) {
@@ -256,6 +288,8 @@ __device__ __forceinline__ Gemm get_gemm(const TcLayout& T, int idx) {
 // the tensor pipe restarts ~0.5K clk after an accumulator completes and idles only ~0.9K clk behind the last publish.
 template <bool TRAIN>
 struct EpiT {
+    static constexpr bool kTrain = TRAIN;
+    bool discard;                          // drop the softplus' scratch lines from L2 after their only read (inference kernels)
     uint8_t* A_hi; uint8_t* A_lo; uint64_t* a_ready;      // a_ready[8]: one per sub-chunk
     // training tape (TRAIN only): `dump` = row of this thread's point in the row-major fp16 [P][256] dump that receives the
     // operand published by the CURRENT epilogue (nullptr: none); `gnx` = packed reverse-sweep adjoints of this tile
@@ -337,7 +371,6 @@ __device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int
     const uint32_t acc = wait_acc() + cq;
     if (E.tl) E.tl[1] = clock64();
     tmem_ld8(acc, vA);
-    uint32_t* const sig_l = E.sig + ((size_t)l * 128 + cq / 2) * TM + E.r;
     auto step = [&](float (&v)[8], float (&b)[8], float (&nv)[8], float* w, const int sc) {
         tmem_wait_ld();
         if (E.tl) E.tl[2 + sc * 3] = clock64();
@@ -377,10 +410,7 @@ __device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int
         }
         if (E.tl) E.tl[4 + sc * 3] = clock64();
         // global traffic goes after the fence inside publish(): softplus' stores, bias of the sub-chunk after next
-        if (GRAD) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sig_l[(size_t)(sc * 16 + i) * TM] = pack_sig2(s[2 * i], s[2 * i + 1]);
-        }
+        if (GRAD) pk_store(E.sig, l, sc, E.gq, E.r, pack_sig2(s[0], s[1]), pack_sig2(s[2], s[3]), pack_sig2(s[4], s[5]), pack_sig2(s[6], s[7]));
         if (sc < 6) {
             ldg8(bias16 + cq + (sc + 2) * 32, b);
             if (LT == 2) ldg8(head_w + cq + (sc + 2) * 32, *reinterpret_cast<float (*)[8]>(w));
@@ -405,15 +435,17 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
     ldg8(bias + cq, bA);
     const uint32_t acc = wait_acc() + cq;
     tmem_ld8(acc, vA);
-    const uint32_t* const sig_l = E.sig + ((size_t)(SDF_LAYERS - 1) * 128 + cq / 2) * TM + E.r;
     auto step = [&](float (&v)[8], float (&b)[8], float (&nv)[8], float (&nb)[8], const int sc) {
         tmem_wait_ld();
         if (sc < 7) { tmem_ld8(acc + (sc + 1) * 32, nv); ldg8(bias + cq + (sc + 1) * 32, nb); }
         float w[8], s[8];
         if (GRAD) {
             ldg8(head_w + cq + sc * 32, w);
+            uint32_t sw[4];
+            pk_load(E.sig, SDF_LAYERS - 1, sc, E.gq, E.r, sw);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 t2 = unpack_sig2(sig_l[(size_t)(sc * 16 + i) * TM]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
+            for (int i = 0; i < 4; ++i) { const float2 t2 = unpack_sig2(sw[i]); s[2 * i] = t2.x; s[2 * i + 1] = t2.y; }
+            if (!EP::kTrain && E.discard) pk_discard(E.sig, SDF_LAYERS - 1, sc, E.gq, E.r);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], OS_F, b[i]);
@@ -448,13 +480,15 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
 template <bool SKIP, bool TRAIN, class EP, class WaitAcc>
 __device__ __forceinline__ void epi_reverse(const EP& E, WaitAcc&& wait_acc, int l) {
     const int cq = E.gq * 8;
-    const uint32_t* const sig_l = E.sig + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
     float vA[8], vB[8];
     uint32_t sA[4], sB[4];
     auto load_sig = [&](uint32_t (&sg)[4], const int sc) {
+        pk_load(E.sig, l - 1, sc, E.gq, E.r, sg);
+        if (SKIP) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            sg[i] = (!SKIP || sc * 32 + cq + 2 * i < SKIP_H) ? sig_l[(size_t)(sc * 16 + i) * TM] : 0u;
+            for (int i = 0; i < 4; ++i)
+                if (sc * 32 + cq + 2 * i >= SKIP_H) sg[i] = 0u;
+        }
     };
     load_sig(sA, 0);
     load_sig(sB, 1);
@@ -482,11 +516,8 @@ __device__ __forceinline__ void epi_reverse(const EP& E, WaitAcc&& wait_acc, int
             if (TRAIN) gpk[TRAIN ? i : 0] = pack_sig2(graw[0], graw[1]);
         }
         E.publish(sc, v);
-        if (TRAIN) {
-            uint32_t* const g_l = E.gnx + ((size_t)(l - 1) * 128 + cq / 2) * TM + E.r;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) g_l[(size_t)(sc * 16 + i) * TM] = gpk[TRAIN ? i : 0];
-        }
+        if (!TRAIN && E.discard) pk_discard(E.sig, l - 1, sc, E.gq, E.r);       // sg of this step has been consumed above
+        if (TRAIN) pk_store(E.gnx, l - 1, sc, E.gq, E.r, gpk[0], gpk[TRAIN ? 1 : 0], gpk[TRAIN ? 2 : 0], gpk[TRAIN ? 3 : 0]);
         if (SKIP) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -554,7 +585,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     for (int img = 0; img < G.nsub; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                        if (P.dbg >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
+                        if (NRH_DBG(P) >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
                         mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
                         bulk_g2s(Bst + s * STAGE, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
                     }
@@ -587,16 +618,16 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             uint32_t it = 0, gc = 0, ready_seen = 0;
             const uint32_t a_hi_lo = desc_lo(smem_u32(A_hi)), a_lo_lo = desc_lo(smem_u32(A_lo)), b_lo0 = desc_lo(smem_u32(Bst));
             const uint32_t ready_s = smem_u32(ready);
-            const bool mma_on = (P.dbg != 2 && P.dbg != 4);
+            const bool mma_on = (NRH_DBG(P) != 2 && NRH_DBG(P) != 4);
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
                 for (int gi = 0; gi < NG; ++gi, ++gc) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
-                    const int lgi = (P.dbg == 9) ? gi - 8 : gi;
-                    const bool lg = lane == 0 && P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
+                    const int lgi = (NRH_DBG(P) == 9) ? gi - 8 : gi;
+                    const bool lg = lane == 0 && NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
                     for (int sc = 0; sc < G.nsub; ++sc, ++it) {
-                        if (lg) P.tlog[lgi * 32 + sc * 3 + 0] = clock64();
+                        if (lg) NRH_TLOG(P)[lgi * 32 + sc * 3 + 0] = clock64();
                         if (ready_seen <= it) {
                             uint32_t spins = 0;
                             while (true) {
@@ -607,31 +638,26 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                             __syncwarp();
                             tc_fence_after();
                         }
-                        if (lg) P.tlog[lgi * 32 + sc * 3 + 1] = clock64();
+                        if (lg) NRH_TLOG(P)[lgi * 32 + sc * 3 + 1] = clock64();
                         const uint32_t s = it % NSTAGES;
                         if (mma_on) {
                             // A: K-steps 2 sc, 2 sc + 1 of the 64-wide chunk sc / 2 (32 B per K-step inside the swizzled rows)
                             const uint32_t ko = (uint32_t)(sc >> 1) * (A_CHUNK >> 4) + (uint32_t)(sc & 1) * 4;
                             const uint32_t ah = a_hi_lo + ko, al = a_lo_lo + ko, bl = b_lo0 + s * (STAGE >> 4);
-                            umma_f16_lo_w(acc, ah, bl, idesc, (uint32_t)(sc != 0));        // A_hi * W_hi
-                            umma_f16_lo_w(acc, ah + 2, bl + 2, idesc, 1u);
-                            umma_f16_lo_w(acc, al, bl, idesc, 1u);                          // A_lo * W_hi
-                            umma_f16_lo_w(acc, al + 2, bl + 2, idesc, 1u);
-                            umma_f16_lo_w(acc, ah, bl + 4, idesc, 1u);                      // A_hi * W_lo
-                            umma_f16_lo_w(acc, ah + 2, bl + 6, idesc, 1u);
+                            umma_group6_ss_w(acc, ah, al, bl, idesc, (uint32_t)(sc != 0));  // A_hi * W_hi, A_lo * W_hi, A_hi * W_lo behind one election
                         }
                         umma_commit_w(&b_empty[s]);
-                        if (lg) P.tlog[lgi * 32 + sc * 3 + 2] = clock64();
+                        if (lg) NRH_TLOG(P)[lgi * 32 + sc * 3 + 2] = clock64();
                     }
                     umma_commit_w(&acc_full[gc & 1]);
-                    if (lg) P.tlog[lgi * 32 + 24] = clock64();
+                    if (lg) NRH_TLOG(P)[lgi * 32 + 24] = clock64();
                 }
         }
     } else if (warp >= EPI_WARP0) {
         // ======================= epilogue warps =======================
         EpiT<TRAIN> E;
         E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
-        E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask;
+        E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask; E.discard = NRH_DBG(P) != 7;
         const int q = warp & 3;
         E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
@@ -710,7 +736,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             float dot = 0.f;
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
-                E.tl = (P.tlog && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? P.tlog + 256 + l * 32 : nullptr;
+                E.tl = (NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? NRH_TLOG(P) + 256 + l * 32 : nullptr;
                 if (TRAIN) E.dump = P.tape_act + ((size_t)l * P.p_pad + p) * 256;            // this epilogue publishes a_{l+1}
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
@@ -874,11 +900,11 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 for (int gi = 0; gi < 4; ++gi, ++gc) {
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const int nch = gi == 0 ? 6 : 4;
-                    const bool lg = P.tlog && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x;
+                    const bool lg = NRH_TLOG(P) && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x;
                     for (int c = 0; c < nch; ++c) {
-                        if (lg && c == 0) P.tlog[gi * 8 + 0] = clock64();
+                        if (lg && c == 0) NRH_TLOG(P)[gi * 8 + 0] = clock64();
                         mbar_wait(&a_ready[c], (a_par >> c) & 1);
-                        if (lg && c == 0) P.tlog[gi * 8 + 1] = clock64();
+                        if (lg && c == 0) NRH_TLOG(P)[gi * 8 + 1] = clock64();
                         a_par ^= (1u << c);
                         tc_fence_after();
                         const uint32_t al = a_lo0 + c * (A_CHUNK >> 4);
@@ -894,7 +920,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     }
                     umma_commit(&acc_full[gc & 1]);
                     if (gi == 3) umma_commit(a_free);
-                    if (lg) P.tlog[gi * 8 + 2] = clock64();
+                    if (lg) NRH_TLOG(P)[gi * 8 + 2] = clock64();
                 }
         }
     } else if (warp >= EPI_WARP0) {
@@ -907,8 +933,8 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p = tile * TM + r;
             const bool valid = p < N;
-            const bool elg = P.tlog && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x && warp == EPI_WARP0 + 2 && lane == 0;
-            if (elg) P.tlog[64] = clock64();
+            const bool elg = NRH_TLOG(P) && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x && warp == EPI_WARP0 + 2 && lane == 0;
+            if (elg) NRH_TLOG(P)[64] = clock64();
             if (streamed) {
                 // features and per-ray inputs arrive as ready-made operand images; only the six per-point columns
                 // (position, normal) of chunk 4 are patched in
@@ -972,7 +998,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                     for (int c = 0; c < 6; ++c) mbar_arrive(&a_ready[c]);
                 }
             }
-            if (elg) P.tlog[65] = clock64();
+            if (elg) NRH_TLOG(P)[65] = clock64();
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
             for (int gi = 0; gi < 4; ++gi, ++gc) {
@@ -981,7 +1007,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 ldg16(bias16, bA);
                 ldg16(bias16 + 64, bB);
                 mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
-                if (elg) P.tlog[66 + gi * 2] = clock64();
+                if (elg) NRH_TLOG(P)[66 + gi * 2] = clock64();
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_base + (gc & 1) * 256 + gq * 16;
                 tmem_ld16(acc, vA);
@@ -1011,7 +1037,7 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
                 step(vB, bB, vA, 1);
                 step(vA, bA, vB, 2);
                 step(vB, bB, vA, 3);
-                if (elg) P.tlog[67 + gi * 2] = clock64();
+                if (elg) NRH_TLOG(P)[67 + gi * 2] = clock64();
                 tc_fence_before();
             }
             d0 *= (1.0f / ACT_SCALE); d1 *= (1.0f / ACT_SCALE); d2 *= (1.0f / ACT_SCALE);
@@ -1179,18 +1205,9 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     return NRH_OK;
 }
 
-// epilogue hand-off steps (bit sc = fence after sub-chunk sc); developer override NRH_TC_FMASK (bits 0 and 7 are forced)
-static uint32_t tc_fence_mask() {
-    const char* e = getenv("NRH_TC_FMASK");
-    const uint32_t m = e ? (uint32_t)strtoul(e, nullptr, 0) : TC_FENCE_MASK_DEFAULT;
-    return (m & 0xFFu) | 0x81u;
-}
-
-// engine generation for the passes generation 2 covers (developer override NRH_TC_GEN=1|2)
-static int tc_generation() {
-    const char* e = getenv("NRH_TC_GEN");
-    return e ? atoi(e) : TC_GENERATION_DEFAULT;
-}
+// epilogue hand-off steps (bit sc = fence after sub-chunk sc; bits 0 and 7 are forced) and engine generation
+static uint32_t tc_fence_mask() { return (dev_options().fmask & 0xFFu) | 0x81u; }
+static int tc_generation() { return dev_options().gen; }
 
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
                float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat, bool feat_as_image,
@@ -1204,8 +1221,7 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
     P.tape_tiles = nullptr; P.tape_act = nullptr; P.tape_u = nullptr; P.p_pad = 0;
-    { const char* e = getenv("NRH_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
-    { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+    P.dbg = dev_options().dbg; P.tlog = dev_options().tlog;
     P.fmask = tc_fence_mask();
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
@@ -1214,6 +1230,12 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     if (!grad && !wfeat && tc_generation() == 2) {          // second-generation engine (mlp_tc2.inc): sdf-only passes
         NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF2_SMEM));
         sdf_tc2_kernel<false, false><<<grid, NTHREADS, SDF2_SMEM, st>>>(P, pts, N, sdf, scratch);
+        NRH_LAUNCH_CHECK();
+        return NRH_OK;
+    }
+    if (!grad && !wfeat && tc_generation() == 3) {          // the same with the two-team epilogue
+        NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_tc2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF2_SMEM));
+        sdf_tc2_kernel<false, false, true><<<grid, NTHREADS, SDF2_SMEM, st>>>(P, pts, N, sdf, scratch);
         NRH_LAUNCH_CHECK();
         return NRH_OK;
     }
@@ -1319,7 +1341,7 @@ int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Stride
     ColTcParams P;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().col_bias16);
-    { const char* e = getenv("NRH_TC_TLOG"); P.tlog = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) + 256 : nullptr; }
+    P.tlog = dev_options().tlog ? dev_options().tlog + 256 : nullptr;
     P.w4t = Pf + L.col_w4t; P.b4 = Pf + L.col_b4;
     P.aux_img = reinterpret_cast<const uint8_t*>(aux_img);
     P.feat_img = aux_img ? reinterpret_cast<const uint8_t*>(feat) : nullptr;
@@ -1331,4 +1353,19 @@ int color_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, Stride
     return NRH_OK;
 }
 
+#ifdef NRH_DEV
+void dev_configure(int gen, int dbg, unsigned fmask, void* tlog) {
+    g_dev = DevOptions{gen, dbg, fmask, reinterpret_cast<long long*>(tlog)};
+}
+#endif
+
 }  // namespace nrh
+
+#ifdef NRH_DEV
+// developer build only: explicit configuration of the hooks above (gen: engine generation, dbg: ablation code, fmask: hand-off
+// mask, tlog: DEVICE buffer of >= 512 int64 that receives clock64 stamps, or NULL)
+extern "C" int nrh_dev_configure(int gen, int dbg, unsigned fmask, void* tlog) {
+    nrh::dev_configure(gen, dbg, fmask, tlog);
+    return 0;
+}
+#endif

@@ -183,6 +183,50 @@ __device__ __forceinline__ void umma_f16_lo_w(uint32_t d_tmem, uint32_t a_lo, ui
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
 }
+// One operand sub-chunk (2 K-steps) of the fp16 hi/lo split as ONE instruction group behind ONE election: A_hi*W_hi, A_lo*W_hi,
+// A_hi*W_lo for both K-steps = 6 MMAs.  Issued one by one through umma_*_w every MMA pays its own ELECT + VOTEU + R2UR.BROADCAST
+// preamble (~13 SASS instructions; the issuing warp shares its scheduler with four arithmetic-heavy epilogue warps, so that is
+// ~85 clk per MMA -- more than the 64.5 clk an N = 128 MMA occupies the tensor pipe); here the preamble is paid once per group.
+// A operand in TENSOR MEMORY: K-step j of the sub-chunk at columns a0 + 16 j (hi) and a0 + 16 j + 8 (lo).
+__device__ __forceinline__ void umma_group6_ts_w(uint32_t d_tmem, uint32_t a0, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 b0, b1, b2, b3;\n\t.reg .b32 a1, a2, a3, t;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 b0, {%2, %5};\n\t"
+        "add.u32 t, %2, 2;\n\tmov.b64 b1, {t, %5};\n\t"
+        "add.u32 t, %2, 4;\n\tmov.b64 b2, {t, %5};\n\t"
+        "add.u32 t, %2, 6;\n\tmov.b64 b3, {t, %5};\n\t"
+        "add.u32 a1, %1, 16;\n\tadd.u32 a2, %1, 8;\n\tadd.u32 a3, %1, 24;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b0, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b0, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b2, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b3, %3, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a0), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
+// the same with the A operand in SHARED memory: descriptor low words a_hi / a_lo of the sub-chunk's first K-step (second: + 2)
+__device__ __forceinline__ void umma_group6_ss_w(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 b0, b1, b2, b3, h0, h1, l0, l1;\n\t.reg .b32 t;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 b0, {%3, %6};\n\t"
+        "add.u32 t, %3, 2;\n\tmov.b64 b1, {t, %6};\n\t"
+        "add.u32 t, %3, 4;\n\tmov.b64 b2, {t, %6};\n\t"
+        "add.u32 t, %3, 6;\n\tmov.b64 b3, {t, %6};\n\t"
+        "mov.b64 h0, {%1, %6};\n\tadd.u32 t, %1, 2;\n\tmov.b64 h1, {t, %6};\n\t"
+        "mov.b64 l0, {%2, %6};\n\tadd.u32 t, %2, 2;\n\tmov.b64 l1, {t, %6};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h0, b0, %4, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b1, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l0, b0, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l1, b1, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h0, b2, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b3, %4, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"

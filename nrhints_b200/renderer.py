@@ -643,19 +643,19 @@ class NeuSHintRenderer(nn.Module):
                                          sdf_fn=sdf_fn, sample_major=captured is not None)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
-    #    pipelines/base_pipeline.py:120, through pageable memory; here: cached pinned staging buffers, one async copy
-    #    per field on the current stream, one sync) -------------------------------------------------------------------
-    def _pinned_like(self, name: str, v: torch.Tensor) -> torch.Tensor:
-        if not hasattr(self, "_pinned"):
-            self._pinned = {}
-        key = (name, tuple(v.shape), v.dtype)
-        buf = self._pinned.get(key)
-        if buf is None:
-            buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-            self._pinned[key] = buf
-        return buf
+    #    pipelines/base_pipeline.py:120, through pageable memory; here: pinned buffers owned by the returned object (recycled by
+    #    torch's caching host allocator once dropped), one async copy per field on the current stream, one sync) -------------
+    @staticmethod
+    def _pinned_like(name: str, v: torch.Tensor) -> torch.Tensor:
+        """A pinned host tensor OWNED BY THE CALLER.  Every call hands out fresh memory from torch's caching host allocator
+        (page-locked blocks are recycled only after the tensor that held them is gone), so results of consecutive calls never
+        alias -- the reference's evaluation loop appends `rendering_res.to('cpu')` of every chunk to a list before `td_concat`
+        (pipelines/base_pipeline.py:112-123) and must be able to do the same with these."""
+        del name
+        return torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
 
-    def to_host(self, out: RenderOutput, _skip=()) -> RenderOutput:
+    def to_host(self, out: RenderOutput, _prefilled=None) -> RenderOutput:
+        """RenderOutput in pinned host memory owned by the returned object (never aliased by later calls)."""
         host = {}
         for k, v in out.as_dict().items():
             if v is None:
@@ -663,9 +663,11 @@ class NeuSHintRenderer(nn.Module):
                 continue
             if k == "relax_inside_sphere":
                 continue
+            if _prefilled is not None and k in _prefilled:
+                host[k] = _prefilled[k]
+                continue
             buf = self._pinned_like(k, v)
-            if k not in _skip:
-                buf.copy_(v.detach(), non_blocking=True)
+            buf.copy_(v.detach(), non_blocking=True)
             host[k] = buf
         host["relax_inside_sphere"] = host["inside_sphere"]
         torch.cuda.current_stream(out.rgb.device).synchronize()
@@ -693,10 +695,13 @@ class NeuSHintRenderer(nn.Module):
                            _early_event=self._early_event)
         early = {k: getattr(out, k) for k in self._EARLY_FIELDS if getattr(out, k, None) is not None}
         self._copy_stream.wait_event(self._early_event)
+        early_host = {}
         with torch.cuda.stream(self._copy_stream):
             for k, v in early.items():
-                self._pinned_like(k, v).copy_(v, non_blocking=True)
-        host = self.to_host(out, _skip=tuple(early))           # the remaining small fields, then a sync of the main stream
+                early_host[k] = self._pinned_like(k, v)
+                early_host[k].copy_(v, non_blocking=True)
+                v.record_stream(self._copy_stream)               # allocated on the main stream, read on the copy stream
+        host = self.to_host(out, _prefilled=early_host)         # the remaining small fields, then a sync of the main stream
         self._copy_stream.synchronize()
         return host
 

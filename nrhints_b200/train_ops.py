@@ -94,7 +94,7 @@ class FlatAdam(torch.optim.Optimizer):
                     p.data = buf["param"][off:off + k].view_as(p)
                     p.grad = buf["grad"][off:off + k].view_as(p)
                     off += k
-            buf["step"] = 0
+            buf["steps"] = [0] * len(ps)                       # per parameter, as torch.optim.Adam counts them
             self._flat.append(buf)
 
     def flat_grads(self) -> List[torch.Tensor]:
@@ -116,6 +116,9 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
+        """One launch per group in the usual case.  Like torch.optim.Adam, parameters that take no part in the optimisation are
+        skipped: a parameter with requires_grad=False (SDFNetwork.freeze_geometry) keeps its value, its moments and its step
+        count; the launch is then split into the contiguous runs of active parameters that share a step count."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -125,22 +128,30 @@ class FlatAdam(torch.optim.Optimizer):
             if not buf:
                 continue
             off = 0
-            for p in group["params"]:                                        # autograd may have re-bound .grad (first backward after set_to_none)
+            runs = []                                                        # [offset, numel, step] of contiguous active parameters
+            for i, p in enumerate(group["params"]):                          # autograd may have re-bound .grad (first backward after set_to_none)
                 k = p.numel()
                 if p.grad is not None and p.grad.data_ptr() != buf["grad"].data_ptr() + 4 * off:
                     buf["grad"][off:off + k].copy_(p.grad.reshape(-1))
                     p.grad = buf["grad"][off:off + k].view_as(p)
+                if p.requires_grad:
+                    buf["steps"][i] += 1
+                    if runs and runs[-1][0] + runs[-1][1] == off and runs[-1][2] == buf["steps"][i]:
+                        runs[-1][1] += k
+                    else:
+                        runs.append([off, k, buf["steps"][i]])
                 off += k
-            buf["step"] += 1
             b1, b2 = group["betas"]
             dev = buf["param"].device
             with torch.cuda.device(dev):
-                _lib.check(lib.nrh_adam_step(buf["param"].data_ptr(), buf["grad"].data_ptr(), buf["exp_avg"].data_ptr(),
-                                             buf["exp_avg_sq"].data_ptr(), buf["param"].numel(), float(group["lr"]), float(b1), float(b2),
-                                             float(group["eps"]), int(buf["step"]), float(grad_scale),
-                                             torch.cuda.current_stream(dev).cuda_stream), "nrh_adam_step")
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                for o, k, st in runs:
+                    _lib.check(lib.nrh_adam_step(buf["param"].data_ptr() + 4 * o, buf["grad"].data_ptr() + 4 * o,
+                                                 buf["exp_avg"].data_ptr() + 4 * o, buf["exp_avg_sq"].data_ptr() + 4 * o, k,
+                                                 float(group["lr"]), float(b1), float(b2), float(group["eps"]), int(st),
+                                                 float(grad_scale), stream), "nrh_adam_step")
             # the kernel wrote through raw pointers: tell autograd / version-keyed caches (the renderer's packed weights)
-            torch.autograd.graph.increment_version(list(group["params"]))
+            torch.autograd.graph.increment_version([p for p in group["params"] if p.requires_grad])
         return loss
 
     # torch.optim.Adam-compatible checkpoints (trainer/trainer.py:156,223)
@@ -148,10 +159,10 @@ class FlatAdam(torch.optim.Optimizer):
         state, groups, idx = {}, [], 0
         for group, buf in zip(self.param_groups, self._flat):
             ids, off = [], 0
-            for p in group["params"]:
+            for i, p in enumerate(group["params"]):
                 k = p.numel()
-                if buf and buf["step"] > 0:
-                    state[idx] = {"step": torch.tensor(float(buf["step"])),
+                if buf and buf["steps"][i] > 0:
+                    state[idx] = {"step": torch.tensor(float(buf["steps"][i])),
                                   "exp_avg": buf["exp_avg"][off:off + k].view_as(p).clone(),
                                   "exp_avg_sq": buf["exp_avg_sq"][off:off + k].view_as(p).clone()}
                 ids.append(idx); idx += 1; off += k
@@ -161,17 +172,38 @@ class FlatAdam(torch.optim.Optimizer):
         return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
+        """Accepts torch.optim.Adam's layout; the layout is validated first (group count, parameters per group, moment shapes) so a
+        mismatching checkpoint raises instead of filling the flat buffers with shifted data."""
+        saved_groups = sd["param_groups"]
+        if len(saved_groups) != len(self.param_groups):
+            raise ValueError(f"loaded state dict has {len(saved_groups)} parameter groups, the optimizer has {len(self.param_groups)}")
         idx = 0
-        for group, buf, saved in zip(self.param_groups, self._flat, sd["param_groups"]):
+        for gi, (group, saved) in enumerate(zip(self.param_groups, saved_groups)):
+            if len(saved["params"]) != len(group["params"]):
+                raise ValueError(f"parameter group {gi}: loaded state dict holds {len(saved['params'])} parameters, "
+                                 f"the optimizer {len(group['params'])}")
+            for p in group["params"]:
+                st = sd["state"].get(idx)
+                if st is not None:
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        if tuple(st[k].shape) != tuple(p.shape):
+                            raise ValueError(f"parameter {idx}: {k} has shape {tuple(st[k].shape)}, the parameter {tuple(p.shape)}")
+                idx += 1
+        idx = 0
+        for group, buf, saved in zip(self.param_groups, self._flat, saved_groups):
             for k, v in saved.items():
                 if k != "params":
                     group[k] = v
             off = 0
-            for p in group["params"]:
+            for i, p in enumerate(group["params"]):
                 k = p.numel()
                 st = sd["state"].get(idx)
                 if st is not None:
                     buf["exp_avg"][off:off + k].copy_(st["exp_avg"].reshape(-1))
                     buf["exp_avg_sq"][off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
-                    buf["step"] = int(st["step"])
+                    buf["steps"][i] = int(st["step"])
+                else:
+                    buf["exp_avg"][off:off + k].zero_()
+                    buf["exp_avg_sq"][off:off + k].zero_()
+                    buf["steps"][i] = 0
                 idx += 1; off += k

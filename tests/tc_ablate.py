@@ -1,9 +1,11 @@
-import os, sys, time, subprocess
+"""Developer ablations of the tcgen05 SDF kernel (GPU box): usage tc_ablate.py [dbg code]"""
+import sys
+import tc_dev
 import torch
-sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
 import nrh_testlib as T
 import nrhints_b200 as nb
-mode = os.environ.get("NRH_TC_DEBUG", "0")
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+tc_dev.configure(gen=1, dbg=mode)
 cfg = nb.NeuSModelConfig(); sd = T.make_state("init", cfg)
 m = nb.NeuSHintRenderer(cfg, mlp_impl="tcgen05"); m.load_state_dict(sd); m.cuda()
 pts = (torch.rand(4096 * 128, 3, device="cuda") - 0.5) * 2

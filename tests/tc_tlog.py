@@ -1,22 +1,23 @@
 """Developer timeline of the tcgen05 SDF kernel (clock64 stamps of block 0, third tile); run on the GPU box.
 usage: tc_tlog.py [sdf|grad] [NRH_TC_DEBUG value]"""
 import os, sys
+import tc_dev
 import torch
-sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
-os.environ["NRH_TC_TLOG"] = hex(buf.data_ptr())
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
 import nrh_testlib as T
 import nrhints_b200 as nb
 cfg = nb.NeuSModelConfig(); sd = T.make_state("init", cfg)
 m = nb.NeuSHintRenderer(cfg, mlp_impl="tcgen05"); m.load_state_dict(sd); m.cuda()
 pts = (torch.rand(4096 * 128, 3, device="cuda") - 0.5) * 2
 grad = len(sys.argv) > 1 and sys.argv[1] == "grad"
-if len(sys.argv) > 2: os.environ["NRH_TC_DEBUG"] = sys.argv[2]
+dbg = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+fmask = int(os.environ.get("NRH_TC_FMASK", "0xFF"), 0)
+tc_dev.configure(gen=1, dbg=dbg, fmask=fmask, tlog=buf)
 m.sdf_query(pts, want_grad=grad); torch.cuda.synchronize()
 buf.zero_(); m.sdf_query(pts, want_grad=grad); torch.cuda.synchronize()
 t = buf.cpu().numpy()
 base = t[t > 0].min()
-print("mode", "grad" if grad else "sdf-only", "dbg", os.environ.get("NRH_TC_DEBUG", "0"))
+print("mode", "grad" if grad else "sdf-only", "dbg", str(dbg))
 print("MMA thread, per gemm gi: [a_ready, issued] x8 sub-chunks (relative to the wait start of sub-chunk 0), then acc commit")
 for gi in range(8):
     r = t[gi * 32: gi * 32 + 25] - base
@@ -29,5 +30,5 @@ for l in range(7):
 cm = [int(t[gi * 32 + 24] - base) for gi in range(8)]
 wa = [int(t[gi * 32 + 1] - t[gi * 32 + 0]) for gi in range(2, 7)]
 ew = [int(t[256 + l * 32 + 1] - t[256 + l * 32]) for l in range(2, 7)]
-print(f"SUMMARY cluster={os.environ.get('NRH_TC_CLUSTER','1')} dbg={os.environ.get('NRH_TC_DEBUG','0')} period/gemm {(cm[6]-cm[2])/4:.0f}  "
+print(f"SUMMARY cluster={os.environ.get('NRH_TC_CLUSTER','1')} dbg={dbg} period/gemm {(cm[6]-cm[2])/4:.0f}  "
       f"MMA first-sub-chunk wait {sum(wa)/len(wa):.0f}  epilogue accumulator wait {sum(ew)/len(ew):.0f}")

@@ -1,9 +1,9 @@
-import os, sys
+"""Developer timeline of the reflectance tcgen05 kernel (GPU box)."""
+import tc_dev
 import torch
 torch.set_grad_enabled(False)
-sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
 buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
-os.environ["NRH_TC_TLOG"] = hex(buf.data_ptr())
+tc_dev.configure(tlog=buf)
 import nrh_testlib as T
 import nrhints_b200 as nb
 from oracle import nrh_oracle as orc

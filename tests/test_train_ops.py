@@ -70,6 +70,54 @@ def test_flat_adam_matches_torch_adam():
     assert float((again._flat[0]["exp_avg"].cpu() - o_dev._flat[0]["exp_avg"].cpu()).abs().max()) < 1e-6
 
 
+def test_flat_adam_skips_frozen_parameters_and_validates_checkpoints():
+    """torch.optim.Adam skips parameters without a gradient: after SDFNetwork.freeze_geometry() (requires_grad=False) frozen
+    parameters, their moments and their step counts must not move; load_state_dict rejects a mismatching layout."""
+    import pytest
+    import nrhints_b200 as nb
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 8), (64,), (3, 64), (3,)]
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    dev = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref]
+    o_ref, o_dev = torch.optim.Adam(ref, lr=1e-2), nb.FlatAdam(dev, lr=1e-2)
+
+    def one_step(active):
+        o_ref.zero_grad(set_to_none=True); o_dev.zero_grad()
+        for i in active:
+            gr = torch.randn(ref[i].shape, generator=g)
+            (ref[i] * gr).sum().backward()
+            (dev[i] * gr.cuda()).sum().backward()
+        o_ref.step(); o_dev.step()
+    for _ in range(3):
+        one_step(range(4))
+    frozen_before = [dev[i].detach().clone() for i in (1, 2)]
+    for i in (1, 2):                                                 # freeze the two middle tensors (non-contiguous active runs)
+        ref[i].requires_grad_(False); dev[i].requires_grad_(False)
+    for _ in range(3):
+        one_step((0, 3))
+    for j, i in enumerate((1, 2)):
+        assert torch.equal(dev[i].detach(), frozen_before[j])          # no drift on stale moments
+    for p, q in zip(ref, dev):
+        assert float((q.detach().cpu() - p.detach()).abs().max()) < 2e-6
+    sd = o_dev.state_dict()
+    assert [float(sd["state"][i]["step"]) for i in range(4)] == [6.0, 3.0, 3.0, 6.0]
+    for i in (1, 2):                                                 # unfreeze: per-parameter step counts continue like torch's
+        ref[i].requires_grad_(True); dev[i].requires_grad_(True)
+    one_step(range(4))
+    for p, q in zip(ref, dev):
+        assert float((q.detach().cpu() - p.detach()).abs().max()) < 2e-6
+    # layout validation
+    other = nb.FlatAdam([torch.nn.Parameter(torch.zeros(64, 8, device="cuda")), torch.nn.Parameter(torch.zeros(7, device="cuda"))])
+    with pytest.raises(ValueError):
+        other.load_state_dict(sd)
+    two = nb.FlatAdam([{"params": [torch.nn.Parameter(torch.zeros(2, device="cuda"))]}, {"params": [torch.nn.Parameter(torch.zeros(2, device="cuda"))]}])
+    with pytest.raises(ValueError):
+        two.load_state_dict(sd)
+    bad = nb.FlatAdam([torch.nn.Parameter(torch.zeros(*s, device="cuda")) for s in [(64, 8), (64,), (64, 3), (3,)]])
+    with pytest.raises(ValueError):
+        bad.load_state_dict(sd)
+
+
 def test_flat_adam_drives_the_renderer():
     """Parameters re-homed into the flat buffer are what the kernels see, and a step invalidates the packed-weight cache."""
     import nrhints_b200 as nb
