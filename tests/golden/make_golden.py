@@ -74,35 +74,39 @@ def main():
         np.savez_compressed(HERE / f"{name}.npz", digest=np.array(T.state_digest(sd)),
                             **{"in_" + k: v.numpy() for k, v in rays.items()}, in_bg=bg.numpy(),
                             **{"out_" + k: v for k, v in ref_np.items()})
-    if only and "train_16x128_grads" not in only:
-        print("fixtures written to", HERE)
-        return
-    # ---- gradients of the training loss (pipelines/base_pipeline.py:57-62) from the reference's autograd --------
-    name = "train_16x128"
-    case = T.CASES[name]
-    cfg = T.make_config(case)
-    sd = T.make_state(case["weights"], cfg)
-    rays, bg = T.case_inputs(case)
-    ref = M.NeuSHintRenderer(ref_config(M, case))
-    ref.load_state_dict(sd, strict=True)
-    bundle = RayBundle(origins=rays["origins"], directions=rays["directions"], pl_positions=rays["pl_positions"],
-                       nears=rays["nears"], fars=rays["fars"])
-    torch.manual_seed(case["rng_seed"])
-    out = ref.forward(bundle, is_training=True, background_rgb=bg, global_step=case["global_step"])
-    gt = torch.rand(case["R"], 3, generator=torch.Generator().manual_seed(77))
-    rgb_loss = torch.nn.functional.l1_loss(out.rgb, gt, reduction="sum") / (out.rgb.size(0) + 1e-5)
-    gerr = (torch.linalg.norm(out.analytic_normals, ord=2, dim=-1) - 1.0) ** 2
-    eik = (out.relax_inside_sphere * gerr).sum() / (out.relax_inside_sphere.sum() + 1e-5)
-    loss = rgb_loss + eik * 0.1
-    loss.backward()
-    gfix = {"loss": np.array(float(loss)), "gt": gt.numpy()}
-    for k, p in ref.named_parameters():
-        g = p.grad.detach()
-        gfix["norm::" + k] = np.array(float(g.norm()))
-        if g.numel() <= 512:
-            gfix["full::" + k] = g.numpy()
-    np.savez_compressed(HERE / "train_16x128_grads.npz", **gfix)
-    print("gradient fixture:", len([k for k in gfix if k.startswith("norm::")]), "parameters, loss", float(loss))
+    # ---- gradients of the training loss (pipelines/base_pipeline.py:57-62) from the reference's autograd: all 46 parameter tensors
+    #      and the ray inputs (camera / light optimisation, camera/ray_generator.py:105-126) --------------------------------
+    for name, gt_seed in T.GRAD_CASES.items():
+        if only and name + "_grads" not in only:
+            continue
+        case = T.CASES[name]
+        cfg = T.make_config(case)
+        sd = T.make_state(case["weights"], cfg)
+        rays, bg = T.case_inputs(case)
+        ref = M.NeuSHintRenderer(ref_config(M, case))
+        ref.load_state_dict(sd, strict=True)
+        leaves = {k: rays[k].clone().requires_grad_(True) for k in ("origins", "directions", "pl_positions")}
+        bundle = RayBundle(origins=leaves["origins"], directions=leaves["directions"], pl_positions=leaves["pl_positions"],
+                           nears=rays["nears"], fars=rays["fars"])
+        torch.manual_seed(case["rng_seed"])
+        out = ref.forward(bundle, is_training=True, background_rgb=bg, global_step=case["global_step"])
+        gt = torch.rand(case["R"], 3, generator=torch.Generator().manual_seed(gt_seed))
+        rgb_loss = torch.nn.functional.l1_loss(out.rgb, gt, reduction="sum") / (out.rgb.size(0) + 1e-5)
+        gerr = (torch.linalg.norm(out.analytic_normals, ord=2, dim=-1) - 1.0) ** 2
+        eik = (out.relax_inside_sphere * gerr).sum() / (out.relax_inside_sphere.sum() + 1e-5)
+        loss = rgb_loss + eik * 0.1
+        loss.backward()
+        gfix = {"loss": np.array(float(loss)), "gt": gt.numpy()}
+        for k, p in ref.named_parameters():
+            g = p.grad.detach()
+            gfix["norm::" + k] = np.array(float(g.norm()))
+            if g.numel() <= 512:
+                gfix["full::" + k] = g.numpy()
+        for k, t in leaves.items():
+            gfix["ray::" + k] = t.grad.detach().numpy()
+        np.savez_compressed(HERE / f"{name}_grads.npz", **gfix)
+        print("gradient fixture", name, ":", len([k for k in gfix if k.startswith("norm::")]), "parameters, loss", float(loss),
+              "max |d origins|", float(leaves["origins"].grad.abs().max()))
     print("fixtures written to", HERE)
 
 

@@ -29,6 +29,8 @@ CASES = {
     "sharp_32x128": dict(R=32, renderer=dict(), weights="sharp", ray_seed=11),
     # training-mode forward: jitter on both marches, cos annealing half way
     "train_16x128": dict(R=16, renderer=dict(), weights="init", ray_seed=5, training=True, global_step=25000, rng_seed=123),
+    # trained-like training step: sharp weights (inv_s ~ 403), past warm-up and annealing (cos_anneal = 1), jitter on both marches
+    "train_sharp_24x128": dict(R=24, renderer=dict(), weights="sharp", ray_seed=13, training=True, global_step=60000, rng_seed=456),
     # PLNaive preset: no hints (316-wide reflectance input)
     "nohint_16x64": dict(R=16, renderer=dict(n_samples=32, n_importance_samples=32, shadow_hint=False, specular_hint=False),
                          weights="init", ray_seed=7),
@@ -139,12 +141,13 @@ TOL = {
     "sharp": dict(per_ray_tol=1e-3, per_sample_tol=1e-3, normals_tol=6e-3),
 }
 # The tcgen05 engine computes every product from fp16 hi/lo operand splits (~22-bit operands) and the tensor core
-# accumulates with truncation, so its SDF carries ~2e-5 absolute noise (fp32 FFMA engine: ~1e-6).  At inv_s ~ 400
-# that moves depth by up to ~1e-3 while rgb stays ~1.5e-4 (measured, tests/tc_check.py); the BASELINE.json gate
-# (rgb < 1e-3, PSNR) is unchanged, depth / displaced-sample allowances are wider for that engine.
+# accumulates with truncation, so its SDF carries ~2e-5 absolute noise (fp32 FFMA engine: ~1e-6).  Measured on B200 at
+# inv_s ~ 403 (gpurun_out/r2_07/r2_08 logs; 4096-ray case and the 32-ray fixture): rgb 1.3e-4, depth 9.7e-4, visibility 2.1e-4,
+# weights 4.1e-4, normals 2.6e-4, 1.5 % (4096 rays) to 6.3 % (32 rays) of the samples displaced.  Every field therefore keeps the
+# 1e-3 gate (normals 2e-3 at sharp weights); only the allowance for displaced far-end samples is wider than the fp32 engine's.
 TOL_TC = {
     "init": dict(per_ray_tol=1e-3, per_sample_tol=1e-3, normals_tol=1e-3, max_displaced_frac=0.10),
-    "sharp": dict(per_ray_tol=1e-3, per_sample_tol=2e-3, normals_tol=6e-3, max_displaced_frac=0.12, depth_tol=2.5e-3),
+    "sharp": dict(per_ray_tol=1e-3, per_sample_tol=1e-3, normals_tol=2e-3, max_displaced_frac=0.08),
 }
 TOL_ORACLE_VS_REF = {
     "init": dict(per_ray_tol=1e-4, per_sample_tol=1e-4, normals_tol=5e-4),
@@ -196,11 +199,20 @@ def compare_outputs(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], per_ray_
                 stats[k + "_flips"] = float((d > 0.5).mean()) if d.size else 0.0
                 assert stats[k + "_flips"] < 1e-3, f"{label}: inside_sphere flips {stats[k + '_flips']}"
                 continue
+            if k == "specular_cue":
+                # Cook-Torrance lobes reach 1 / (pi r^2) ~ 800 at roughness 0.02 (models/neus_hint_model.py:600-614): the gate is
+                # relative for values above 1 (absolute below), otherwise it would ask for 1e-6 relative accuracy at the peak
+                mag = np.maximum(1.0, np.abs(b[k].astype(np.float64)).reshape(R, S, -1).max(axis=-1))[ok]
+                d = d / mag
             tol = normals_tol if ("normals" in k and normals_tol is not None) else per_sample_tol
             m = float(d.max()) if d.size else 0.0
             stats[k] = m
             assert m < tol, f"{label}: max |d {k}| = {m:.3e} >= {tol}"
     return stats
+
+
+# training-gradient fixtures (tests/golden/<name>_grads.npz): the reference's own loss.backward() on these cases
+GRAD_CASES = {"train_16x128": 77, "train_sharp_24x128": 78}          # case -> seed of the ground-truth colours
 
 
 # ---- ray generation: seeded RawPixelBundle-like inputs --------------------------------------------

@@ -64,7 +64,7 @@ def test_forward_matches_oracle_and_fixture(name, impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("name", ["train_16x128", "outside_train_8x128"])
+@pytest.mark.parametrize("name", ["train_16x128", "train_sharp_24x128", "outside_train_8x128"])
 def test_training_mode_forward(name, impl):
     """jitter on both marches (+ the outside samples with the outside NeRF) + cos annealing; the jitters are drawn by
     torch.rand on the device in the reference's order, so the oracle is fed the very same numbers."""
@@ -177,11 +177,61 @@ def test_full_size_properties():
     assert (out.depth[:256].cpu() - want["depth"]).abs().max() < 1e-3
 
 
+# Limits per case / engine / tensor group as [max-abs error, L2 error], both relative to the tensor (max |g|, ||g||).  Measured on
+# B200 (gpurun_out/r2_07_pytest_grad.log), worst tensor of each group:
+#   init weights, cos_anneal 0.5 (16 rays): fp32 engine 4.7e-4 / 1.9e-4; tcgen05 engine 1.4e-3 / 7.4e-4; tensors behind the fp16
+#     reflectance backward (color_network.*, sdf_network.out_feat.*, light positions) 2.1e-2 / 7.8e-3
+#   sharp weights, step 60000 (24 rays, inv_s ~ 403): fp32 engine 3.6e-3 / 2.5e-3 and 6.6e-3 for the variance -- that is the fp32
+#     noise floor of the case (the oracle itself sits 2-3e-3 from the reference fixture: a displaced importance sample changes
+#     which points a ray evaluates); tcgen05 engine 7.7e-3 / 7.2e-3, reflectance group 1.4e-2 / 5.7e-3
+GRAD_TOL = {
+    "init": {"fp32": dict(max=1.5e-3, l2=1e-3), "auto": dict(max=4e-3, l2=2.5e-3), "auto_color": dict(max=4e-2, l2=1.5e-2)},
+    "sharp": {"fp32": dict(max=1.2e-2, l2=1.2e-2), "auto": dict(max=1.5e-2, l2=1.5e-2), "auto_color": dict(max=3e-2, l2=1.5e-2)},
+}
+VERBOSE_GRADS = False
+
+
+def _grad_group(pname, impl):
+    """Tensors whose gradient passes through the reflectance MLP's fp16 backward (tcgen05 engine) carry its noise."""
+    if impl != "fp32" and (pname.startswith("color_network.") or pname.startswith("sdf_network.out_feat") or pname == "ray::pl_positions"):
+        return "auto_color"
+    return impl
+
+
+
+
+@torch.no_grad()
+def test_full_size_sharp_all_fields_match_oracle():
+    """BASELINE.json config #2 size (4096 rays x 128 samples) with the trained-like sharp weights (inv_s ~ 403, perturbed
+    non-spherical field): EVERY RenderOutput field of the CUDA path against the oracle (evaluated in 512-ray chunks, the
+    reference's inference_chunk_size), at the same tolerances as the small sharp fixture."""
+    cfg = nb.NeuSModelConfig()
+    sd = T.make_state("sharp", cfg)
+    m = nb.NeuSHintRenderer(cfg, mlp_impl="auto"); m.load_state_dict(sd); m.cuda()
+    rays = orc.synthetic_rays(4096, seed=4242, crop=800)
+    out = m(nb.RayBundle(**rays).to("cuda"), background_rgb=torch.ones(1, 3).cuda(), return_extras=True)
+    got = T.to_np(out)
+    ocfg = orc.OracleConfig.from_model_config(cfg)
+    parts = []
+    for i0 in range(0, 4096, 512):
+        sl = {k: v[i0:i0 + 512] for k, v in rays.items()}
+        parts.append(T.to_np(orc.render_forward(sd, ocfg, sl["origins"], sl["directions"], sl["pl_positions"], sl["nears"], sl["fars"],
+                                                background_rgb=torch.ones(1, 3))))
+    want = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+    stats = T.compare_outputs(got, want, label="cuda[auto]-vs-oracle[4096 sharp]", **T.TOL_TC["sharp"])
+    assert stats["psnr_between"] > 60
+    print("FULLSHARP", {k: f"{v:.2e}" for k, v in stats.items()})
+
+
 @pytest.mark.parametrize("impl", IMPLS)
-def test_training_gradients_match_oracle(impl):
-    """Training-mode forward + loss.backward() (interim autograd backend: CUDA kernels for everything the reference
-    keeps under no_grad, torch ops for the differentiable fine pass) against the oracle's autograd gradients."""
-    case = T.CASES["train_16x128"]
+@pytest.mark.parametrize("name", list(T.GRAD_CASES))
+def test_training_gradients_match_oracle(name, impl):
+    """Training-mode forward + loss.backward() through the CUDA path (fused SDF forward-with-tape / second-order backward, CUDA
+    compositing node, reflectance MLP) against the oracle's autograd gradients -- which tests/test_oracle_golden.py pins to the
+    reference's own loss.backward() fixtures -- for all 46 parameter tensors INCLUDING deviation_network.variance and for the ray
+    inputs (origins / directions / light positions).  Two cases: init weights half way through annealing, and trained-like sharp
+    weights (inv_s ~ 403) at global_step 60000 (cos_anneal = 1)."""
+    case = T.CASES[name]
     m, cfg, sd = build_module(case, impl)
     rays, bg = T.case_inputs(case)
     R = case["R"]
@@ -189,46 +239,80 @@ def test_training_gradients_match_oracle(impl):
     jp = torch.rand([R, 1], device="cuda")
     js = torch.rand([R, cfg.renderer.n_shadow_samples], device="cuda")
     torch.manual_seed(7)
-    out = m(nb.RayBundle(**rays).to("cuda"), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"])
+    dev_rays = {k: v.cuda() for k, v in rays.items()}
+    for k in ("origins", "directions", "pl_positions"):
+        dev_rays[k].requires_grad_(True)
+    out = m(nb.RayBundle(**dev_rays), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"])
     assert out.rgb.requires_grad and out.weights.requires_grad and out.analytic_normals.requires_grad and out.s_val.requires_grad
     assert not out.depth.requires_grad and not out.visibilities.requires_grad
-    gt = torch.rand(R, 3, generator=torch.Generator().manual_seed(77))
+    gt = torch.rand(R, 3, generator=torch.Generator().manual_seed(T.GRAD_CASES[name]))
     loss = orc.training_loss({"rgb": out.rgb, "analytic_normals": out.analytic_normals,
                               "relax_inside_sphere": out.relax_inside_sphere}, gt.cuda())
     loss.backward()
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    leaves = {k: rays[k].clone().requires_grad_(True) for k in ("origins", "directions", "pl_positions")}
     ocfg = orc.OracleConfig.from_model_config(cfg)
-    want = orc.render_forward(sdr, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"], rays["fars"],
-                              is_training=True, background_rgb=bg, cos_anneal=0.5, jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
+    want = orc.render_forward(sdr, ocfg, leaves["origins"], leaves["directions"], leaves["pl_positions"], rays["nears"], rays["fars"],
+                              is_training=True, background_rgb=bg, cos_anneal=min(1.0, case["global_step"] / cfg.anneal_end),
+                              jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
     loss_o = orc.training_loss(want, gt)
     assert abs(float(loss) - float(loss_o)) < 1e-4
     keys = sorted(sdr)
-    go = dict(zip(keys, torch.autograd.grad(loss_o, [sdr[k] for k in keys])))
-    for name, p in m.named_parameters():
-        assert p.grad is not None and torch.isfinite(p.grad).all(), name          # DDP find_unused_parameters=False is safe
-        if name == "deviation_network.variance":
-            continue
-        g = go[name]
-        err = float((p.grad.cpu() - g).abs().max() / g.abs().max().clamp_min(1e-8))
-        # tcgen05 engine: the reflectance MLP runs on fp16 operands (as its inference kernel does); on this 2048-point batch a
-        # handful of ReLU units whose pre-activation sits within fp16 rounding of zero flip, which moves single rows of the
-        # reflectance weight gradients by a few percent of the tensor's maximum (not systematic; averages out with batch size)
-        lim = 5e-2 if (impl != "fp32" and name.startswith("color_network.")) else 2e-2
-        assert err < lim, (name, err)
+    allg = torch.autograd.grad(loss_o, [sdr[k] for k in keys] + list(leaves.values()))
+    go = dict(zip(keys, allg[:len(keys)]))
+    go.update({"ray::" + k: g for k, g in zip(leaves, allg[len(keys):])})
+    got = {n_: p.grad for n_, p in m.named_parameters()}
+    got.update({"ray::" + k: dev_rays[k].grad for k in leaves})
+    worst, failures = {}, []
+    for pname, g_cuda in got.items():
+        assert g_cuda is not None and torch.isfinite(g_cuda).all(), pname          # DDP find_unused_parameters=False is safe
+        g = go[pname]
+        d = g_cuda.detach().cpu() - g
+        e_max = float(d.abs().max() / g.abs().max().clamp_min(1e-8))
+        e_l2 = float(d.norm() / g.norm().clamp_min(1e-8))
+        grp = _grad_group(pname, impl)
+        w = worst.setdefault(grp, [0.0, 0.0, ""])
+        if e_max > w[0]:
+            w[0], w[2] = e_max, pname
+        w[1] = max(w[1], e_l2)
+        tol = GRAD_TOL[case["weights"]][grp]
+        if not (e_max < tol["max"] and e_l2 < tol["l2"]):
+            failures.append(f"{pname}: max-abs {e_max:.2e} (limit {tol['max']:.0e}), L2 {e_l2:.2e} (limit {tol['l2']:.0e})")
+        if VERBOSE_GRADS:
+            print(f"GRAD {name} {impl} {pname:45s} max {e_max:.2e} l2 {e_l2:.2e}")
+    print("GRADERR", name, impl, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}", v[2]) for k, v in worst.items()})
+    assert not failures, f"{name}[{impl}]: " + "; ".join(failures)
+    assert "deviation_network.variance" in got and float(go["deviation_network.variance"].abs()) > 0
 
 
-def test_camera_gradients_flow():
-    """cam-opt / register_view (pipelines/base_pipeline.py:71-91): gradients reach origins, directions, light positions."""
-    case = T.CASES["cfg1_64x32"]
+@pytest.mark.parametrize("kind", ["init", "sharp"])
+def test_camera_gradients_match_oracle(kind):
+    """cam-opt / register_view (pipelines/base_pipeline.py:71-91): with the network frozen, the gradients of an image loss
+    w.r.t. origins, directions and light positions equal the oracle's autograd gradients (values, not just non-zero)."""
+    case = dict(T.CASES["cfg1_64x32"], weights=kind)
     m, cfg, sd = build_module(case, "auto")
     for p in m.parameters():
         p.requires_grad_(False)
     rays, bg = T.case_inputs(case)
     dev = {k: v.cuda().requires_grad_(True) for k, v in rays.items()}
+    gt = torch.rand(case["R"], 3, generator=torch.Generator().manual_seed(5))
     out = m(nb.RayBundle(**dev), is_training=False, background_rgb=bg.cuda())
-    out.rgb.sum().backward()
-    for k in ("origins", "directions", "pl_positions"):
-        assert dev[k].grad is not None and torch.isfinite(dev[k].grad).all() and float(dev[k].grad.abs().max()) > 0, k
+    (out.rgb - gt.cuda()).abs().sum().backward()
+    leaves = {k: rays[k].clone().requires_grad_(True) for k in ("origins", "directions", "pl_positions")}
+    want = orc.render_forward(sd, orc.OracleConfig.from_model_config(cfg), leaves["origins"], leaves["directions"], leaves["pl_positions"],
+                              rays["nears"], rays["fars"], background_rgb=bg)
+    go = torch.autograd.grad((want["rgb"] - gt).abs().sum(), list(leaves.values()))
+    # measured on B200: init 1.0e-4 (origins) / 9.4e-5 (directions) / 2.1e-2 (light positions: their gradient runs through the
+    # fp16 reflectance backward only); sharp <= 9.3e-3 / ... (fp32 noise floor of the sharp field, see GRAD_TOL)
+    lim = {"init": dict(origins=2e-3, directions=2e-3, pl_positions=4e-2), "sharp": dict(origins=2e-2, directions=2e-2, pl_positions=4e-2)}[kind]
+    errs = {}
+    for k, g in zip(leaves, go):
+        got = dev[k].grad
+        assert got is not None and torch.isfinite(got).all() and float(g.abs().max()) > 0, k
+        errs[k] = float((got.cpu() - g).abs().max() / g.abs().max())
+    print("CAMGRAD", kind, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e < lim[k], f"{kind} d loss / d {k}: rel err {e:.2e} (limit {lim[k]:.0e})"
     # the reference's final z_vals are produced under no_grad (models/neus_hint_model.py:696-713): near / far get no gradient
     assert dev["nears"].grad is None or float(dev["nears"].grad.abs().max()) == 0.0
 

@@ -66,23 +66,29 @@ def test_oracle_edge_cases():
     assert torch.isfinite(out["rgb"]).all() and torch.isfinite(out["analytic_normals"]).all()
 
 
-def test_oracle_autograd_gradients_match_reference_fixture():
-    """Gradients of the training loss w.r.t. all 46 parameter tensors: oracle autograd (through its explicit reverse
-    sweep, i.e. including the second-order terms) vs the reference's own loss.backward(), committed as a fixture."""
+@pytest.mark.parametrize("name", list(T.GRAD_CASES))
+def test_oracle_autograd_gradients_match_reference_fixture(name):
+    """Gradients of the training loss w.r.t. all 46 parameter tensors (incl. deviation_network.variance) and the ray inputs
+    (origins / directions / light positions: camera and light optimisation): oracle autograd (through its explicit reverse sweep,
+    i.e. including the second-order terms) vs the reference's own loss.backward(), committed as fixtures -- the init weights half
+    way through annealing, and the trained-like sharp weights (inv_s ~ 403) at global_step 60000."""
     from oracle import nrh_oracle as orc
-    fx = np.load(T.GOLDEN_DIR / "train_16x128_grads.npz")
-    case = T.CASES["train_16x128"]
+    fx = np.load(T.GOLDEN_DIR / f"{name}_grads.npz")
+    case = T.CASES[name]
     cfg = T.make_config(case)
     sd = {k: v.clone().requires_grad_(True) for k, v in T.make_state(case["weights"], cfg).items()}
     rays, bg = T.case_inputs(case)
+    leaves = {k: rays[k].clone().requires_grad_(True) for k in ("origins", "directions", "pl_positions")}
     jp, _, js = T.case_jitters(case, cfg)
     ocfg = orc.OracleConfig.from_model_config(cfg)
-    out = orc.render_forward(sd, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"], rays["fars"],
-                             is_training=True, background_rgb=bg, cos_anneal=0.5, jitter_primary=jp, jitter_shadow=js)
+    out = orc.render_forward(sd, ocfg, leaves["origins"], leaves["directions"], leaves["pl_positions"], rays["nears"], rays["fars"],
+                             is_training=True, background_rgb=bg, cos_anneal=min(1.0, case["global_step"] / cfg.anneal_end),
+                             jitter_primary=jp, jitter_shadow=js)
     loss = orc.training_loss(out, torch.tensor(fx["gt"]))
     assert abs(float(loss) - float(fx["loss"])) < 2e-5
     keys = sorted(sd)
-    grads = dict(zip(keys, torch.autograd.grad(loss, [sd[k] for k in keys])))
+    allg = torch.autograd.grad(loss, [sd[k] for k in keys] + list(leaves.values()))
+    grads = dict(zip(keys, allg[:len(keys)]))
     n = 0
     for k in keys:
         want = float(fx["norm::" + k])
@@ -92,4 +98,8 @@ def test_oracle_autograd_gradients_match_reference_fixture():
             g = torch.tensor(fx["full::" + k])
             assert (grads[k] - g).abs().max() <= 3e-3 * g.abs().max().clamp_min(1e-7) + 1e-8, k
         n += 1
-    assert n == 46
+    assert n == 46 and "full::deviation_network.variance" in fx.files
+    for k, g in zip(leaves, allg[len(keys):]):
+        want = torch.tensor(fx["ray::" + k])
+        assert float(want.abs().max()) > 0
+        assert (g - want).abs().max() <= 3e-3 * want.abs().max(), (k, float((g - want).abs().max() / want.abs().max()))

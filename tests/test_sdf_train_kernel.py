@@ -43,12 +43,12 @@ def test_fused_sdf_backward_matches_autograd(kind, N):
     params = [p for n, p in m.named_parameters() if n.startswith("sdf_network.")]
     gs = torch.autograd.grad(loss, [x] + params)
     err = float((gs[0] - dpts_r).abs().max() / dpts_r.abs().max())
-    assert err < 1e-2, ("d_pts", err)
+    assert err < 2e-3, f"d_pts: rel err {err:.2e} (measured on B200: 1.5e-4 init / 4e-4 sharp; limit 2e-3)"
     worst = 0.0
     for n, gk in zip(names, gs[1:]):
         gr = gp_r[n]
         assert torch.isfinite(gk).all(), n
         e = float((gk - gr).abs().max() / gr.abs().max().clamp_min(1e-12))
         worst = max(worst, e)
-        assert e < 2e-2, (n, e)
+        assert e < 5e-3, f"{n}: rel err {e:.2e} (measured on B200: <= 7e-4 init / 1.5e-3 sharp; limit 5e-3)"
     print(kind, N, "d_pts rel err", err, "worst param rel err", worst)
