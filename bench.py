@@ -8,9 +8,12 @@ ray of 64 + 64 samples per primary ray, both hints, white background, inference 
 800x800 workload (nrhints_b200/workload.py), random-init (geometric) weights at seed 3407.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
 
---impl reference times the reference algorithm on the host cores: the reference is pure Python/PyTorch and
-cannot travel to the GPU box, so the timed code is the oracle port (oracle/nrh_oracle.py, pinned to the
-reference by the golden fixtures), on all host threads, on a bounded sample of the same workload.
+--impl reference times the UNMODIFIED reference (iamNCJ/NRHints, installed byte-for-byte into baseline/_ref/ by
+baseline/install_ref.py; it travels to the GPU box with the snapshot) on the box's host cores: its own
+NeuSHintRenderer.forward on the same weights and rays, one 512-ray chunk (the reference's inference_chunk_size) of the
+4096-ray workload per step, all host threads.  Only if baseline/_ref is absent does it fall back to the oracle port.
+The main arm also reports `gpu_baseline` (the same reference module on this B200 through PyTorch CUDA, TF32 off) and
+`parity_vs_reference` (our output against the reference's on the very rays that were timed).
 """
 import argparse
 import json
@@ -89,75 +92,152 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-_BEST_THREADS = None
+def workload_config(R: int, world: int, scaling: str = "weak") -> dict:
+    """The `config` object of the JSON line -- identical for the main arm and the reference arm."""
+    return {"workload": "NRHints NeuSHintRenderer.forward, BASELINE config #2: 4096 rays x (64+64) samples, shadow ray 64+64, "
+                        "shadow+specular hints, white bg, 800x800 synthetic scene, geometric-init weights seed 3407",
+            "rays_per_gpu": R, "samples_per_ray": 128, "parallelism": f"rays sharded x{world}, no data-path collective",
+            "l2": "256 MiB buffer rewritten between timed steps (L2 flush); per-step working set ~0.9 GB > 126 MB L2"}
 
 
-def _pick_threads():
-    """The reference runs PyTorch with min(8, cpus/gpus) threads (trainer/launcher.py:43); on a many-core host more
-    threads help only up to a point and over-subscription hurts, so calibrate once on a small sample and keep the best."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
-    cores = os.cpu_count() or 1
-    best, best_t = None, None
-    for th in sorted({min(cores, t) for t in (8, 16, 32, 64, cores)}):
-        _, med = cpu_reference_leg(32, 0, threads=th)
-        if best_t is None or med < best_t:
-            best, best_t = th, med
-    _BEST_THREADS = best
-    return best
+METRIC = "rays/sec (4096 rays x 128 samples forward render)"
+REF_CHUNK = 512                      # the reference's inference_chunk_size (models/neus_hint_model.py:212)
 
 
-def cpu_reference_leg(n_rays: int, repeats: int, threads: int = None):
-    """The reference algorithm (oracle port) on the host cores on `n_rays` rays of the workload."""
-    from oracle import nrh_oracle as orc
+def _reference_module(device="cpu"):
+    """The unmodified reference NeuSHintRenderer (baseline/_ref) with the benchmark's weights: torch.manual_seed(3407) + geometric
+    init gives a state_dict bit-identical to ours (checked when the fixtures are generated), loaded explicitly anyway."""
+    sys.path.insert(0, str(ROOT / "baseline"))
+    import ref_loader
+    if not ref_loader.available():
+        return None, None
+    ns = ref_loader.load()
     import nrhints_b200 as nb
-    from nrhints_b200.workload import synthetic_rays
-    cores = threads if threads is not None else _pick_threads()
-    torch.set_num_threads(cores)
-    cfg = nb.NeuSModelConfig()
     torch.manual_seed(3407)
-    state = {k: v.detach().clone() for k, v in nb.NeuSHintRenderer(cfg).state_dict().items()}
-    ocfg = orc.OracleConfig.from_model_config(cfg)
-    rays = synthetic_rays(n_rays, seed=3407)
-    bg = torch.ones(1, 3)
-    times = []
-    for i in range(repeats + 1):                   # first pass = warm-up
-        t0 = time.perf_counter()
+    ours = nb.NeuSHintRenderer(nb.NeuSModelConfig())
+    torch.manual_seed(3407)
+    ref = ns.NeuSHintRenderer(ns.NeuSModelConfig())
+    ref.load_state_dict({k: v.detach().clone() for k, v in ours.state_dict().items()}, strict=True)
+    return ref.to(device), ns
+
+
+def _ref_forward_chunks(ref, ns, rays: dict, device, chunk=REF_CHUNK):
+    """reference forward over `rays` in chunks, as its own evaluation loop does (pipelines/base_pipeline.py:112-120)."""
+    outs = []
+    bg = torch.ones(1, 3, device=device)
+    n = rays["origins"].shape[0]
+    for i0 in range(0, n, chunk):
+        b = ns.RayBundle(**{k: v[i0:i0 + chunk].to(device) for k, v in rays.items()})
         with torch.no_grad():
-            orc.render_forward(state, ocfg, rays["origins"], rays["directions"], rays["pl_positions"], rays["nears"],
-                               rays["fars"], background_rgb=bg)
-        times.append(time.perf_counter() - t0)
-    times = sorted(times[1:]) if repeats > 0 else times
-    med = times[len(times) // 2]
-    return {"value": n_rays / med, "unit": "rays/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
-            "sample": f"{n_rays} rays x 128 samples of the same workload, 1 warm-up + median of {max(repeats, 1)} passes, "
-                      f"torch {torch.get_num_threads()} threads = best of {{8,16,32,64,all}} on this host "
-                      f"(oracle port of the reference PyTorch path)"}, med
+            o = ref.forward(b, is_training=False, background_rgb=bg)
+        outs.append({"rgb": o.rgb.detach(), "depth": o.depth.detach(), "visibilities": o.visibilities.detach(),
+                     "weights": o.weights.detach(), "normals": o.normalized_analytic_normals.detach()})
+    return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+
+def cpu_reference_leg(n_chunks: int, warm: bool = True):
+    """`n_chunks` 512-ray chunks of the 4096-ray workload through the reference on the host cores -> (cpu_baseline dict, seconds per
+    chunk list).  Falls back to the oracle port when baseline/_ref is absent."""
+    from nrhints_b200.workload import synthetic_rays
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rays = synthetic_rays(4096, seed=3407)
+    ref, ns = _reference_module("cpu")
+    kind = "reference"
+    if ref is None:
+        kind = "port"
+        from oracle import nrh_oracle as orc
+        import nrhints_b200 as nb
+        cfg = nb.NeuSModelConfig()
+        torch.manual_seed(3407)
+        state = {k: v.detach().clone() for k, v in nb.NeuSHintRenderer(cfg).state_dict().items()}
+        ocfg = orc.OracleConfig.from_model_config(cfg)
+
+    def one(ci):
+        sl = {k: v[ci * REF_CHUNK:(ci + 1) * REF_CHUNK] for k, v in rays.items()}
+        t0 = time.perf_counter()
+        if kind == "reference":
+            _ref_forward_chunks(ref, ns, sl, "cpu")
+        else:
+            with torch.no_grad():
+                orc.render_forward(state, ocfg, sl["origins"], sl["directions"], sl["pl_positions"], sl["nears"], sl["fars"],
+                                   background_rgb=torch.ones(1, 3))
+        return time.perf_counter() - t0
+    if warm:
+        small = {k: v[:64] for k, v in rays.items()}
+        if kind == "reference":
+            _ref_forward_chunks(ref, ns, small, "cpu")
+    times = [one(ci % 8) for ci in range(n_chunks)]
+    mean = sum(times) / len(times)
+    base = {"value": REF_CHUNK / mean, "unit": "rays/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
+            "sample": f"{n_chunks} chunk(s) of {REF_CHUNK} rays x 128 samples of the same 4096-ray workload (the reference's "
+                      f"inference_chunk_size; a 4096-ray batch needs ~58 GB), torch.set_num_threads({cores}); "
+                      + ("UNMODIFIED reference NeuSHintRenderer.forward from baseline/_ref (manifest-verified)" if kind == "reference"
+                         else "oracle port (baseline/_ref absent)")}
+    return base, times
+
+
+def gpu_reference_leg(model, dev, rays: dict, flush):
+    """the unmodified reference module on THIS B200 through PyTorch CUDA (TF32 off, the torch default),
+    same weights and rays -- as 8 chunks of 512 (its own evaluation loop) and un-chunked -- and our output against its output."""
+    import nrhints_b200 as nb
+    ref, ns = _reference_module(dev)
+    if ref is None:
+        return None, None
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    drays = {k: v.to(dev) for k, v in rays.items()}
+    n = drays["origins"].shape[0]
+
+    def timed(chunk, reps=3):
+        with torch.device(dev):                     # the reference has device-less tensor constructors (models/neus_hint_model.py:327);
+            out = _ref_forward_chunks(ref, ns, drays, dev, chunk)      # its trainer sets the default tensor type to CUDA (trainer/trainer.py:50)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = _ref_forward_chunks(ref, ns, drays, dev, chunk)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2], out
+    ms_chunked, out = timed(REF_CHUNK)
+    ms_full = None
+    try:
+        ms_full, _ = timed(n)
+    except torch.OutOfMemoryError:
+        pass
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        mine = model(nb.RayBundle(**drays), is_training=False, background_rgb=torch.ones(1, 3, device=dev))
+    mse = float(((mine.rgb - out["rgb"]).double() ** 2).mean())
+    parity = {"rays": n, "max_abs_d_rgb": float((mine.rgb - out["rgb"]).abs().max()),
+              "psnr_between_db": float(10 * math.log10(1.0 / max(mse, 1e-30))),
+              "max_abs_d_depth": float((mine.depth - out["depth"]).abs().max()),
+              "max_abs_d_visibility": float((mine.visibilities - out["visibilities"]).abs().max()),
+              "gate": "BASELINE.json: per-pixel max |d rgb| < 1e-3, PSNR delta < 0.01 dB (<=> the two images are > 60 dB apart)",
+              "against": "unmodified reference (baseline/_ref) on the same B200, PyTorch CUDA fp32, identical weights and rays"}
+    gpu = {"value": n / (ms_chunked * 1e-3), "unit": "rays/s", "ms": ms_chunked, "kind": "reference",
+           "what": f"unmodified reference NeuSHintRenderer.forward on this GPU through PyTorch CUDA (allow_tf32=False), {n} rays as "
+                   f"{n // REF_CHUNK} chunks of {REF_CHUNK}, 1 warm-up + median of 3",
+           "unchunked": ({"value": n / (ms_full * 1e-3), "ms": ms_full} if ms_full else None)}
+    return gpu, parity
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = 256
-    per_step = []
-    base, _ = cpu_reference_leg(n_rays, 0)           # warm-up pass
-    from oracle import nrh_oracle as orc  # noqa: F401
-    for _ in range(max(args.warmup - 1, 0)):
-        cpu_reference_leg(n_rays, 0)
-    vals = []
-    for _ in range(args.steps):
-        b, med = cpu_reference_leg(n_rays, 0)
-        vals.append(med)
-    ms = 1e3 * sum(vals) / len(vals)
-    value = n_rays / (sum(vals) / len(vals))
-    base.update(value=value)
-    line = {"impl": "reference", "metric": "rays/sec (4096 rays x 128 samples forward render)", "value": value, "unit": "rays/s",
+    cpu_reference_leg(1, warm=True)                      # warm-up: one small + one full chunk (threads, allocator), whatever --warmup says
+    base, times = cpu_reference_leg(args.steps, warm=False)
+    ms = 1e3 * sum(times) / len(times)
+    value = REF_CHUNK / (sum(times) / len(times))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "NRHints forward render, 64+64 samples, shadow 64+64, both hints, 800x800 synthetic scene, "
-                                   f"bounded sample of {n_rays} rays per step on host CPU", "rays_per_step": n_rays},
+            "config": workload_config(args.rays, args.gpus), "rays_per_step": REF_CHUNK,
             "cpu_baseline": base, "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
@@ -224,8 +304,13 @@ def main():
     torch.set_grad_enabled(False)          # config #2 is the inference render (the reference evaluates under @torch.no_grad(),
                                            # pipelines/base_pipeline.py:93); with grad enabled the module would add its autograd backend
 
-    def step():
-        return model(dev_rays, is_training=False, background_rgb=bg)
+    fine_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for e in fine_ev:
+        e.record()                                # materialise the CUDA events; the library re-records them around the fine pass
+    fine_ms = []
+
+    def step(timed: bool = False):
+        return model(dev_rays, is_training=False, background_rgb=bg, _fine_events=fine_ev if timed else None)
 
     for _ in range(W):
         step()
@@ -255,6 +340,11 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - t_wall0
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    for _ in range(3):                            # the dominant kernel timed INSIDE a step (events recorded by the library)
+        flush.zero_()
+        step(timed=True)
+        torch.cuda.synchronize()
+        fine_ms.append(fine_ev[0].elapsed_time(fine_ev[1]))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -312,7 +402,9 @@ def main():
                              "MMAs per logical product (its own ceiling is 1/3 of the fp16 MMA rate: 469 TFLOP/s logical), the fp32-simt "
                              "engine runs on FFMA (75 TFLOP/s nominal)",
                 "frac_of_sustained_peak": achieved / peak_sus,
-                "kernel_ms": k_ms, "flop_per_launch": FLOP_PER_FINE_POINT * R * 128, "traffic": (_ncu_traffic(engine) or {}).get("bytes_per_launch"), "traffic_unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                "kernel_ms": k_ms, "kernel_ms_in_step": sum(fine_ms) / len(fine_ms),
+                "achieved_in_step": FLOP_PER_FINE_POINT * R * 128 / (sum(fine_ms) / len(fine_ms) * 1e-3) / 1e12,
+                "flop_per_launch": FLOP_PER_FINE_POINT * R * 128, "traffic": (_ncu_traffic(engine) or {}).get("bytes_per_launch"), "traffic_unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                 "traffic_detail": _ncu_traffic(engine),
                 "whole_step": {"achieved_tflops": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12,
                                "frac_of_tensor_peak": FLOP_PER_RAY * R / (ms_per_step * 1e-3) / 1e12 / peak_sus,
@@ -359,7 +451,22 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms = float(tt.item())
+        ar_ms = None
+        if dist is not None:                                   # the step's one collective, timed alone on the compute stream
+            for _ in range(3):
+                allreduce_flat(opt.flat_grads())
+            torch.cuda.synchronize(); dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                allreduce_flat(opt.flat_grads())
+            b.record(); torch.cuda.synchronize()
+            ar = torch.tensor([a.elapsed_time(b) / 10], device=dev, dtype=torch.float64)
+            dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+            ar_ms = float(ar.item())
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
+                 "allreduce_ms": ar_ms, "allreduce_bytes": sum(g.numel() * 4 for g in opt.flat_grads()),
+                 "allreduce_share_of_step": (ar_ms / t_ms if ar_ms else None),
                  "what": "BASELINE config #3: ray generation + forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU (the reference's train_iter), is_training=True (jitter, "
                          "global_step 60000); fused CUDA SDF forward-with-tape / backward (tcgen05), fused loss (2 launches) and flat-buffer Adam (1 launch); "
                          "CUDA compositing node (forward + hand-derived backward), reflectance MLP on fp16 library GEMMs"
@@ -367,22 +474,63 @@ def main():
         torch.set_grad_enabled(False)
         del opt
 
-    cpu = None
+    # ---- strong scaling (the reference's semantics: a FIXED global batch split over the ranks, trainer/trainer.py:118) ----------
+    # R rays in total => R / world per GPU; the forward of a rank is captured in a CUDA graph (at 512 rays per GPU the ~35 launches
+    # of a step are launch-latency bound otherwise).  Same barrier + device-event + max-over-ranks timing as the headline.
+    strong = None
+    if world > 1 and R % world == 0:
+        Rs = R // world
+        full = synthetic_rays(R, seed=3407)
+        mine_rays = nb.RayBundle(**{k: v[rank * Rs:(rank + 1) * Rs] for k, v in full.items()}).to(dev)
+
+        def time_steps(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for a, b in ev:
+                flush.zero_()
+                a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / K], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        eager_ms = time_steps(lambda: model(mine_rays, is_training=False, background_rgb=bg))
+        graph_ms = None
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                model(mine_rays, is_training=False, background_rgb=bg)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            with torch.cuda.graph(g):
+                model(mine_rays, is_training=False, background_rgb=bg)
+            graph_ms = time_steps(g.replay)
+        except Exception as e:                                  # capture is an optimisation, never a requirement
+            print("CUDA graph capture of the forward failed:", repr(e), file=sys.stderr)
+        best = min(x for x in (eager_ms, graph_ms) if x is not None)
+        strong = {"scaling": "strong", "global_rays": R, "rays_per_gpu": Rs, "value": R / (best * 1e-3), "unit": "rays/s",
+                  "ms_per_step": best, "ms_per_step_eager": eager_ms, "ms_per_step_cuda_graph": graph_ms,
+                  "what": "the same 4096-ray batch split over the ranks (no collective in the forward)"}
+
+    cpu = gpu_base = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_leg(256, 1)
+        cpu, _ = cpu_reference_leg(2, warm=True)           # 2 x 512 rays through the unmodified reference on the host cores
+        gpu_base, parity = gpu_reference_leg(model, dev, synthetic_rays(R, seed=3407 + rank), flush)
 
     if rank == 0:
         line = {
-            "metric": "rays/sec (4096 rays x 128 samples forward render)", "value": value, "unit": "rays/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if engine == "fp32-simt" else "f32 (fp16 hi/lo split operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "NRHints NeuSHintRenderer.forward, BASELINE config #2: 4096 rays x (64+64) samples, shadow ray 64+64, "
-                                   "shadow+specular hints, white bg, 800x800 synthetic scene, geometric-init weights seed 3407",
-                       "rays_per_gpu": R, "samples_per_ray": 128, "mlp_engine": engine, "parallelism": f"rays sharded x{world}, no data-path collective",
-                       "l2": "256 MiB buffer rewritten between timed steps (L2 flush); per-step working set ~0.9 GB > 126 MB L2"},
+            "dtype": "f32" if engine == "fp32-simt" else "f32 results; SDF network: fp16 hi/lo split operands x3 MMAs, fp32 accumulate; "
+                                                         "reflectance network: SINGLE-PASS fp16 operands, fp32 accumulate (narrower than the reference's fp32)",
+            "data": "synthetic", "config": workload_config(R, world), "engine": engine,
             "e2e": {"value": world * R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "pinned host RayBundle -> device, forward, full RenderOutput -> pinned host buffers (pipelines/base_pipeline.py:114-120 pattern)"},
-            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train_step": train,
+            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity_vs_reference": parity,
+            "train_step": train, "strong_scaling": strong,
             "wall_s_timed_region": wall,
         }
         _emit(line)

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 5
+#define NRH_ABI_VERSION 6
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -161,6 +161,10 @@ typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model
      * (pipelines/base_pipeline.py:120) can overlap that copy with the rest of the render on a second stream. */
     void* early_event;
     const NrhTrainCapture* train_capture;   /* nullable: see NrhTrainCapture */
+    /* nullable cudaEvent_t pair recorded on `stream` right before / after the primary fine-pass SDF kernel (forward + feature head
+     * + reverse sweep over R*S points, the dominant kernel): lets a caller time that launch INSIDE a step (bench.py roofline). */
+    void* fine_begin_event;
+    void* fine_end_event;
 } NrhOutputs;
 
 int nrh_version(void);

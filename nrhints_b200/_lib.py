@@ -22,7 +22,7 @@ _SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_en
 _HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "raygen_math.cuh", "composite_train_math.cuh",
             "../../include/nrhints_b200.h"]
 
-NRH_ABI_VERSION = 5
+NRH_ABI_VERSION = 6
 NRH_MAX_ROUGHNESS = 4
 NRH_MAX_OUTSIDE = 64
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
@@ -64,7 +64,7 @@ class NrhOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "weights", "inside_sphere", "analytic_normals", "normalized_normals",
         "visibilities", "specular_cue", "inv_s", "z_vals", "z_shadow", "sampled_color",
-        "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event", "train_capture")]
+        "normal_map", "normalized_normal_map", "specular_cue_ray", "early_event", "train_capture", "fine_begin_event", "fine_end_event")]
 
 
 class NrhTrainCapture(C.Structure):

@@ -467,6 +467,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
         if (cap->tape_bytes < sdf_train_layout((int64_t)S * R, sms).tape_bytes) { set_error("train_capture: tape too small"); return NRH_ERR_WORKSPACE; }
     }
     const bool streamed = !cap && resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
+    if (out->fine_begin_event) NRH_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(out->fine_begin_event), st));
     if (cap) {
         // the training forward (same arithmetic + tape) straight into the caller's buffers; the compositor reads them there
         const int64_t N = (int64_t)S * R;
@@ -481,6 +482,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
         NRH_CUDA_CHECK(cudaMemcpyAsync(cap->pts_soa + 2 * N, w.prim.pz, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
     } else if ((rc = run_sdf(*cfg, packed, L, P, (int64_t)S * R, w.fine.sdf, w.fine.gx, w.fine.gy, w.fine.gz, 1, w.feat,
                              w.mlp_scratch, w.mlp_scratch_bytes, sms, st, streamed))) return rc;
+    if (out->fine_end_event) NRH_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(out->fine_end_event), st));
     // ---- outside NeRF on the merged sample set (render_outside, :716-724): background alpha / colour per section ----
     const int n_out = cfg->use_outside_nerf ? cfg->n_outside : 0;
     const int St = S + n_out;

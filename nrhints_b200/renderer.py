@@ -39,9 +39,12 @@ from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NormalCo
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class RenderOutput:
-    """Same fields / shapes as the reference RenderOutput (a nerfstudio TensorDataclass there).
-    `RenderOutput.cast(cls)` re-wraps the tensors in the reference's own class when the caller is
-    the unmodified reference pipeline."""
+    """Same fields / shapes as the reference RenderOutput (models/neus_hint_model.py:216-233) and the batch operations its callers
+    use on it (the reference type is a nerfstudio-style TensorDataclass): `.shape` (batch shape), `len()`, indexing, `.reshape()`,
+    `.flatten()`, `.to()`, `.detach()`.  The reference's own helpers work on it unchanged -- `td_concat` only needs a dataclass
+    whose fields are tensors or None (utils/tensor_dataclass.py:365-384) -- so the unmodified pipeline
+    (pipelines/base_pipeline.py:114-124: `.to('cpu')`, `td_concat(rets)`, `.reshape(img.shape)`) runs with this type as is.
+    `RenderOutput.cast(cls)` re-wraps the reference fields in another class if a caller insists on the reference's own."""
     rgb: torch.Tensor                          # [R,3]
     depth: torch.Tensor                        # [R,1]
     weights: torch.Tensor                      # [R,S]
@@ -59,16 +62,21 @@ class RenderOutput:
 
     _REFERENCE_FIELDS = ("rgb", "depth", "weights", "s_val", "inside_sphere", "relax_inside_sphere",
                          "analytic_normals", "normalized_analytic_normals", "visibilities", "specular_cue")
+    # number of trailing (non-batch) dimensions per field; 1 unless listed (the reference's _field_custom_dimensions)
+    _TRAILING = {"analytic_normals": 2, "normalized_analytic_normals": 2, "specular_cue": 2, "sampled_color": 2}
 
     def as_dict(self) -> Dict[str, Optional[torch.Tensor]]:
         return {f.name: getattr(self, f.name) for f in dataclasses.fields(self)}
 
+    def _map(self, fn) -> "RenderOutput":
+        """fn(tensor, n_trailing_dims) on every tensor field."""
+        return RenderOutput(**{k: (fn(v, self._TRAILING.get(k, 1)) if v is not None else None) for k, v in self.as_dict().items()})
+
     def to(self, device, non_blocking: bool = False) -> "RenderOutput":
-        return RenderOutput(**{k: (v.to(device, non_blocking=non_blocking) if v is not None else None)
-                               for k, v in self.as_dict().items()})
+        return self._map(lambda v, t: v.to(device, non_blocking=non_blocking))
 
     def detach(self) -> "RenderOutput":
-        return RenderOutput(**{k: (v.detach() if v is not None else None) for k, v in self.as_dict().items()})
+        return self._map(lambda v, t: v.detach())
 
     def cast(self, cls):
         return cls(**{k: getattr(self, k) for k in self._REFERENCE_FIELDS})
@@ -76,6 +84,34 @@ class RenderOutput:
     @property
     def shape(self):
         return tuple(self.rgb.shape[:-1])
+
+    @property
+    def ndim(self) -> int:
+        return self.rgb.dim() - 1
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    def __len__(self) -> int:
+        if not self.shape:
+            raise TypeError("len() of a 0-d RenderOutput")
+        return self.shape[0]
+
+    def __getitem__(self, idx) -> "RenderOutput":
+        """Index the batch dimensions; the trailing dimensions of every field are kept whole."""
+        if isinstance(idx, torch.Tensor):
+            return self._map(lambda v, t: v[idx])
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        return self._map(lambda v, t: v[idx + (slice(None),) * t])
+
+    def reshape(self, shape) -> "RenderOutput":
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        return self._map(lambda v, t: v.reshape(shape + tuple(v.shape[v.dim() - t:])))
+
+    def flatten(self) -> "RenderOutput":
+        return self.reshape((-1,))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,8 +232,30 @@ class ReflectanceNetwork(nn.Module):
         for l in range(self.num_layers - 1):
             setattr(self, f"lin{l}", WNLinear(nn.Linear(dims[l], dims[l + 1]), config.weight_norm))
 
-    def forward(self, *args, **kwargs):
-        raise RuntimeError("ReflectanceNetwork is evaluated inside NeuSHintRenderer.forward (fused CUDA pipeline)")
+    def forward(self, points, normals, view_dirs, feature_vectors, point_lights, visibilities=None, specular_cue=None):
+        """Stand-alone evaluation with the reference's signature and input order (fields/reflectance_network.py:68-96:
+        [points | PE(view) | normals | PE(light) | features | PE(visibility) | PE(specular cue)] -> 4 x (Linear, ReLU) -> Linear ->
+        sigmoid).  API compatibility only: the render path never calls this -- NeuSHintRenderer.forward evaluates the network
+        inside the fused CUDA pipeline (csrc/mlp_tc.cu::color_tc_kernel) -- so this accessor is plain fp32 torch on whatever
+        device its inputs live."""
+        nf = self.config.multi_res
+
+        def pe(x):
+            freqs = 2.0 ** torch.linspace(0.0, nf - 1, nf, device=x.device, dtype=x.dtype)
+            sx = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
+            return torch.cat([x, torch.sin(torch.cat([sx, sx + torch.pi / 2.0], dim=-1))], dim=-1)   # cosine as sin(x + pi/2), as the reference
+        parts = [points, pe(view_dirs), normals, pe(point_lights), feature_vectors]
+        if self.shadow_hint:
+            parts.append(pe(visibilities))
+        if self.specular_hint:
+            parts.append(pe(specular_cue))
+        x = torch.cat(parts, dim=-1)
+        for l in range(self.num_layers - 1):
+            lin = getattr(self, f"lin{l}")
+            x = torch.nn.functional.linear(x, lin.effective_weight(), lin.bias)
+            if l < self.num_layers - 2:
+                x = torch.relu(x)
+        return torch.sigmoid(x)
 
 
 class OutsideNeRF(nn.Module):
@@ -501,7 +559,7 @@ class NeuSHintRenderer(nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
-                global_step: int = 0, return_extras: bool = False, _early_event=None) -> RenderOutput:
+                global_step: int = 0, return_extras: bool = False, _early_event=None, _fine_events=None) -> RenderOutput:
         lib = _lib.load()
         rays_o = ray_bundle.origins
         device = rays_o.device
@@ -561,6 +619,8 @@ class NeuSHintRenderer(nn.Module):
         c_out = _lib.NrhOutputs(**{k: (v.data_ptr() if v is not None else None) for k, v in out.items()})
         if _early_event is not None:
             c_out.early_event = _early_event.cuda_event
+        if _fine_events is not None:               # (begin, end) torch.cuda.Event pair around the primary fine-pass kernel
+            c_out.fine_begin_event, c_out.fine_end_event = _fine_events[0].cuda_event, _fine_events[1].cuda_event
         # training capture (tcgen05 engine): the primary fine pass of the render call doubles as the forward of the SDF autograd
         # node (it writes the tape), so the 128 fine samples per ray are evaluated once per step instead of twice
         captured = c_cap = None

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_version_and_config_validation_without_gpu():
     lib = _lib.load()
-    assert lib.nrh_version() == 5
+    assert lib.nrh_version() == _lib.NRH_ABI_VERSION == 6
     import nrhints_b200 as nb
     m = nb.NeuSHintRenderer(nb.NeuSModelConfig())
     cfg = m._c_config()
@@ -48,7 +48,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.NrhRawWeights) == (8 + 8 + 4 + 5 + 5 + 1 + 8 + 8 + 8) * 8
     assert _lib.NRH_ABI_VERSION == int(re.search(r"#define NRH_ABI_VERSION (\d+)", HEADER).group(1))
     assert C.sizeof(_lib.NrhRays) == 7 * 8
-    assert C.sizeof(_lib.NrhOutputs) == 17 * 8
+    assert C.sizeof(_lib.NrhOutputs) == 19 * 8
     assert C.sizeof(_lib.NrhTrainCapture) == 6 * 8 and C.sizeof(_lib.NrhRayGenInputs) == 10 * 8 and C.sizeof(_lib.NrhCamera) == 6 * 4
     fields = re.findall(r"(?:float|void|const NrhTrainCapture)\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
     assert fields == [n for n, _ in _lib.NrhOutputs._fields_]
