@@ -104,7 +104,7 @@ METRIC = "rays/sec (4096 rays x 128 samples forward render)"
 REF_CHUNK = 512                      # the reference's inference_chunk_size (models/neus_hint_model.py:212)
 
 
-def _reference_module(device="cpu"):
+def _reference_module(device="cpu", state=None):
     """The unmodified reference NeuSHintRenderer (baseline/_ref) with the benchmark's weights: torch.manual_seed(3407) + geometric
     init gives a state_dict bit-identical to ours (checked when the fixtures are generated), loaded explicitly anyway."""
     sys.path.insert(0, str(ROOT / "baseline"))
@@ -113,11 +113,12 @@ def _reference_module(device="cpu"):
         return None, None
     ns = ref_loader.load()
     import nrhints_b200 as nb
-    torch.manual_seed(3407)
-    ours = nb.NeuSHintRenderer(nb.NeuSModelConfig())
+    if state is None:
+        torch.manual_seed(3407)
+        state = nb.NeuSHintRenderer(nb.NeuSModelConfig()).state_dict()
     torch.manual_seed(3407)
     ref = ns.NeuSHintRenderer(ns.NeuSModelConfig())
-    ref.load_state_dict({k: v.detach().clone() for k, v in ours.state_dict().items()}, strict=True)
+    ref.load_state_dict({k: v.detach().clone().cpu() for k, v in state.items()}, strict=True)
     return ref.to(device), ns
 
 
@@ -181,8 +182,8 @@ def gpu_reference_leg(model, dev, rays: dict, flush):
     """the unmodified reference module on THIS B200 through PyTorch CUDA (TF32 off, the torch default),
     same weights and rays -- as 8 chunks of 512 (its own evaluation loop) and un-chunked -- and our output against its output."""
     import nrhints_b200 as nb
-    ref, ns = _reference_module(dev)
-    if ref is None:
+    ref, ns = _reference_module(dev, state=model.state_dict())          # the weights `model` holds NOW (the training-step
+    if ref is None:                                                     # measurement above has moved them a few Adam steps)
         return None, None
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
