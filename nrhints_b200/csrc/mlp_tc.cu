@@ -580,6 +580,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
+#pragma unroll 1
                 for (int gi = 0; gi < NG; ++gi) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     for (int img = 0; img < G.nsub; ++img, ++it) {
@@ -601,6 +602,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             uint32_t it = 0, a_par = 0;
             const uint32_t ready_s = smem_u32(ready);
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
+#pragma unroll 1
                 for (int gi = 0; gi < NG; ++gi) {
                     const int nsub = get_gemm<GRAD, FEAT>(T, gi).nsub;
                     for (int sc = 0; sc < nsub; ++sc, ++it) {
@@ -620,6 +622,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             const uint32_t ready_s = smem_u32(ready);
             const bool mma_on = (NRH_DBG(P) != 2 && NRH_DBG(P) != 4);
             for (int64_t tile = tile0; tile < tiles_padded; tile += tstride)
+#pragma unroll 1
                 for (int gi = 0; gi < NG; ++gi, ++gc) {
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
