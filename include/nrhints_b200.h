@@ -308,6 +308,25 @@ int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * adjoint dumps (db_l = sum_p zb_l / S above).  width: multiple of 8 with 256 % (width / 8) == 0; matrices 16-byte aligned. */
 int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_t mat_stride, float scale, float* out, void* stream);
 
+/* Weight-gradient reductions of a training step (the dW = delta^T h products the reference leaves to autograd behind every
+ * F.linear: fields/sdf_field.py:106-123, fields/reflectance_network.py:84-96; trainer/trainer.py:279), ALL of them in one call:
+ *     out[m, n] += scale * (*dev_scale if non-NULL) * sum_{p < rows} A[p, a_col0 + m] * B[p, b_col0 + n]
+ * A, B: row-major fp16 device matrices [rows][a_ld] / [rows][b_ld] (the operand dumps the forward / backward kernels publish),
+ * out: fp32 [m][ld_out], ACCUMULATED (the caller zeroes its gradient buffer once per step).  m == 256 with n in {64,128,192,256}
+ * runs on tcgen05 (one persistent launch for all such jobs: TMA tensor-map loads of MN-major operand tiles, 256 x n fp32
+ * accumulators in tensor memory, split-K over contiguous tile ranges, one vectorised red.add flush per CTA and job);
+ * m <= 8 (A needs 8 readable columns) is a streaming reduction on the CUDA cores.  rows_valid / cols_valid (0 = all) limit what is
+ * written.  Operands: 16-byte aligned, leading dimensions multiples of 8, a_col0 / b_col0 multiples of 8. */
+typedef struct NrhWgradJob {
+    const void* a; int64_t a_ld; int32_t a_col0;
+    const void* b; int64_t b_ld; int32_t b_col0;
+    int64_t rows;
+    int32_t m, n, rows_valid, cols_valid;
+    float scale; const float* dev_scale;
+    float* out; int64_t ld_out;
+} NrhWgradJob;
+int nrh_wgrad_f16(const NrhWgradJob* jobs, int n_jobs, void* stream);
+
 /* Differentiable compositing of the primary ray for a training step: get_alpha (models/neus_hint_model.py:339-356), the
  * transmittance scan / weights (:521-526) and rgb = sum_j w_j c_j + bg (1 - sum_j w_j) (:635-637), and the vector-Jacobian
  * product torch autograd derives for them.  Per-point inputs sdf [N], grad [N,3], color [N,3] (N = R*S) are addressed as

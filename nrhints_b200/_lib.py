@@ -18,7 +18,7 @@ _CSRC = Path(__file__).resolve().parent / "csrc"
 # such hooks and reads nothing from the environment.
 DEV_BUILD = os.environ.get("NRH_DEV_LIB", "0") == "1"
 _LIB_PATH = _CSRC / ("libnrhints_b200_dev.so" if DEV_BUILD else "libnrhints_b200.so")
-_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu"]
+_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu", "wgrad_tc.cu"]
 _HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "raygen_math.cuh", "composite_train_math.cuh",
             "../../include/nrhints_b200.h"]
 
@@ -87,6 +87,12 @@ class NrhRayGenInputs(C.Structure):
                                           "cam_pose_adjustment", "pl_adjustment")] + [("n_cameras", C.c_int64)]
 
 
+class NrhWgradJob(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a_ld", C.c_int64), ("a_col0", C.c_int32), ("b", C.c_void_p), ("b_ld", C.c_int64), ("b_col0", C.c_int32),
+                ("rows", C.c_int64), ("m", C.c_int32), ("n", C.c_int32), ("rows_valid", C.c_int32), ("cols_valid", C.c_int32),
+                ("scale", C.c_float), ("dev_scale", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64)]
+
+
 CAM_OPT_MODES = {"off": 0, "SO3xR3": 1, "SE3": 2}
 
 EXPORTS = {
@@ -128,6 +134,7 @@ EXPORTS = {
     "nrh_composite_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_wgrad_f16": (C.c_int, [C.POINTER(NrhWgradJob), C.c_int, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

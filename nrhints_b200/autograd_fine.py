@@ -149,17 +149,25 @@ class _ReflectanceF16(torch.autograd.Function):
         amax = dy.abs().max().clamp_min(1e-30)
         s = torch.exp2(torch.floor(torch.log2(256.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40)
         inv = 1.0 / s
+        from .train_ops import WgradBatch
         dz = torch.zeros(P, 8, dtype=torch.float16, device=dy.device)
         dz[:, :dy.shape[1]] = dy * s
         dws, dbs = [None] * n, [None] * n
-        dws[n - 1] = torch.mm(dz.t(), acts[n - 1], out_dtype=torch.float32)[:dy.shape[1]] * inv
+        inv1 = inv.reshape(1).contiguous()                                   # device scalar multiplied in by the reduction kernel
+        wb = WgradBatch()                                                    # all five dW = dz^T a reductions: ONE tcgen05 launch at the end
+        dws[n - 1] = torch.zeros(dy.shape[1], acts[n - 1].shape[1], dtype=torch.float32, device=dy.device)
+        wb.add(dz, acts[n - 1], dws[n - 1], dev_scale=inv1, m=dy.shape[1])
         dbs[n - 1] = dy.sum(0)
         for l in range(n - 2, -1, -1):
             dh = torch.mm(dz, w16s[l + 1])                                   # fp16 out, fp32 accumulate: the next operand
             dz = torch.ops.aten.threshold_backward(dh, acts[l + 1], 0.0)     # ReLU mask from the saved activation
-            dw = torch.mm(dz.t(), acts[l], out_dtype=torch.float32) * inv
+            kw = acts[l].shape[1]
+            dw = torch.zeros(dz.shape[1], kw, dtype=torch.float32, device=dy.device)
+            for c0 in range(0, kw, 256):                                     # the 384-wide input layer as a 256- and a 128-column job
+                wb.add(dz, acts[l], dw[:, c0:], dev_scale=inv1, b_col0=c0, n=min(256, kw - c0))
             dws[l] = dw[:, :K] if l == 0 else dw
             dbs[l] = colsum_f16(dz) * inv
+        wb.run()
         dx16 = torch.mm(dz, w16s[0])                                         # [P, Kp] fp16, loss-scaled
         G0, G1, ray_axis = ctx.ray_dims
         dparts, off = [], 0

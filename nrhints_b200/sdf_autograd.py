@@ -7,8 +7,8 @@ autograd node:
 
   forward : nrh_sdf_train_forward  (tcgen05 fused MLP: forward + feature head + reverse sweep, writing a tape)
   backward: nrh_sdf_train_backward (tcgen05, phase A / phase B chains incl. the second-order terms; csrc/mlp_tc_bwd.inc)
-            -> d_pts and fp16 operand dumps; the weight gradients are point-reductions over the dumps, done here with
-            plain library GEMMs (torch.mm, fp16 operands, fp32 accumulate/out).
+            -> d_pts and fp16 operand dumps; the weight gradients are point-reductions over the dumps: all 19 of them in ONE
+            hand-written tcgen05 launch (nrh_wgrad_f16, csrc/wgrad_tc.cu: TMA tensor-map loads, accumulators in tensor memory).
 
 The effective (weight-normed) weights enter as autograd inputs so that torch differentiates the weight-norm
 re-parametrisation itself (as in the reference); their VALUES are taken from the renderer's packed weight buffer.
@@ -22,19 +22,11 @@ from typing import List
 import torch
 
 from . import _lib
-from .train_ops import colsum_f16
+from .train_ops import WgradBatch, colsum_f16
 
 _ACT_SCALE = 16.0
 _G_SCALE = 1024.0
 _SDF_SCALE = 3.0
-
-
-def _mm_t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a^T @ b for fp16 [P,m], [P,n] operands with fp32 accumulation AND fp32 output (the sums run over ~5e5 points)."""
-    try:
-        return torch.mm(a.t(), b, out_dtype=torch.float32)
-    except (TypeError, RuntimeError):
-        return a.t().float() @ b.float()
 
 
 def _fourier(x: torch.Tensor, n_freq: int) -> torch.Tensor:
@@ -109,32 +101,43 @@ class _SdfFine(torch.autograd.Function):
         gb0 = view(bwd, int(lay.bwd_gb0_off), 1, 64)[0]     # gb_0 (S units)
         gb = view(bwd, int(lay.bwd_gb_off), 8)              # gb_1 .. gb_8
         zb = view(bwd, int(lay.bwd_zb_off), 8)              # zb_0 .. zb_7
-        inv_s = 1.0 / scale
-        grads: List[torch.Tensor] = []
+        inv_s = (1.0 / scale).reshape(1).contiguous()        # device scalar: the reductions below multiply by it (no host sync)
         # bias gradients: column sums of the fp16 dumps, all eight layers in ONE launch (nrh_colsum_f16) + the sdf head's
         db_all = colsum_f16(zb) * inv_s                      # [8,256]
         gb8_sum = colsum_f16(gb[7]) * inv_s                  # [256]
+        # weight gradients: dW_l = u_l^T gb_{l-1} / (1024 S) + zb_l^T a_{l-1} / (16 S), the feature head and the d_sdf row of the sdf
+        # head -- 19 point-reductions over the dumps, ALL in one tcgen05 launch (nrh_wgrad_f16, csrc/wgrad_tc.cu)
+        z32 = lambda r, c: torch.zeros(r, c, dtype=torch.float32, device=device)        # noqa: E731
+        wb = WgradBatch()
+        # a_0 = PE(3 pts) enters as an fp16 operand like every other activation (|PE| <= 1.5: no scaling needed)
+        e = torch.zeros(P, 64, dtype=torch.float16, device=device)
+        e[:N, :39] = _fourier(x * _SDF_SCALE, 6).to(torch.float16)
+        dWs = [z32(256, 64)] + [z32(256, 256) for _ in range(7)]
+        wb.add(u[0], gb0, dWs[0], scale=1.0 / _G_SCALE, dev_scale=inv_s).add(zb[0], e, dWs[0], dev_scale=inv_s)
+        for l in range(1, 8):
+            rv = 217 if l == 3 else 0
+            wb.add(u[l], gb[l - 1], dWs[l], scale=1.0 / _G_SCALE, dev_scale=inv_s, rows_valid=rv)
+            wb.add(zb[l], act[l - 1], dWs[l], scale=1.0 / _ACT_SCALE, dev_scale=inv_s, rows_valid=rv)
+        a8 = act[7]
+        # head operands: d_feat * S as fp16 [P,256] (feature head) and d_sdf * S as column 0 of an fp16 [P,8] matrix (sdf head row)
+        df16 = torch.zeros(P, 256, dtype=torch.float16, device=device)
+        df16[:N] = d_feat * scale
+        ds16 = torch.zeros(P, 8, dtype=torch.float16, device=device)
+        ds16[:N, 0] = d_sdf.reshape(N) * scale
+        dW_f, head_s = z32(256, 256), z32(1, 256)
+        wb.add(df16, a8, dW_f, scale=1.0 / _ACT_SCALE, dev_scale=inv_s)
+        wb.add(ds16, a8, head_s, scale=1.0 / _ACT_SCALE, dev_scale=inv_s, m=1)
+        wb.run()
+        grads: List[torch.Tensor] = []
         for l in range(8):
+            dW, db = dWs[l], db_all[l]
             if l == 0:
-                # a_0 = PE(3 pts) enters as an fp16 operand like every other activation (|PE| <= 1.5: no scaling needed)
-                e = torch.zeros(P, 64, dtype=torch.float16, device=device)
-                e[:N, :39] = _fourier(x * _SDF_SCALE, 6).to(torch.float16)
-                dW = _mm_t(u[0], gb0)[:, :39] * (inv_s / _G_SCALE) + _mm_t(zb[0], e)[:, :39] * inv_s
-            else:
-                dW = _mm_t(u[l], gb[l - 1]) * (inv_s / _G_SCALE) + _mm_t(zb[l], act[l - 1]) * (inv_s / _ACT_SCALE)
-            db = db_all[l]
+                dW = dW[:, :39]
             if l == 3:
                 dW, db = dW[:217], db[:217]
             grads += [dW, db]
-        a8 = act[7]
-        # head operands [d_sdf | d_feat] * scale as ONE fp16 matrix [P, 264] -> one GEMM against a_8 gives dw_sdf's second term and dW_feat
-        dh = torch.zeros(P, 264, dtype=torch.float16, device=device)
-        dh[:N, :256] = (d_feat * scale).to(torch.float16)
-        dh[:N, 256] = (d_sdf.reshape(N) * scale).to(torch.float16)
-        head = _mm_t(dh, a8) * (inv_s / _ACT_SCALE)          # [264,256]
-        d_ws = (gb8_sum + head[256]) / _SDF_SCALE
+        d_ws = (gb8_sum + head_s[0]) / _SDF_SCALE
         d_bs = d_sdf.sum().reshape(1) / _SDF_SCALE
-        dW_f = head[:256]
         db_f = d_feat.sum(0)
         grads += [d_ws.reshape(1, 256), d_bs, dW_f, db_f]
         return (None, d_pts, None) + tuple(grads)

@@ -33,6 +33,50 @@ def colsum_f16(mats: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     return out if mats.dim() == 3 else out[0]
 
 
+class WgradBatch:
+    """All weight-gradient reductions of a training step in ONE launch (nrh_wgrad_f16, csrc/wgrad_tc.cu: tcgen05 + TMA tensor maps):
+        out[m, n] += scale * dev_scale * sum_p A[p, a_col0 + m] * B[p, b_col0 + n]
+    `add()` queues a job (A [P, a_ld] / B [P, b_ld]: fp16 row-major CUDA tensors or column windows of them; out: fp32 [m, >= n],
+    accumulated); `run()` launches them and keeps the operands alive until then."""
+
+    def __init__(self):
+        self.jobs, self.keep = [], []
+
+    def add(self, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scale: float = 1.0, dev_scale: torch.Tensor = None,
+            m: int = None, n: int = None, a_col0: int = 0, b_col0: int = 0, rows_valid: int = 0, cols_valid: int = 0):
+        for t in (a, b):
+            if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 2 and t.stride(1) == 1):
+                raise RuntimeError("WgradBatch operands must be 2-D fp16 CUDA tensors with unit column stride (no CPU fallback)")
+        if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1):
+            raise RuntimeError("WgradBatch output must be a 2-D fp32 CUDA tensor with unit column stride")
+        if a.shape[0] != b.shape[0]:
+            raise RuntimeError("WgradBatch operands need the same number of rows")
+        j = _lib.NrhWgradJob()
+        j.a, j.a_ld, j.a_col0 = a.data_ptr(), a.stride(0), a_col0
+        j.b, j.b_ld, j.b_col0 = b.data_ptr(), b.stride(0), b_col0
+        j.rows = a.shape[0]
+        j.m = m if m is not None else a.shape[1] - a_col0
+        j.n = n if n is not None else b.shape[1] - b_col0
+        j.rows_valid, j.cols_valid = rows_valid, cols_valid
+        j.scale = float(scale)
+        j.dev_scale = dev_scale.data_ptr() if dev_scale is not None else None
+        j.out, j.ld_out = out.data_ptr(), out.stride(0)
+        self.jobs.append(j)
+        self.keep += [a, b, out, dev_scale]
+        return self
+
+    def run(self):
+        if not self.jobs:
+            return
+        import ctypes as C
+        lib = _lib.load()
+        dev = self.keep[0].device
+        arr = (_lib.NrhWgradJob * len(self.jobs))(*self.jobs)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrh_wgrad_f16(arr, len(self.jobs), torch.cuda.current_stream(dev).cuda_stream), "nrh_wgrad_f16")
+        self.jobs, self.keep = [], []
+
+
 class _TrainLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgb, rgb_gt, normals, mask, igr_weight: float):

@@ -84,6 +84,21 @@ def test_reflectance_node_chain_rule(monkeypatch):
     monkeypatch.setattr(torch, "mm", mm)
     monkeypatch.setattr(torch, "_addmm_activation", lambda b, x, w: torch.relu(orig_mm(x.float(), w.float()) + b.float()).half())
     monkeypatch.setattr(train_ops, "colsum_f16", lambda m, scale=1.0: m.float().sum(0) * scale)
+
+    class HostWgrad:                    # nrh_wgrad_f16 (one tcgen05 launch on the GPU): out += scale * dev_scale * A^T B, fp32 accumulation
+        def __init__(self):
+            self.jobs = []
+
+        def add(self, a, b, out, scale=1.0, dev_scale=None, m=None, n=None, a_col0=0, b_col0=0, rows_valid=0, cols_valid=0):
+            m = m if m is not None else a.shape[1] - a_col0
+            n = n if n is not None else b.shape[1] - b_col0
+            self.jobs.append((a[:, a_col0:a_col0 + m], b[:, b_col0:b_col0 + n], out, scale * (float(dev_scale) if dev_scale is not None else 1.0), m, n))
+            return self
+
+        def run(self):
+            for a, b, out, sc, m, n in self.jobs:
+                out[:m, :n] += orig_mm(a.float().t(), b.float()) * sc
+    monkeypatch.setattr(train_ops, "WgradBatch", HostWgrad)
     g = torch.Generator().manual_seed(0)
     R, S, widths = 8, 20, [3, 27, 3, 27, 256, 9, 36]                   # the 361-wide input of the nr-hints preset
     P = R * S
