@@ -211,15 +211,43 @@ template <int MR>
 __global__ void __launch_bounds__(256)
 k_wgrad_skinny(const __half* __restrict__ A, long long a_ld, const __half* __restrict__ B, long long b_ld, long long rows, int n,
                float scale, const float* __restrict__ dev_scale, float* __restrict__ out, long long ld_out, int rows_valid) {
+    static_assert(MR == 8, "one 16-byte load fetches the 8 A values of a row");
     const int col = blockIdx.y * 256 + threadIdx.x;
     float acc[MR];
 #pragma unroll
     for (int i = 0; i < MR; ++i) acc[i] = 0.f;
     if (col < n) {
-        for (long long p = blockIdx.x; p < rows; p += gridDim.x) {
-            const float b = __half2float(B[p * b_ld + col]);
+        const long long stride = gridDim.x;
+        long long p = blockIdx.x;
+        // four rows in flight per trip: the loop is latency-bound otherwise (one dependent 16-byte broadcast load + one 2-byte load per row)
+        for (; p + 3 * stride < rows; p += 4 * stride) {
+            uint4 a4[4]; float b4[4];
 #pragma unroll
-            for (int i = 0; i < MR; ++i) acc[i] = fmaf(__half2float(__ldg(A + p * a_ld + i)), b, acc[i]);
+            for (int u = 0; u < 4; ++u) {
+                a4[u] = __ldg(reinterpret_cast<const uint4*>(A + (p + u * stride) * a_ld));
+                b4[u] = __half2float(B[(p + u * stride) * b_ld + col]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&a4[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    acc[2 * i] = fmaf(f.x, b4[u], acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(f.y, b4[u], acc[2 * i + 1]);
+                }
+            }
+        }
+        for (; p < rows; p += stride) {
+            const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(A + p * a_ld));
+            const float b = __half2float(B[p * b_ld + col]);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&a4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h2[i]);
+                acc[2 * i] = fmaf(f.x, b, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(f.y, b, acc[2 * i + 1]);
+            }
         }
         const float sc = scale * (dev_scale ? __ldg(dev_scale) : 1.0f);
 #pragma unroll
@@ -273,10 +301,11 @@ extern "C" int nrh_wgrad_f16(const NrhWgradJob* jobs, int njobs, void* stream) {
         const NrhWgradJob& J = jobs[i];
         if (!J.a || !J.b || !J.out || J.rows <= 0) { set_error("nrh_wgrad_f16: job %d has a null operand or no rows", i); return NRH_ERR_INVALID; }
         if (J.m <= 8) {                                 // skinny reduction on the CUDA cores
+            if ((reinterpret_cast<uintptr_t>(J.a) & 15) || (J.a_ld & 7) || (J.a_col0 & 7)) { set_error("nrh_wgrad_f16: job %d: skinny A rows must be 16-byte aligned", i); return NRH_ERR_INVALID; }
             if (J.n <= 0 || J.n > 1024 || J.m < 1) { set_error("nrh_wgrad_f16: job %d: bad shape %d x %d", i, J.m, J.n); return NRH_ERR_INVALID; }
             const __half* A = reinterpret_cast<const __half*>(J.a) + J.a_col0;
             const __half* B = reinterpret_cast<const __half*>(J.b) + J.b_col0;
-            dim3 grid(296, (J.n + 255) / 256);
+            dim3 grid(1184, (J.n + 255) / 256);                   // 8 CTAs per SM, ~440 rows each
             k_wgrad_skinny<8><<<grid, 256, 0, st>>>(A, J.a_ld, B, J.b_ld, J.rows, J.cols_valid > 0 ? J.cols_valid : J.n, J.scale, J.dev_scale,
                                                     J.out, J.ld_out, J.rows_valid > 0 ? (J.rows_valid < J.m ? J.rows_valid : J.m) : J.m);
             NRH_LAUNCH_CHECK();
