@@ -308,6 +308,18 @@ int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * adjoint dumps (db_l = sum_p zb_l / S above).  width: multiple of 8 with 256 % (width / 8) == 0; matrices 16-byte aligned. */
 int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_t mat_stride, float scale, float* out, void* stream);
 
+/* Reflectance network of a training step (fields/reflectance_network.py:68-96 under autograd in the reference), tcgen05 engine.
+ * Forward: x16 = the concatenated network input [P][384] fp16, row-major, in the reference's order [points 3 | PE(view) 27 | normal 3
+ * | PE(light) 27 | feature 256 | PE(visibility) 9 | PE(specular cue) 36] (columns beyond the configuration's input width must be zero)
+ * -> acts [4][P][256] fp16 (post-ReLU hidden activations x16, kept for the backward and as weight-gradient operands) and y [P][4]
+ * fp32 (columns 0..2 = the pre-sigmoid output).  Backward: dy [P][3] fp32 and the power-of-two loss scale *loss_scale (device) ->
+ * dz [4][P][256] fp16 (adjoints of the hidden pre-activations, layer 0 first), dy16 [P][8] fp16 (dy * S in columns 0..2) and
+ * dx [P][384] fp16 (adjoint of x16), all in units of S.  The weight gradients follow with nrh_wgrad_f16:
+ *   dW_l = dz_l^T a_l / (16 S) (a_0 = x16: / S), dW_out = dy16^T a_4 / (16 S); biases: column sums of dz_l / S. */
+int nrh_color_train_forward(const NrhConfig* cfg, const void* packed, const void* x16, int64_t P, void* acts, float* y, void* stream);
+int nrh_color_train_backward(const NrhConfig* cfg, const void* packed, const float* dy, const float* loss_scale, const void* acts,
+                             int64_t P, void* dz, void* dy16, void* dx, void* stream);
+
 /* Weight-gradient reductions of a training step (the dW = delta^T h products the reference leaves to autograd behind every
  * F.linear: fields/sdf_field.py:106-123, fields/reflectance_network.py:84-96; trainer/trainer.py:279), ALL of them in one call:
  *     out[m, n] += scale * (*dev_scale if non-NULL) * sum_{p < rows} A[p, a_col0 + m] * B[p, b_col0 + n]

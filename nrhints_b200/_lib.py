@@ -19,7 +19,7 @@ _CSRC = Path(__file__).resolve().parent / "csrc"
 DEV_BUILD = os.environ.get("NRH_DEV_LIB", "0") == "1"
 _LIB_PATH = _CSRC / ("libnrhints_b200_dev.so" if DEV_BUILD else "libnrhints_b200.so")
 _SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu", "wgrad_tc.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "raygen_math.cuh", "composite_train_math.cuh",
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "color_train_tc.inc", "raygen_math.cuh", "composite_train_math.cuh",
             "../../include/nrhints_b200.h"]
 
 NRH_ABI_VERSION = 6
@@ -135,6 +135,9 @@ EXPORTS = {
                                                C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrh_wgrad_f16": (C.c_int, [C.POINTER(NrhWgradJob), C.c_int, C.c_void_p]),
+    "nrh_color_train_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_color_train_backward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

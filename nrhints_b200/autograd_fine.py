@@ -86,6 +86,22 @@ class _LinearF16(torch.autograd.Function):
         return dx, dw, dy.sum(0)
 
 
+def _split_input_gradient(ctx, dx16: Tensor, inv: Tensor):
+    """dx16 [P, Kp] fp16 (loss-scaled adjoint of the concatenated input) -> the gradients of the column blocks that need one
+    (per-ray blocks: summed over the samples of the ray)."""
+    G0, G1, ray_axis = ctx.ray_dims
+    dparts, off = [], 0
+    for i, k in enumerate(ctx.widths):
+        if not ctx.needs_input_grad[3 + i]:
+            dparts.append(None)
+        elif ctx.per_ray[i]:
+            dparts.append(dx16.view(G0, G1, -1)[:, :, off:off + k].sum(1 - ray_axis, dtype=torch.float32) * inv)
+        else:
+            dparts.append(dx16[:, off:off + k].float() * inv)
+        off += k
+    return tuple(dparts)
+
+
 class _ReflectanceF16(torch.autograd.Function):
     """The reflectance MLP (fields/reflectance_network.py:84-96: 4 x (Linear 256, ReLU), Linear 3; the sigmoid stays outside)
     as ONE autograd node on fp16-operand / fp32-accumulate library GEMMs -- the operand precision of the CUDA reflectance
@@ -96,8 +112,11 @@ class _ReflectanceF16(torch.autograd.Function):
     GEMMs and bias gradients one column-sum launch each (nrh_colsum_f16)."""
 
     @staticmethod
-    def forward(ctx, n_parts, ray_dims, *args):
-        """args = the n_parts column blocks of the input (concatenated in order) followed by 5 weights and 5 biases.  A block is
+    def forward(ctx, renderer, n_parts, ray_dims, *args):
+        """renderer: the owning NeuSHintRenderer -> forward AND backward run on the hand-written tcgen05 kernels
+        (nrh_color_train_forward / _backward, csrc/color_train_tc.inc; weights come from its packed operand images) and the weight
+        gradients on nrh_wgrad_f16; None -> the same arithmetic on library GEMMs (kept for the host-side chain-rule test).
+        args = the n_parts column blocks of the input (concatenated in order) followed by 5 weights and 5 biases.  A block is
         either per point ([P, k_i] fp32) or per RAY ([R, k_i]: view / light / hint encodings are the same for all samples of a
         ray); ray_dims = (G0, G1, ray_axis) says how the P points factor into [G0, G1] and which axis is the ray.  The blocks are
         written straight into the padded fp16 operand (no fp32 concatenation pass, per-ray blocks by a broadcast copy) and
@@ -112,7 +131,7 @@ class _ReflectanceF16(torch.autograd.Function):
         per_ray = [t.shape[0] != P for t in parts]
         assert all(t.shape[0] == (n_rays if pr else P) for t, pr in zip(parts, per_ray))
         K = sum(widths)
-        Kp = (K + 63) // 64 * 64
+        Kp = 384 if renderer is not None else (K + 63) // 64 * 64
         h16 = torch.empty(P, Kp, dtype=torch.float16, device=parts[0].device)
         h3 = h16.view(G0, G1, Kp)
         off = 0
@@ -124,6 +143,13 @@ class _ReflectanceF16(torch.autograd.Function):
             off += k
         if Kp > K:
             h16[:, K:] = 0
+        ctx.renderer = renderer
+        ctx.n, ctx.K, ctx.widths, ctx.per_ray, ctx.ray_dims = n, K, widths, per_ray, ray_dims
+        if renderer is not None:
+            from .train_ops import color_train_forward
+            acts4, y4 = color_train_forward(renderer, h16)
+            ctx.save_for_backward(h16, acts4)
+            return y4[:, :ws[-1].shape[0]]
         acts, w16s = [h16], []
         for l in range(n - 1):
             w16 = ws[l].detach().to(torch.float16)
@@ -137,18 +163,34 @@ class _ReflectanceF16(torch.autograd.Function):
         w16s.append(wl)
         y = torch.mm(h16, wl.t(), out_dtype=torch.float32)[:, :ws[-1].shape[0]] + bs[-1].detach()
         ctx.save_for_backward(*acts, *w16s)
-        ctx.n, ctx.K, ctx.widths, ctx.per_ray, ctx.ray_dims = n, K, widths, per_ray, ray_dims
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from .train_ops import colsum_f16
         n, K = ctx.n, ctx.K
-        acts, w16s = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         P = dy.shape[0]
         amax = dy.abs().max().clamp_min(1e-30)
         s = torch.exp2(torch.floor(torch.log2(256.0 / amax))).clamp(2.0 ** -40, 2.0 ** 40)
         inv = 1.0 / s
+        if ctx.renderer is not None:
+            # hand-written path: one tcgen05 kernel for the adjoint chain, one for all weight gradients, one column-sum launch
+            from .train_ops import WgradBatch, color_train_backward
+            h16, acts4 = ctx.saved_tensors
+            s1, inv1 = s.reshape(1).contiguous(), inv.reshape(1).contiguous()
+            dz4, dy16, dx16 = color_train_backward(ctx.renderer, dy, s1, acts4)
+            z32 = lambda r, c: torch.zeros(r, c, dtype=torch.float32, device=dy.device)      # noqa: E731
+            dws = [z32(256, 384)] + [z32(256, 256) for _ in range(3)] + [z32(dy.shape[1], 256)]
+            wb = WgradBatch()
+            wb.add(dz4[0], h16, dws[0], dev_scale=inv1, n=256).add(dz4[0], h16, dws[0][:, 256:], dev_scale=inv1, b_col0=256, n=128)
+            for l in range(1, 4):
+                wb.add(dz4[l], acts4[l - 1], dws[l], scale=1.0 / 16.0, dev_scale=inv1)           # the saved activations are x16
+            wb.add(dy16, acts4[3], dws[4], scale=1.0 / 16.0, dev_scale=inv1, m=dy.shape[1])
+            wb.run()
+            dws[0] = dws[0][:, :K]
+            dbs = list(colsum_f16(dz4) * inv) + [dy.sum(0)]
+            return (None, None, None) + _split_input_gradient(ctx, dx16, inv) + tuple(dws) + tuple(dbs)
+        acts, w16s = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         from .train_ops import WgradBatch
         dz = torch.zeros(P, 8, dtype=torch.float16, device=dy.device)
         dz[:, :dy.shape[1]] = dy * s
@@ -169,17 +211,7 @@ class _ReflectanceF16(torch.autograd.Function):
             dbs[l] = colsum_f16(dz) * inv
         wb.run()
         dx16 = torch.mm(dz, w16s[0])                                         # [P, Kp] fp16, loss-scaled
-        G0, G1, ray_axis = ctx.ray_dims
-        dparts, off = [], 0
-        for i, k in enumerate(ctx.widths):
-            if not ctx.needs_input_grad[2 + i]:
-                dparts.append(None)
-            elif ctx.per_ray[i]:
-                dparts.append(dx16.view(G0, G1, -1)[:, :, off:off + k].sum(1 - ray_axis, dtype=torch.float32) * inv)
-            else:
-                dparts.append(dx16[:, off:off + k].float() * inv)
-            off += k
-        return (None, None) + tuple(dparts) + tuple(dws) + tuple(dbs)
+        return (None, None, None) + _split_input_gradient(ctx, dx16, inv) + tuple(dws) + tuple(dbs)
 
 
 class _CompositeTrain(torch.autograd.Function):
@@ -250,7 +282,7 @@ def _linear_f16_ok(x: Tensor) -> bool:
 def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
                 sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
                 background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
-                refl_freq: int = 4, sdf_fn=None, sample_major: bool = False) -> Dict[str, Tensor]:
+                refl_freq: int = 4, sdf_fn=None, sample_major: bool = False, renderer=None) -> Dict[str, Tensor]:
     """render_core's differentiable part (models/neus_hint_model.py:475-651) given the sample positions and hints.
 
     weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b; col_w, col_b: lists of 5).
@@ -311,7 +343,7 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
         if specular_cue is not None:
             parts.append(_fourier(specular_cue, refl_freq))
         ray_dims = (S, R, 1) if sample_major else (R, S, 0)
-        hcol = _ReflectanceF16.apply(len(parts), ray_dims, *parts, *weights["col_w"], *weights["col_b"])
+        hcol = _ReflectanceF16.apply(renderer, len(parts), ray_dims, *parts, *weights["col_w"], *weights["col_b"])
     else:
         parts = [pts, _fourier(dirs, refl_freq), n_hat if normalized_normals else grad, _fourier(pls, refl_freq), feat]
         if visibilities is not None:

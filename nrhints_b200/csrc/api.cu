@@ -392,6 +392,27 @@ int nrh_sdf_train_backward(const NrhConfig* cfg, const void* packed, const float
                                  reinterpret_cast<float*>(workspace), workspace_bytes, sms, (cudaStream_t)stream);
 }
 
+int nrh_color_train_forward(const NrhConfig* cfg, const void* packed, const void* x16, int64_t P, void* acts, float* y, void* stream) {
+    g_launches = 0;
+    int rc = nrh_check_config(cfg); if (rc) return rc;
+    if (resolve_impl(*cfg) != NRH_MLP_TCGEN05) { set_error("nrh_color_train_forward needs the tcgen05 engine"); return NRH_ERR_UNSUPPORTED; }
+    if (P == 0) return NRH_OK;
+    if (!packed || !x16 || !acts || !y || P < 0) { set_error("null argument"); return NRH_ERR_INVALID; }
+    int sms; if ((rc = device_sms(&sms))) return rc;
+    return color_train_forward_tc(packed, make_layout(*cfg), x16, P, acts, y, sms, (cudaStream_t)stream);
+}
+
+int nrh_color_train_backward(const NrhConfig* cfg, const void* packed, const float* dy, const float* loss_scale, const void* acts,
+                             int64_t P, void* dz, void* dy16, void* dx, void* stream) {
+    g_launches = 0;
+    int rc = nrh_check_config(cfg); if (rc) return rc;
+    if (resolve_impl(*cfg) != NRH_MLP_TCGEN05) { set_error("nrh_color_train_backward needs the tcgen05 engine"); return NRH_ERR_UNSUPPORTED; }
+    if (P == 0) return NRH_OK;
+    if (!packed || !dy || !loss_scale || !acts || !dz || !dy16 || !dx || P < 0) { set_error("null argument"); return NRH_ERR_INVALID; }
+    int sms; if ((rc = device_sms(&sms))) return rc;
+    return color_train_backward_tc(packed, make_layout(*cfg), dy, loss_scale, acts, P, dz, dy16, dx, sms, (cudaStream_t)stream);
+}
+
 int nrh_sphere_trace(const NrhConfig* cfg, const void* packed, const float* origins, const float* directions, int64_t R,
                      int max_iterations, float threshold, float far_limit, int check_every,
                      float* hit_points, float* hit_depths, void* workspace, size_t workspace_bytes, void* stream) {

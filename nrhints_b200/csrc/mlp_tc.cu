@@ -16,6 +16,7 @@
 //
 // Reference semantics: /root/reference/fields/sdf_field.py:106-148, fields/reflectance_network.py:68-96,
 // fields/encodings.py:168-176.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -74,6 +75,13 @@ struct TcLayout {
     uint32_t sdf_bias16;          // [8][256] fp32 biases * ACT_SCALE
     uint32_t col_bias16;          // [4][256] fp32 biases * ACT_SCALE
     uint32_t feat_rev;            // 8 images of W_feat^T (backward of the feature head)
+    // reflectance network, training step (color_train_tc.cu): layer 0 in the reference's NATURAL input order
+    // [pts | PE(view) | normal | PE(light) | feature | PE(vis) | PE(spec)] (6 chunks, K padded to 384), and the transposed
+    // weights of the backward: col_rev[l] (l = 1..3): 4 images [256 in x 64 out]; col_rev0: per 64-wide out-chunk one
+    // [256 x 64] image (input rows 0..255) followed by one [128 x 64] image (input rows 256..383)
+    uint32_t col_fwd0n;
+    uint32_t col_rev[4];          // [0] unused (see col_rev0)
+    uint32_t col_rev0;
     uint32_t total;
 };
 __host__ __device__ inline TcLayout tc_layout() {
@@ -86,6 +94,10 @@ __host__ __device__ inline TcLayout tc_layout() {
     t.sdf_bias16 = off; off += SDF_LAYERS * 256 * 4;
     t.col_bias16 = off; off += 4 * 256 * 4;
     t.feat_rev = off; off += 8 * IMG;
+    t.col_fwd0n = off; off += 6 * IMG;
+    t.col_rev[0] = 0;
+    for (int l = 1; l < 4; ++l) { t.col_rev[l] = off; off += 4 * IMG; }
+    t.col_rev0 = off; off += 4 * (IMG + IMG / 2);
     t.total = off;
     return t;
 }
@@ -1062,12 +1074,15 @@ color_tc_kernel(ColTcParams P, Strided3 pts, Strided3 nrm, const float* __restri
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+#include "color_train_tc.inc"
+
 // ===============================================================================================================
 // operand-image builders (weight packing)
 // ===============================================================================================================
 struct Seg { int dst_k0, src_col0, len, lo; };      // lo: 0 = fp16(x), 1 = the residual x - fp16(x)
 struct ImgJob {
-    const float* src; int src_ld;        // element (n, kcol) = src[n*src_ld + kcol]
+    const float* src; int src_ld;        // element (n, kcol) = src[n*src_ld + kcol]   (tr: src[kcol*src_ld + n])
+    int tr;
     int nrows_valid;                     // rows beyond are zero
     int nrows_img;                       // 256 or 64
     Seg seg[4]; int nseg;                // k-range mapping inside this 64-wide chunk
@@ -1091,7 +1106,8 @@ __global__ void k_build_images(const __grid_constant__ JobTable Tb) {
         if (n < J.nrows_valid)
             for (int s = 0; s < J.nseg; ++s)
                 if (k >= J.seg[s].dst_k0 && k < J.seg[s].dst_k0 + J.seg[s].len) {
-                    v = J.src[(size_t)n * J.src_ld + J.seg[s].src_col0 + (k - J.seg[s].dst_k0)] * J.scale;
+                    const int kc = J.seg[s].src_col0 + (k - J.seg[s].dst_k0);
+                    v = (J.tr ? J.src[(size_t)kc * J.src_ld + n] : J.src[(size_t)n * J.src_ld + kc]) * J.scale;
                     lo |= J.seg[s].lo;
                 }
         const __half h = __float2half_rn(v);
@@ -1105,7 +1121,7 @@ __global__ void k_scale_copy(const float* __restrict__ src, float* __restrict__ 
 }
 
 // jobs are collected on the host and flushed by tc_pack in one launch
-struct JobList { JobTable t; int n; };
+struct JobList { JobTable t; int n; int tr; };       // tr: jobs queued from now on read their source transposed
 thread_local JobList* g_jobs = nullptr;
 
 int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
@@ -1113,7 +1129,7 @@ int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, co
     (void)st;
     if (!g_jobs || g_jobs->n >= TC_MAX_JOBS) { set_error("image job table overflow"); return NRH_ERR_INVALID; }
     ImgJob& J = g_jobs->t.j[g_jobs->n++];
-    J.src = src; J.src_ld = src_ld; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
+    J.src = src; J.src_ld = src_ld; J.tr = g_jobs->tr; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
     for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0, 0};
     J.lo = lo; J.scale = W_SCALE; J.dst = reinterpret_cast<__half*>(dst);
     return NRH_OK;
@@ -1160,7 +1176,7 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     const TcLayout T = tc_layout();
     int rc;
     static thread_local JobList jobs;              // 20 KB: kept off the stack
-    jobs.n = 0;
+    jobs.n = 0; jobs.tr = 0;
     g_jobs = &jobs;
     struct Reset { ~Reset() { g_jobs = nullptr; } } reset_on_exit;
     // forward: B[n = out][k = in] = W native [out][in]
@@ -1194,6 +1210,18 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     }
     for (int l = 1; l < 4; ++l)
         if ((rc = build_matrix(raw.col_W[l], 256, 256, 256, 256, 4, false, tcb + T.col[l], IMG, st))) return rc;
+    // training images of the reflectance network: layer 0 in natural input order, and W_l^T for the backward chain
+    if ((rc = build_matrix(raw.col_W[0], cin, 256, 256, cin, 6, false, tcb + T.col_fwd0n, IMG, st))) return rc;
+    jobs.tr = 1;                                          // B[n = in][k = out] = W[k][n]: read the native [out][in] matrix transposed
+    for (int l = 1; l < 4; ++l)
+        if ((rc = build_matrix(raw.col_W[l], 256, 256, 256, 256, 4, false, tcb + T.col_rev[l], IMG, st))) return rc;
+    for (int c = 0; c < 4; ++c) {
+        Seg s{0, c * 64, 64};
+        uint8_t* dst = tcb + T.col_rev0 + (size_t)c * (IMG + IMG / 2);
+        if ((rc = build_image(raw.col_W[0], cin, cin < 256 ? cin : 256, 256, &s, 1, 0, dst, st))) return rc;
+        if ((rc = build_image(raw.col_W[0] + 256, cin, cin - 256, 128, &s, 1, 0, dst + IMG, st))) return rc;
+    }
+    jobs.tr = 0;
     if ((rc = flush_image_jobs(st))) return rc;
     // biases pre-multiplied by ACT_SCALE (the forward epilogues work in x16 units)
     for (int l = 0; l < SDF_LAYERS; ++l) {
@@ -1330,6 +1358,44 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
     Strided3 S3{pts, pts + 1, pts + 2, 3};
     NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM));
     sdf_bwd_tc_kernel<<<grid, NTHREADS, SDF_SMEM, st>>>(P, S3, N, scratch);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int color_train_forward_tc(const void* packed, const PackedLayout& L, const void* x16, int64_t P, void* acts, float* y, int num_sms,
+                           cudaStream_t st) {
+    if (P <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    ColTrainParams A{};
+    A.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    A.bias16 = reinterpret_cast<const float*>(A.tc + tc_layout().col_bias16);
+    A.w4t = Pf + L.col_w4t; A.b4 = Pf + L.col_b4;
+    A.acts = reinterpret_cast<__half*>(acts); A.y = y; A.P = P;
+    alignas(64) CUtensorMap xmap;
+    int rc;
+    if ((rc = encode_tensor_map_f16(&xmap, x16, 384, P, 64, TM))) return rc;      // boxes of [128 points x 64 columns]: one K-major operand chunk
+    const int64_t ntiles = (P + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(color_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLT_SMEM));
+    color_train_fwd_kernel<<<grid, NTHREADS, COLT_SMEM, st>>>(xmap, A);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int color_train_backward_tc(const void* packed, const PackedLayout& L, const float* dy, const float* scale, const void* acts, int64_t P,
+                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st) {
+    if (P <= 0) return NRH_OK;
+    const float* Pf = reinterpret_cast<const float*>(packed);
+    ColTrainParams A{};
+    A.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
+    A.w4t = Pf + L.col_w4t;
+    A.acts = const_cast<__half*>(reinterpret_cast<const __half*>(acts));
+    A.dy = dy; A.scale = scale;
+    A.dz = reinterpret_cast<__half*>(dz); A.dy16 = reinterpret_cast<__half*>(dy16); A.dx = reinterpret_cast<__half*>(dx); A.P = P;
+    const int64_t ntiles = (P + TM - 1) / TM;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(color_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLT_SMEM));
+    color_train_bwd_kernel<<<grid, NTHREADS, COLT_SMEM, st>>>(A);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

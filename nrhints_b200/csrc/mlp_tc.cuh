@@ -10,6 +10,9 @@ constexpr float TC_ACT_SCALE = 16.0f;          // forward activations are stored
 constexpr uint32_t TC_TILE_FEAT_BYTES = 65536; // one tile of features as operand images: 4 chunks x [128 x 64] fp16
 constexpr uint32_t TC_TILE_AUX_BYTES = 32768;  // one ray block of non-feature reflectance inputs: 2 chunks
 
+// host helper (wgrad_tc.cu): CUtensorMap (128 bytes, 64-byte aligned, passed as void*) of a row-major fp16 matrix, SWIZZLE_128B boxes
+int encode_tensor_map_f16(void* out_map, const void* ptr, long long ld, long long rows, int box_cols, int box_rows);
+
 bool tc_available();
 size_t tc_packed_bytes(const NrhConfig& cfg);
 size_t tc_scratch_bytes(int num_sms);
@@ -50,5 +53,14 @@ int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Stri
 int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
                           const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
                           float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);
+
+// ---- training: reflectance network forward (with activation dumps) and backward (color_train_tc.inc) ------------------------------
+// x16: [P][384] fp16 input in the reference's concatenation order (361 valid columns, rest zero); acts: [4][P][256] fp16 a_1..a_4
+// (x TC_ACT_SCALE); y: [P][4] fp32 pre-sigmoid outputs.  Backward: dy [P][3] fp32, *scale = power-of-two loss scale S;
+// dz: [4][P][256] fp16 dz_0..dz_3, dy16: [P][8] fp16, dx: [P][384] fp16 -- all in S units.
+int color_train_forward_tc(const void* packed, const PackedLayout& L, const void* x16, int64_t P, void* acts, float* y, int num_sms,
+                           cudaStream_t st);
+int color_train_backward_tc(const void* packed, const PackedLayout& L, const float* dy, const float* scale, const void* acts, int64_t P,
+                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st);
 
 }  // namespace nrh

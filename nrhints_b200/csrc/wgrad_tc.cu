@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nrh_common.cuh"
+#include "mlp_tc.cuh"
 #include "tc_primitives.cuh"
 
 namespace nrh {
@@ -60,10 +61,6 @@ struct WgParams {
 };
 static_assert(sizeof(WgParams) <= 32000, "wgrad parameter block exceeds the kernel parameter space");
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
 // kind::f16, fp16 x fp16 -> fp32, BOTH operands MN-major (bits 15 / 16), dense
 __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
     return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -256,18 +253,31 @@ k_wgrad_skinny(const __half* __restrict__ A, long long a_ld, const __half* __res
     }
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
+}  // namespace
+
+// Tensor map of a row-major fp16 matrix [rows][ld] for boxes of [box_rows x box_cols] elements, SWIZZLE_128B (box_cols = 64: the
+// 128-byte rows of the canonical K-major / MN-major operand atoms), zero fill outside.  The driver entry point is looked up through the
+// runtime (no link dependency on libcuda).
+int encode_tensor_map_f16(void* out_map, const void* ptr, long long ld, long long rows, int box_cols, int box_rows) {
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    if (!enc) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+            enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
     }
-    return fn;
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NRH_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) { set_error("tensor-map operands need 16-byte alignment and ld %% 8 == 0"); return NRH_ERR_INVALID; }
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] fp16 matrix", (int)r, rows, ld); return NRH_ERR_CUDA; }
+    return NRH_OK;
 }
 
-}  // namespace
 }  // namespace nrh
 
 extern "C" int nrh_wgrad_f16(const NrhWgradJob* jobs, int njobs, void* stream) {
@@ -283,16 +293,8 @@ extern "C" int nrh_wgrad_f16(const NrhWgradJob* jobs, int njobs, void* stream) {
         for (int i = 0; i < nmaps; ++i)
             if (keys[i].p == ptr && keys[i].ld == ld && keys[i].rows == rows) { *idx = i; return NRH_OK; }
         if (nmaps >= WG_MAX_MAPS) { set_error("nrh_wgrad_f16: too many distinct operand matrices"); return NRH_ERR_INVALID; }
-        PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
-        if (!enc) { set_error("nrh_wgrad_f16: cuTensorMapEncodeTiled is not available from this driver"); return NRH_ERR_CUDA; }
-        if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) { set_error("nrh_wgrad_f16: operands need 16-byte alignment and ld %% 8 == 0"); return NRH_ERR_INVALID; }
-        const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-        const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-        const cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
-        const CUresult r = enc(&P.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] fp16 matrix", (int)r, rows, ld); return NRH_ERR_CUDA; }
+        const int rc = encode_tensor_map_f16(&P.maps[nmaps], ptr, ld, rows, 64, 64);
+        if (rc) return rc;
         keys[nmaps] = Key{ptr, ld, rows};
         *idx = nmaps++;
         return NRH_OK;

@@ -700,7 +700,8 @@ class NeuSHintRenderer(nn.Module):
         sdf_fn = (lambda pts: sdf_autograd.sdf_fine(self, pts, w, cap)) if self.mlp_impl in ("auto", "tcgen05") else None
         return autograd_fine.render_fine(w, rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
                                          float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res,
-                                         sdf_fn=sdf_fn, sample_major=captured is not None)
+                                         sdf_fn=sdf_fn, sample_major=captured is not None,
+                                         renderer=self if (sdf_fn is not None and self.color_network.d_in_total <= 384) else None)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: pinned buffers owned by the returned object (recycled by

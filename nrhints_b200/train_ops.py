@@ -77,6 +77,41 @@ class WgradBatch:
         self.jobs, self.keep = [], []
 
 
+def color_train_forward(renderer, x16: torch.Tensor):
+    """Reflectance network forward of a training step on tcgen05 (nrh_color_train_forward): x16 [P,384] fp16 (the reference's input
+    order, zero padded) -> (acts [4,P,256] fp16 = post-ReLU hidden activations x16, y [P,4] fp32 pre-sigmoid outputs)."""
+    import ctypes as C
+    lib = _lib.load()
+    if not (x16.is_cuda and x16.dtype == torch.float16 and x16.dim() == 2 and x16.shape[1] == 384 and x16.is_contiguous()):
+        raise RuntimeError("color_train_forward needs a contiguous CUDA fp16 [P,384] input (no CPU fallback)")
+    dev, P = x16.device, x16.shape[0]
+    packed, cfg = renderer._ensure_packed(dev), renderer._c_config()
+    acts = torch.empty(4, P, 256, dtype=torch.float16, device=dev)
+    y = torch.empty(P, 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nrh_color_train_forward(C.byref(cfg), packed.data_ptr(), x16.data_ptr(), P, acts.data_ptr(), y.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream), "nrh_color_train_forward")
+    return acts, y
+
+
+def color_train_backward(renderer, dy: torch.Tensor, scale: torch.Tensor, acts: torch.Tensor):
+    """Backward chain of the reflectance network on tcgen05 (nrh_color_train_backward): dy [P,3] fp32, scale = device scalar S ->
+    (dz [4,P,256] fp16, dy16 [P,8] fp16, dx [P,384] fp16), all in units of S."""
+    import ctypes as C
+    lib = _lib.load()
+    dev, P = dy.device, dy.shape[0]
+    packed, cfg = renderer._ensure_packed(dev), renderer._c_config()
+    dy = dy.to(torch.float32).contiguous()
+    dz = torch.empty(4, P, 256, dtype=torch.float16, device=dev)
+    dy16 = torch.empty(P, 8, dtype=torch.float16, device=dev)
+    dx = torch.empty(P, 384, dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nrh_color_train_backward(C.byref(cfg), packed.data_ptr(), dy.data_ptr(), scale.data_ptr(), acts.data_ptr(), P,
+                                                dz.data_ptr(), dy16.data_ptr(), dx.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream), "nrh_color_train_backward")
+    return dz, dy16, dx
+
+
 class _TrainLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgb, rgb_gt, normals, mask, igr_weight: float):

@@ -112,7 +112,7 @@ def test_reflectance_node_chain_rule(monkeypatch):
         for i in (0, 1, 2, 3, 4):                                      # position, view, normal, light, feature carry gradients
             parts[i].requires_grad_(True)
         ray_dims = (S, R, 1) if sample_major else (R, S, 0)
-        y = autograd_fine._ReflectanceF16.apply(len(parts), ray_dims, *parts, *ws, *bs)
+        y = autograd_fine._ReflectanceF16.apply(None, len(parts), ray_dims, *parts, *ws, *bs)
         cot = torch.randn(P, 3, generator=g) * 1e-3
         leaves = parts[:5] + ws + bs
         got = torch.autograd.grad((y * cot).sum(), leaves)
