@@ -34,6 +34,10 @@ FLOP_PER_RAY = 766.6e6          # algorithmic, de-duplicated forward FLOPs per r
 BYTES_PER_RAY = 7240            # 52 B in + 7188 B out
 # dominant kernel = the fine-pass SDF kernel (forward with feature head + reverse sweep) over R*128 points
 FLOP_PER_FINE_POINT = 1049088.0 + 918016.0
+# backward of a training step per fine point: SDF phase A (918 016) + phase B incl. the feature head (1 049 088)
+# + 17 weight-gradient products (2 x 918 016 + 131 072) + reflectance adjoint chain and weight gradients (2 x 579 584)
+FLOP_PER_FINE_POINT_BWD = 918016.0 + 1049088.0 + (2 * 918016.0 + 131072.0) + 2 * 579584.0
+FLOP_PER_RAY_TRAIN = FLOP_PER_RAY + 128 * FLOP_PER_FINE_POINT_BWD
 
 
 def measured_peaks():
@@ -428,30 +432,42 @@ def main():
         pixels = SimpleNamespace(**{k: v.to(dev) for k, v in vars(pb).items()})
         opt = pipe.make_optimizer()                              # parameters / gradients / moments re-homed into flat buffers
 
+        sync = (lambda: allreduce_flat(opt.flat_grads())) if dist is not None else None
+
         def train_step():
-            opt.zero_grad()                                        # one memset
+            # NRHintPipeline.train_step: ray generation -> nrh_render_train_forward -> nrh_train_loss -> nrh_render_backward (gradients
+            # written straight into FlatAdam's flat buffer) -> the one collective of the loop on that buffer (its mean folded into the
+            # Adam launch) -> nrh_adam_step; no autograd graph, no library GEMM
+            pipe.train_step(pixels, global_step=60000, optimizer=opt, grad_sync=sync)
+
+        def train_step_autograd():
+            # the same step the way an unmodified trainer drives it (trainer/trainer.py:269-283): loss.backward() lands in ONE autograd node
+            opt.zero_grad()
             res = pipe(pixels, global_step=60000)
-            loss = pipe.get_train_loss_dict(res, pixels)["loss"]  # pipelines/base_pipeline.py:57-62, 2 launches
+            loss = pipe.get_train_loss_dict(res, pixels)["loss"]
             loss.backward()
-            # the one collective of the training loop: the flat gradient buffer itself (no packing); the mean over ranks is
-            # folded into the Adam launch
             scale = allreduce_flat(opt.flat_grads()) if dist is not None else 1.0
             opt.step(grad_scale=scale)
-        for _ in range(2):
-            train_step()
-        torch.cuda.synchronize()
+
+        def time_train(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            if dist is not None:
+                dist.barrier()
+            for a, b in tev:
+                flush.zero_()
+                a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev) / n], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
         tsteps = max(3, min(K, 5))
-        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(tsteps)]
-        if dist is not None:
-            dist.barrier()
-        for a, b in tev:
-            flush.zero_()
-            a.record(); train_step(); b.record()
-        torch.cuda.synchronize()
-        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev) / tsteps], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_ms = float(tt.item())
+        t_ms = time_train(train_step, tsteps)
+        train_launches = int(model.last_launch_count + getattr(model, "last_backward_launch_count", 0))
+        t_auto_ms = time_train(train_step_autograd, tsteps)
         ar_ms = None
         if dist is not None:                                   # the step's one collective, timed alone on the compute stream
             for _ in range(3):
@@ -465,12 +481,21 @@ def main():
             ar = torch.tensor([a.elapsed_time(b) / 10], device=dev, dtype=torch.float64)
             dist.all_reduce(ar, op=dist.ReduceOp.MAX)
             ar_ms = float(ar.item())
+        tf = FLOP_PER_RAY_TRAIN * R / (t_ms * 1e-3) / 1e12
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
+                 "ms_per_step_through_autograd_node": t_auto_ms,
+                 "library_launches_forward_plus_backward": train_launches,
                  "allreduce_ms": ar_ms, "allreduce_bytes": sum(g.numel() * 4 for g in opt.flat_grads()),
                  "allreduce_share_of_step": (ar_ms / t_ms if ar_ms else None),
-                 "what": "BASELINE config #3: ray generation + forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU (the reference's train_iter), is_training=True (jitter, "
-                         "global_step 60000); fused CUDA SDF forward-with-tape / backward (tcgen05), fused loss (2 launches) and flat-buffer Adam (1 launch); "
-                         "CUDA compositing node (forward + hand-derived backward), reflectance MLP on fp16 library GEMMs"
+                 "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"] if "bf16_tflops_sustained" in peaks else None,
+                              "unit": "TFLOP/s", "frac": (tf / peaks["bf16_tflops_sustained"]) if "bf16_tflops_sustained" in peaks else None,
+                              "flop_per_step": FLOP_PER_RAY_TRAIN * R,
+                              "note": "logical FLOPs of forward + backward (each SDF product is issued as 3 fp16 MMAs) over the whole step, "
+                                      "against the measured sustained cuBLAS bf16 peak"},
+                 "what": "BASELINE config #3: ray generation + forward + L1/eikonal loss + backward + Adam on 4096 rays/GPU (the reference's train_iter), is_training=True "
+                         "(jitter, global_step 60000) as NRHintPipeline.train_step: nrh_render_train_forward + nrh_train_loss + nrh_render_backward + nrh_adam_step -- every "
+                         "GEMM (SDF forward-with-tape, second-order backward, reflectance forward / backward, all weight-gradient reductions) on hand-written tcgen05 "
+                         "kernels, gradients written straight into the flat all-reduce buffer, no autograd graph, no library GEMM"
                          + ("; flat-buffer gradient all-reduce" if dist is not None else "")}
         torch.set_grad_enabled(False)
         del opt

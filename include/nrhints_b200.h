@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define NRH_ABI_VERSION 6
+#define NRH_ABI_VERSION 7
 
 #define NRH_OK 0
 #define NRH_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment)         */
@@ -319,6 +319,53 @@ int nrh_colsum_f16(const void* mats, int n_mats, int64_t rows, int width, int64_
 int nrh_color_train_forward(const NrhConfig* cfg, const void* packed, const void* x16, int64_t P, void* acts, float* y, void* stream);
 int nrh_color_train_backward(const NrhConfig* cfg, const void* packed, const float* dy, const float* loss_scale, const void* acts,
                              int64_t P, void* dz, void* dy16, void* dx, void* stream);
+
+/* ---- the fused training step: forward, and ONE backward entry point that writes parameter gradients ----------
+ * What the reference does per step under autograd (pipelines/base_pipeline.py:39-48 -> models/neus_hint_model.py:653-751, then
+ * loss.backward(), trainer/trainer.py:269-283) as two calls on caller-owned memory, tcgen05 engine, no outside NeRF:
+ *
+ *   nrh_render_train_forward  = nrh_render_forward in training mode (samplers on both rays, shadow visibility, depth, specular cue:
+ *       everything the reference keeps under no_grad) with the primary fine pass writing its tape, followed by the differentiable
+ *       tail: reflectance network (tensor cores, activations kept), sigmoid, NeuS alpha / weights / compositing.  `out` receives the
+ *       RenderOutput fields as for nrh_render_forward (rgb, weights from the differentiable tail).
+ *   nrh_render_backward       : d rgb [R,3] (+ optional adjoints of the analytic_normals / normalized_analytic_normals / weights
+ *       outputs) -> gradients of ALL 46 parameter tensors, written straight to the pointers of NrhTrainParams (e.g. views of an
+ *       optimizer's flat gradient buffer: the all-reduce operand), and d origins / d directions / d light positions [R,3] (nullable).
+ *       Chain: compositor backward -> sigmoid -> reflectance backward (tcgen05) -> input scatter -> SDF second-order backward
+ *       (tcgen05) -> all weight-gradient reductions (tcgen05, one launch) -> bias column sums -> weight-norm backward (one launch).
+ *       Loss scales are chosen on the device; the call never synchronises.
+ *
+ * `train_ws` (nrh_train_workspace_bytes) carries the render workspace, the tape and every intermediate from the forward call to the
+ * backward call of the same step; the caller must not touch it in between.  Parameters are given as the module stores them: weight-
+ * normed layers as (v [out,in], g [out,1], bias [out]) -- the library applies W = g v / ||v||_row itself (nrh_pack_weights_wn). */
+typedef struct NrhLayerParams {
+    const float* v; const float* g; const float* bias;     /* parameters (device, fp32, contiguous) */
+    float* d_v; float* d_g; float* d_bias;                 /* gradients, OVERWRITTEN by nrh_render_backward (same shapes) */
+} NrhLayerParams;
+typedef struct NrhTrainParams {
+    NrhLayerParams sdf[8];        /* sdf_network.lin0..7 */
+    NrhLayerParams sdf_out;       /* sdf_network.out_sdf  ([1,256]) */
+    NrhLayerParams feat_out;      /* sdf_network.out_feat ([256,256]) */
+    NrhLayerParams col[5];        /* color_network.lin0..4 */
+    const float* variance; float* d_variance;              /* deviation_network.variance */
+} NrhTrainParams;
+typedef struct NrhTrainAdjoints {
+    const float* d_rgb;                /* [R,3] */
+    const float* d_analytic_normals;   /* [R,S,3] nullable (eikonal loss) */
+    const float* d_normalized_normals; /* [R,S,3] nullable */
+    const float* d_weights;            /* [R,S] nullable */
+    float* d_origins; float* d_directions; float* d_pl_positions;   /* [R,3] each, nullable */
+} NrhTrainAdjoints;
+size_t nrh_train_workspace_bytes(const NrhConfig* cfg, int64_t R);
+/* effective weights from (v, g) for all weight-normed layers in one launch, then nrh_pack_weights; `wn_scratch`: >= 3.4 MB */
+int nrh_pack_weights_wn(const NrhConfig* cfg, const NrhTrainParams* params, void* wn_scratch, size_t wn_scratch_bytes, void* packed,
+                        size_t packed_bytes, void* stream);
+int nrh_render_train_forward(const NrhConfig* cfg, const void* packed, const NrhRays* rays, int64_t R, const float* bg_rgb,
+                             const float* jitter_primary, const float* jitter_shadow, float cos_anneal, int warmup,
+                             const NrhOutputs* out, void* train_ws, size_t train_ws_bytes, void* stream);
+int nrh_render_backward(const NrhConfig* cfg, const void* packed, const NrhTrainParams* params, const NrhRays* rays, int64_t R,
+                        const float* bg_rgb, float cos_anneal, const NrhTrainAdjoints* adj, void* train_ws, size_t train_ws_bytes,
+                        void* stream);
 
 /* Weight-gradient reductions of a training step (the dW = delta^T h products the reference leaves to autograd behind every
  * F.linear: fields/sdf_field.py:106-123, fields/reflectance_network.py:84-96; trainer/trainer.py:279), ALL of them in one call:

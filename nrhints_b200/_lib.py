@@ -18,11 +18,11 @@ _CSRC = Path(__file__).resolve().parent / "csrc"
 # such hooks and reads nothing from the environment.
 DEV_BUILD = os.environ.get("NRH_DEV_LIB", "0") == "1"
 _LIB_PATH = _CSRC / ("libnrhints_b200_dev.so" if DEV_BUILD else "libnrhints_b200.so")
-_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu", "wgrad_tc.cu"]
-_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "color_train_tc.inc", "raygen_math.cuh", "composite_train_math.cuh",
+_SOURCES = ["api.cu", "mlp_simt.cu", "sampler_kernels.cu", "mlp_tc.cu", "hash_encode.cu", "raygen.cu", "train_ops.cu", "wgrad_tc.cu", "train_step.cu"]
+_HEADERS = ["nrh_common.cuh", "ray_math.cuh", "sampler_kernels.cuh", "mlp_tc.cuh", "tc_primitives.cuh", "mlp_tc_bwd.inc", "mlp_tc2.inc", "color_train_tc.inc", "raygen_math.cuh", "composite_train_math.cuh", "train_step.cuh",
             "../../include/nrhints_b200.h"]
 
-NRH_ABI_VERSION = 6
+NRH_ABI_VERSION = 7
 NRH_MAX_ROUGHNESS = 4
 NRH_MAX_OUTSIDE = 64
 NRH_MLP_AUTO, NRH_MLP_FP32_SIMT, NRH_MLP_TCGEN05 = 0, 1, 2
@@ -93,6 +93,20 @@ class NrhWgradJob(C.Structure):
                 ("scale", C.c_float), ("dev_scale", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64)]
 
 
+class NrhLayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("v", "g", "bias", "d_v", "d_g", "d_bias")]
+
+
+class NrhTrainParams(C.Structure):
+    _fields_ = [("sdf", NrhLayerParams * 8), ("sdf_out", NrhLayerParams), ("feat_out", NrhLayerParams), ("col", NrhLayerParams * 5),
+                ("variance", C.c_void_p), ("d_variance", C.c_void_p)]
+
+
+class NrhTrainAdjoints(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_rgb", "d_analytic_normals", "d_normalized_normals", "d_weights", "d_origins",
+                                          "d_directions", "d_pl_positions")]
+
+
 CAM_OPT_MODES = {"off": 0, "SO3xR3": 1, "SE3": 2}
 
 EXPORTS = {
@@ -138,6 +152,13 @@ EXPORTS = {
     "nrh_color_train_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrh_color_train_backward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrh_train_workspace_bytes": (C.c_size_t, [C.POINTER(NrhConfig), C.c_int64]),
+    "nrh_pack_weights_wn": (C.c_int, [C.POINTER(NrhConfig), C.POINTER(NrhTrainParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    "nrh_render_train_forward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.POINTER(NrhRays), C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_float, C.c_int, C.POINTER(NrhOutputs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrh_render_backward": (C.c_int, [C.POINTER(NrhConfig), C.c_void_p, C.POINTER(NrhTrainParams), C.POINTER(NrhRays), C.c_int64,
+                                      C.c_void_p, C.c_float, C.POINTER(NrhTrainAdjoints), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrh_last_launch_count": (C.c_int, []),
 }
 

@@ -44,7 +44,7 @@ constexpr float W_SCALE = TC_W_SCALE;
 constexpr float ACT_SCALE = TC_ACT_SCALE;
 constexpr float G_SCALE = 1024.0f;         // reverse-sweep signals are stored * 2^10
 constexpr float INV_SQRT2 = 0.70710678f;
-constexpr int TC_MAX_JOBS = 192;                     // operand images per weight set (156 today)
+constexpr int TC_MAX_JOBS = 208;                     // operand images per weight set (156 today)
 constexpr int TC_GENERATION_DEFAULT = 1;
 constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed off on its own
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
@@ -82,6 +82,7 @@ struct TcLayout {
     uint32_t col_fwd0n;
     uint32_t col_rev[4];          // [0] unused (see col_rev0)
     uint32_t col_rev0;
+    uint32_t col_rev0p;           // the same for the fused step's operand order [feature 256 | aux 128] (see train_step.cu::k_train_assemble)
     uint32_t total;
 };
 __host__ __device__ inline TcLayout tc_layout() {
@@ -98,6 +99,7 @@ __host__ __device__ inline TcLayout tc_layout() {
     t.col_rev[0] = 0;
     for (int l = 1; l < 4; ++l) { t.col_rev[l] = off; off += 4 * IMG; }
     t.col_rev0 = off; off += 4 * (IMG + IMG / 2);
+    t.col_rev0p = off; off += 4 * (IMG + IMG / 2);
     t.total = off;
     return t;
 }
@@ -1083,6 +1085,7 @@ struct Seg { int dst_k0, src_col0, len, lo; };      // lo: 0 = fp16(x), 1 = the 
 struct ImgJob {
     const float* src; int src_ld;        // element (n, kcol) = src[n*src_ld + kcol]   (tr: src[kcol*src_ld + n])
     int tr;
+    int row_lo, row_hi;                  // the job writes image rows [row_lo, row_hi) only (source row = n - row_lo); default: all
     int nrows_valid;                     // rows beyond are zero
     int nrows_img;                       // 256 or 64
     Seg seg[4]; int nseg;                // k-range mapping inside this 64-wide chunk
@@ -1100,7 +1103,9 @@ __global__ void k_build_images(const __grid_constant__ JobTable Tb) {
     const ImgJob& J = Tb.j[blockIdx.y];
     const int total = J.nrows_img * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int n = i >> 6, k = i & 63;
+        const int nrow = i >> 6, k = i & 63;
+        if (nrow < J.row_lo || nrow >= J.row_hi) continue;
+        const int n = nrow - J.row_lo;
         float v = 0.f;
         int lo = J.lo;
         if (n < J.nrows_valid)
@@ -1112,16 +1117,13 @@ __global__ void k_build_images(const __grid_constant__ JobTable Tb) {
                 }
         const __half h = __float2half_rn(v);
         const __half out = lo ? __float2half_rn(v - __half2float(h)) : h;
-        J.dst[sw128_offset(n, k) >> 1] = out;
+        J.dst[sw128_offset(nrow, k) >> 1] = out;
     }
 }
 
-__global__ void k_scale_copy(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i] * scale;
-}
-
 // jobs are collected on the host and flushed by tc_pack in one launch
-struct JobList { JobTable t; int n; int tr; };       // tr: jobs queued from now on read their source transposed
+struct JobList { JobTable t; int n; int tr; int row_lo, row_hi; };   // tr: jobs queued from now on read their source transposed;
+                                                                       // row_lo / row_hi: ... and write that row range only (0, 0 = all)
 thread_local JobList* g_jobs = nullptr;
 
 int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, const Seg* segs, int nseg, int lo,
@@ -1130,6 +1132,7 @@ int build_image(const float* src, int src_ld, int nrows_valid, int nrows_img, co
     if (!g_jobs || g_jobs->n >= TC_MAX_JOBS) { set_error("image job table overflow"); return NRH_ERR_INVALID; }
     ImgJob& J = g_jobs->t.j[g_jobs->n++];
     J.src = src; J.src_ld = src_ld; J.tr = g_jobs->tr; J.nrows_valid = nrows_valid; J.nrows_img = nrows_img; J.nseg = nseg;
+    J.row_lo = g_jobs->row_lo; J.row_hi = g_jobs->row_hi > 0 ? g_jobs->row_hi : nrows_img;
     for (int i = 0; i < 4; ++i) J.seg[i] = i < nseg ? segs[i] : Seg{0, 0, 0, 0};
     J.lo = lo; J.scale = W_SCALE; J.dst = reinterpret_cast<__half*>(dst);
     return NRH_OK;
@@ -1176,7 +1179,7 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
     const TcLayout T = tc_layout();
     int rc;
     static thread_local JobList jobs;              // 20 KB: kept off the stack
-    jobs.n = 0; jobs.tr = 0;
+    jobs.n = 0; jobs.tr = 0; jobs.row_lo = jobs.row_hi = 0;
     g_jobs = &jobs;
     struct Reset { ~Reset() { g_jobs = nullptr; } } reset_on_exit;
     // forward: B[n = out][k = in] = W native [out][in]
@@ -1221,17 +1224,32 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
         if ((rc = build_image(raw.col_W[0], cin, cin < 256 ? cin : 256, 256, &s, 1, 0, dst, st))) return rc;
         if ((rc = build_image(raw.col_W[0] + 256, cin, cin - 256, 128, &s, 1, 0, dst + IMG, st))) return rc;
     }
+    // the same in the fused step's operand order: rows 0..255 = the 256 feature inputs (natural columns 60..315); the [128 x 64] image =
+    // aux rows [pts, PE(view), normal, PE(light)] (natural 0..59) | PE(vis) at 60 (natural 316..) | PE(spec) at 69 | zero
+    {
+        const int spec0 = 316 + (cfg.shadow_hint ? 9 : 0);
+        for (int c = 0; c < 4; ++c) {
+            Seg s{0, c * 64, 64};
+            uint8_t* dst = tcb + T.col_rev0p + (size_t)c * (IMG + IMG / 2);
+            if ((rc = build_image(raw.col_W[0] + 60, cin, 256, 256, &s, 1, 0, dst, st))) return rc;
+            jobs.row_lo = 0; jobs.row_hi = 60;
+            if ((rc = build_image(raw.col_W[0], cin, 60, 128, &s, 1, 0, dst + IMG, st))) return rc;
+            jobs.row_lo = 60; jobs.row_hi = 69;
+            if ((rc = build_image(raw.col_W[0] + 316, cin, cfg.shadow_hint ? 9 : 0, 128, &s, 1, 0, dst + IMG, st))) return rc;
+            jobs.row_lo = 69; jobs.row_hi = 128;
+            if ((rc = build_image(raw.col_W[0] + spec0, cin, cfg.specular_hint ? 9 * cfg.n_roughness : 0, 128, &s, 1, 0, dst + IMG, st))) return rc;
+            jobs.row_lo = jobs.row_hi = 0;
+        }
+    }
     jobs.tr = 0;
     if ((rc = flush_image_jobs(st))) return rc;
     // biases pre-multiplied by ACT_SCALE (the forward epilogues work in x16 units)
     for (int l = 0; l < SDF_LAYERS; ++l) {
         const int out = (l == SDF_SKIP - 1) ? SKIP_H : 256;
-        k_scale_copy<<<1, 256, 0, st>>>(raw.sdf_b[l], reinterpret_cast<float*>(tcb + T.sdf_bias16) + l * 256, out, ACT_SCALE);
-        NRH_LAUNCH_CHECK();
+        if ((rc = queue_scaled_copy(raw.sdf_b[l], reinterpret_cast<float*>(tcb + T.sdf_bias16) + l * 256, out, ACT_SCALE, st))) return rc;
     }
     for (int l = 0; l < 4; ++l) {
-        k_scale_copy<<<1, 256, 0, st>>>(raw.col_b[l], reinterpret_cast<float*>(tcb + T.col_bias16) + l * 256, 256, ACT_SCALE);
-        NRH_LAUNCH_CHECK();
+        if ((rc = queue_scaled_copy(raw.col_b[l], reinterpret_cast<float*>(tcb + T.col_bias16) + l * 256, 256, ACT_SCALE, st))) return rc;
     }
     return NRH_OK;
 }
@@ -1336,7 +1354,8 @@ int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float*
 
 int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
                           const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
-                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st) {
+                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st,
+                          const SdfBwdFeat16* feat16, const Strided3* pts_strided) {
     if (N <= 0) return NRH_OK;
     const float* Pf = reinterpret_cast<const float*>(packed);
     const SdfTrainLayout TL = sdf_train_layout(N, num_sms);
@@ -1347,6 +1366,8 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
     P.scale = scale;
     P.tape_tiles = reinterpret_cast<const uint8_t*>(tape) + TL.tape_tiles_off;
     P.d_sdf = d_sdf; P.d_feat = d_feat; P.d_grad = d_grad;
+    P.d_feat16 = nullptr; P.d_feat16_ld = 0; P.d_feat16_mul = nullptr;
+    if (feat16) { P.d_feat = nullptr; P.d_feat16 = reinterpret_cast<const __half*>(feat16->rows); P.d_feat16_ld = feat16->ld; P.d_feat16_mul = feat16->mul; }
     uint8_t* ob = reinterpret_cast<uint8_t*>(bwd_out);
     P.gb0 = reinterpret_cast<__half*>(ob + TL.bwd_gb0_off);
     P.gb = reinterpret_cast<__half*>(ob + TL.bwd_gb_off);
@@ -1356,6 +1377,7 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     Strided3 S3{pts, pts + 1, pts + 2, 3};
+    if (pts_strided) S3 = *pts_strided;
     NRH_CUDA_CHECK(cudaFuncSetAttribute(sdf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDF_SMEM));
     sdf_bwd_tc_kernel<<<grid, NTHREADS, SDF_SMEM, st>>>(P, S3, N, scratch);
     NRH_LAUNCH_CHECK();
@@ -1363,14 +1385,14 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
 }
 
 int color_train_forward_tc(const void* packed, const PackedLayout& L, const void* x16, int64_t P, void* acts, float* y, int num_sms,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool permuted) {
     if (P <= 0) return NRH_OK;
     const float* Pf = reinterpret_cast<const float*>(packed);
     ColTrainParams A{};
     A.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     A.bias16 = reinterpret_cast<const float*>(A.tc + tc_layout().col_bias16);
     A.w4t = Pf + L.col_w4t; A.b4 = Pf + L.col_b4;
-    A.acts = reinterpret_cast<__half*>(acts); A.y = y; A.P = P;
+    A.acts = reinterpret_cast<__half*>(acts); A.y = y; A.P = P; A.permuted = permuted ? 1 : 0;
     alignas(64) CUtensorMap xmap;
     int rc;
     if ((rc = encode_tensor_map_f16(&xmap, x16, 384, P, 64, TM))) return rc;      // boxes of [128 points x 64 columns]: one K-major operand chunk
@@ -1383,7 +1405,7 @@ int color_train_forward_tc(const void* packed, const PackedLayout& L, const void
 }
 
 int color_train_backward_tc(const void* packed, const PackedLayout& L, const float* dy, const float* scale, const void* acts, int64_t P,
-                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st) {
+                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st, bool permuted) {
     if (P <= 0) return NRH_OK;
     const float* Pf = reinterpret_cast<const float*>(packed);
     ColTrainParams A{};
@@ -1392,6 +1414,7 @@ int color_train_backward_tc(const void* packed, const PackedLayout& L, const flo
     A.acts = const_cast<__half*>(reinterpret_cast<const __half*>(acts));
     A.dy = dy; A.scale = scale;
     A.dz = reinterpret_cast<__half*>(dz); A.dy16 = reinterpret_cast<__half*>(dy16); A.dx = reinterpret_cast<__half*>(dx); A.P = P;
+    A.permuted = permuted ? 1 : 0;
     const int64_t ntiles = (P + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     NRH_CUDA_CHECK(cudaFuncSetAttribute(color_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLT_SMEM));

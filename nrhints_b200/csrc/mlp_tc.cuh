@@ -50,17 +50,21 @@ int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float*
 int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf, float* gx, float* gy,
                                  float* gz, int64_t gstride, float* feat, void* tape, float* scratch, size_t scratch_bytes, int num_sms,
                                  cudaStream_t st);
+// feat16 (fused training step): d_feat as fp16 rows [N][ld] already in units of another power-of-two loss scale, *mul converts to S;
+// pts_strided: the points as strided coordinate arrays instead of [N][3]
+struct SdfBwdFeat16 { const void* rows; int64_t ld; const float* mul; };
 int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float* pts, int64_t N, const void* tape,
                           const float* d_sdf, const float* d_feat, const float* d_grad, const float* scale, void* bwd_out,
-                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st);
+                          float* d_pts, float* scratch, size_t scratch_bytes, int num_sms, cudaStream_t st,
+                          const SdfBwdFeat16* feat16 = nullptr, const Strided3* pts_strided = nullptr);
 
 // ---- training: reflectance network forward (with activation dumps) and backward (color_train_tc.inc) ------------------------------
 // x16: [P][384] fp16 input in the reference's concatenation order (361 valid columns, rest zero); acts: [4][P][256] fp16 a_1..a_4
 // (x TC_ACT_SCALE); y: [P][4] fp32 pre-sigmoid outputs.  Backward: dy [P][3] fp32, *scale = power-of-two loss scale S;
 // dz: [4][P][256] fp16 dz_0..dz_3, dy16: [P][8] fp16, dx: [P][384] fp16 -- all in S units.
 int color_train_forward_tc(const void* packed, const PackedLayout& L, const void* x16, int64_t P, void* acts, float* y, int num_sms,
-                           cudaStream_t st);
+                           cudaStream_t st, bool permuted = false);
 int color_train_backward_tc(const void* packed, const PackedLayout& L, const float* dy, const float* scale, const void* acts, int64_t P,
-                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st);
+                            void* dz, void* dy16, void* dx, int num_sms, cudaStream_t st, bool permuted = false);
 
 }  // namespace nrh

@@ -72,6 +72,8 @@ struct Strided3 {                    // three coordinate arrays with a common el
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// api.cu: small fp32 copy queued into the one re-layout launch of the running nrh_pack_weights call
+int queue_scaled_copy(const float* src, float* dst, int n, float scale, cudaStream_t st);
 
 #define NRH_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \

@@ -14,6 +14,7 @@ from torch import nn
 from .config import NeuSModelConfig
 from .ray_generator import CameraModel, RayGenerator, RayGeneratorConfig
 from .renderer import NeuSHintRenderer, RenderOutput
+from . import fused_step
 from .train_ops import FlatAdam, train_loss_dict
 
 
@@ -46,6 +47,37 @@ class NRHintPipeline(nn.Module):
     def make_optimizer(self) -> FlatAdam:
         """trainer/trainer.py:99 with flat buffers (one Adam launch per parameter group; empty groups are skipped)."""
         return FlatAdam([g for g in self.get_param_groups() if len(g["params"]) > 0])
+
+    def train_step(self, pixel_bundle, global_step: int = 0, optimizer: Optional[torch.optim.Optimizer] = None,
+                   grad_sync=None) -> Dict[str, torch.Tensor]:
+        """The reference's train_iter (trainer/trainer.py:269-283: forward, get_train_loss_dict, zero_grad, backward, step) without an
+        autograd graph: ray generation -> nrh_render_train_forward -> nrh_train_loss -> nrh_render_backward, the gradients of the
+        renderer's parameters written straight into their `.grad` tensors (with FlatAdam: views of the flat gradient buffer, i.e. the
+        all-reduce operand), the adjoints of the rays handed to the ray generator's backward when it has parameters to optimise.
+        `grad_sync`: optional callable run between backward and the optimizer step (grad_sync.allreduce_flat); its return value is
+        passed to FlatAdam.step as grad_scale.  Returns the loss dict of get_train_loss_dict (0-d device tensors, no host sync)."""
+        if getattr(self, "_fused", None) is None or self._fused.renderer is not self.renderer:
+            self._fused = fused_step.FusedTrainStep(self.renderer)
+        need_ray = any(p.requires_grad for p in self.ray_generator.parameters())
+        if optimizer is not None:
+            optimizer.zero_grad()
+        with torch.set_grad_enabled(need_ray):
+            rays = self.ray_generator(pixel_bundle)
+        det = lambda t: t.detach().to(torch.float32).contiguous()      # noqa: E731
+        res = self._fused.forward_backward(det(rays.origins), det(rays.directions), det(rays.pl_positions), det(rays.nears),
+                                           det(rays.fars), det(pixel_bundle.rgb_gt), self._background(pixel_bundle.pls.device),
+                                           global_step, self.model_config.igr_weight, need_ray_grads=need_ray)
+        if need_ray:
+            torch.autograd.backward([rays.origins, rays.directions, rays.pl_positions],
+                                    [res["d_origins"], res["d_directions"], res["d_pl_positions"]])
+        if optimizer is not None:
+            scale = grad_sync() if grad_sync is not None else None
+            if scale is not None:
+                optimizer.step(grad_scale=scale)
+            else:
+                optimizer.step()
+        st = res["stats"]
+        return {"loss": st[0], "rgb_loss": st[1], "eikonal_loss": st[2], "s_val": res["s_val"], "psnr": st[3]}
 
     @torch.enable_grad()
     def register_view(self, pixel_bundles: Iterator, steps: int = 500, optimizer: Optional[torch.optim.Optimizer] = None):

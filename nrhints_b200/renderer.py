@@ -29,6 +29,7 @@ from torch import nn
 
 from . import _lib
 from . import autograd_fine
+from . import fused_step
 from . import sdf_autograd
 from .config import (DepthComputationType, NeRFConfig, NeuSModelConfig, NormalComputationType, ReflectanceNetConfig,
                      SDFNetConfig)
@@ -334,6 +335,9 @@ class NeuSHintRenderer(nn.Module):
         self._packed_key = None
         self._workspace = None
         self.last_launch_count = 0
+        # gradients through ONE fused autograd node (fused_step.py) when the configuration allows it; False keeps the composed
+        # autograd path (autograd_fine.py / sdf_autograd.py), which the parity tests use as a second implementation
+        self.fused_training = True
 
     # -- C-ABI plumbing ---------------------------------------------------------------------------
     def _c_config(self) -> _lib.NrhConfig:
@@ -381,6 +385,12 @@ class NeuSHintRenderer(nn.Module):
             return self._packed
         lib = _lib.load()
         cfg = self._c_config()
+        if fused_step.can_pack_wn(self) and all(p.device == device and p.dtype == torch.float32 and p.is_contiguous()
+                                                for p in self.parameters()):
+            # weight norm of all layers + the operand images by the library itself (nrh_pack_weights_wn): 4 launches instead of ~90
+            fused_step.pack_weights_wn(self, device)
+            self._packed_key = key
+            return self._packed
         with torch.no_grad():
             ws = [w.detach().to(device=device, dtype=torch.float32).contiguous() for w in self._weight_tensors()]
         raw = _lib.NrhRawWeights()
@@ -599,6 +609,20 @@ class NeuSHintRenderer(nn.Module):
                 jit_o = torch.rand([R, r.n_outside_samples], device=device)
             if self.has_shadow_hint and not warmup and r.shadow_hint:
                 jit_s = torch.rand([R, r.n_shadow_samples], device=device)
+
+        if needs_grad and R > 0 and not return_extras and self.fused_training and fused_step.eligible(self):
+            # the whole differentiable step as ONE autograd node on two library calls (nrh_render_train_forward / nrh_render_backward)
+            side = dict(near=near, far=far, bg=bg, jit_p=jit_p, jit_s=jit_s, cos_anneal=cos_anneal, warmup=warmup)
+            rgb, w, an, nn_ = fused_step.FusedRender.apply(self, side, rays_o, ray_bundle.directions, ray_bundle.pl_positions,
+                                                           *fused_step.param_list(self))
+            fo = side["out"]
+            inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6).to(device)
+            return RenderOutput(
+                rgb=rgb, depth=fo["depth"], weights=w, s_val=(1.0 / inv_s).reshape(1, 1).expand(R, S),
+                inside_sphere=fo["inside_sphere"], relax_inside_sphere=fo["inside_sphere"], analytic_normals=an,
+                normalized_analytic_normals=nn_, visibilities=fo["visibilities"] if self.has_shadow_hint else None,
+                specular_cue=fo["specular_cue"] if self.has_specular_hint else None, z_vals=fo["z_vals"], z_shadow=None,
+                sampled_color=None)
 
         out = dict(
             rgb=torch.empty(R, 3, **f32), depth=torch.empty(R, 1, **f32), weights=torch.empty(R, St, **f32),

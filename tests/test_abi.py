@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_version_and_config_validation_without_gpu():
     lib = _lib.load()
-    assert lib.nrh_version() == _lib.NRH_ABI_VERSION == 6
+    assert lib.nrh_version() == _lib.NRH_ABI_VERSION == 7
     import nrhints_b200 as nb
     m = nb.NeuSHintRenderer(nb.NeuSModelConfig())
     cfg = m._c_config()

@@ -13,9 +13,12 @@ IMPLS = ["fp32", "auto"]
 
 
 def build_module(case, impl):
+    """impl "auto-composed": the tcgen05 engine with gradients through the composed autograd nodes (autograd_fine.py /
+    sdf_autograd.py) instead of the single fused node (fused_step.py, the default): two implementations of the same step."""
     cfg = T.make_config(case)
     sd = T.make_state(case["weights"], cfg)
-    m = nb.NeuSHintRenderer(cfg, mlp_impl=impl)
+    m = nb.NeuSHintRenderer(cfg, mlp_impl="auto" if impl == "auto-composed" else impl)
+    m.fused_training = impl != "auto-composed"
     m.load_state_dict(sd)
     return m.cuda(), cfg, sd
 
@@ -193,6 +196,7 @@ VERBOSE_GRADS = False
 
 def _grad_group(pname, impl):
     """Tensors whose gradient passes through the reflectance MLP's fp16 backward (tcgen05 engine) carry its noise."""
+    impl = "auto" if impl == "auto-composed" else impl
     if impl != "fp32" and (pname.startswith("color_network.") or pname.startswith("sdf_network.out_feat") or pname == "ray::pl_positions"):
         return "auto_color"
     return impl
@@ -223,7 +227,7 @@ def test_full_size_sharp_all_fields_match_oracle():
     print("FULLSHARP", {k: f"{v:.2e}" for k, v in stats.items()})
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + ["auto-composed"])
 @pytest.mark.parametrize("name", list(T.GRAD_CASES))
 def test_training_gradients_match_oracle(name, impl):
     """Training-mode forward + loss.backward() through the CUDA path (fused SDF forward-with-tape / second-order backward, CUDA
