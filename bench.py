@@ -60,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -79,7 +79,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, pw, mx, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             f = [x.strip() for x in s.split(",")]
@@ -89,11 +89,16 @@ class ClockSampler:
                 sm.append(float(f[0])); mx = float(f[1])
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        sm.sort(); pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": sm[0] if sm else None, "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None}
 
 
 def workload_config(R: int, world: int, scaling: str = "weak") -> dict:
@@ -416,6 +421,26 @@ def main():
                                "hbm_algorithmic_gbs": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9,
                                "frac_of_hbm_peak": BYTES_PER_RAY * R / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
 
+    # ---- sustained clocks / board power under this workload: the forward looped for ~2.5 s while nvidia-smi samples every 20 ms.
+    # The tcgen05 kernels run into the board's power cap (sw_power_cap): the SM clock settles well below its maximum, so the step
+    # time is set by energy per point, not by issue slots.  Reported, never used for `value`.
+    sustained = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sp = ClockSampler(local_rank)
+        sp.start()
+        t_end, n_it = time.perf_counter() + 2.5, 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        while time.perf_counter() < t_end:
+            for _ in range(10):
+                step()
+            n_it += 10
+            torch.cuda.synchronize()
+        b.record(); torch.cuda.synchronize()
+        sustained = sp.stop()
+        sustained["ms_per_step_back_to_back"] = a.elapsed_time(b) / n_it
+        sustained["what"] = "forward steps back to back for 2.5 s (no L2 flush in between), nvidia-smi every 20 ms"
+
     # ---- BASELINE.json config #3: one training step (forward + loss + backward + Adam) on the same 4096 rays ---------
     train = None
     if not args.no_train:
@@ -555,7 +580,7 @@ def main():
             "data": "synthetic", "config": workload_config(R, world), "engine": engine,
             "e2e": {"value": world * R / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "pinned host RayBundle -> device, forward, full RenderOutput -> pinned host buffers (pipelines/base_pipeline.py:114-120 pattern)"},
-            "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity_vs_reference": parity,
+            "gpu_launches": launches_per_step * K, "clocks": clocks, "clocks_sustained": sustained, "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "parity_vs_reference": parity,
             "train_step": train, "strong_scaling": strong,
             "wall_s_timed_region": wall,
         }
@@ -567,7 +592,9 @@ def main():
 def _ncu_traffic(engine):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
     (profiles/r1x_traffic.json, written from profiles/r1x_tc_fine_kernel_ncu.txt); None if there is no capture for this engine."""
-    p = ROOT / "profiles" / "r1x_traffic.json"
+    p = ROOT / "profiles" / "r2d_traffic.json"
+    if not p.exists():
+        p = ROOT / "profiles" / "r1x_traffic.json"
     if not p.exists():
         return None
     d = json.loads(p.read_text()).get(engine)
