@@ -455,7 +455,8 @@ def main():
         pipe.renderer = model
         pipe = pipe.to(dev)
         pixels = SimpleNamespace(**{k: v.to(dev) for k, v in vars(pb).items()})
-        opt = pipe.make_optimizer()                              # parameters / gradients / moments re-homed into flat buffers
+        opt = pipe.make_optimizer(capturable=True)               # parameters / gradients / moments re-homed into flat buffers; step count
+                                                                 # and learning rate on the device so that the step can live in a CUDA graph
 
         sync = (lambda: allreduce_flat(opt.flat_grads())) if dist is not None else None
 
@@ -493,6 +494,12 @@ def main():
         t_ms = time_train(train_step, tsteps)
         train_launches = int(model.last_launch_count + getattr(model, "last_backward_launch_count", 0))
         t_auto_ms = time_train(train_step_autograd, tsteps)
+        t_graph_ms = None
+        try:                                                   # the whole step (weight pack ... Adam, all-reduce included) as ONE CUDA graph
+            graphed = pipe.capture_train_step(pixels, opt, grad_sync=sync, global_step=60000)
+            t_graph_ms = time_train(lambda: graphed(pixels, 60000), tsteps)
+        except Exception as e:                                 # capture is an optimisation, never a requirement
+            print("CUDA graph capture of the training step failed:", repr(e), file=sys.stderr)
         ar_ms = None
         if dist is not None:                                   # the step's one collective, timed alone on the compute stream
             for _ in range(3):
@@ -507,8 +514,9 @@ def main():
             dist.all_reduce(ar, op=dist.ReduceOp.MAX)
             ar_ms = float(ar.item())
         tf = FLOP_PER_RAY_TRAIN * R / (t_ms * 1e-3) / 1e12
+        peaks = measured_peaks()
         train = {"value": world * R / (t_ms * 1e-3), "unit": "rays/s", "ms_per_step": t_ms, "steps": tsteps,
-                 "ms_per_step_through_autograd_node": t_auto_ms,
+                 "ms_per_step_through_autograd_node": t_auto_ms, "ms_per_step_cuda_graph": t_graph_ms,
                  "library_launches_forward_plus_backward": train_launches,
                  "allreduce_ms": ar_ms, "allreduce_bytes": sum(g.numel() * 4 for g in opt.flat_grads()),
                  "allreduce_share_of_step": (ar_ms / t_ms if ar_ms else None),
@@ -565,6 +573,36 @@ def main():
         strong = {"scaling": "strong", "global_rays": R, "rays_per_gpu": Rs, "value": R / (best * 1e-3), "unit": "rays/s",
                   "ms_per_step": best, "ms_per_step_eager": eager_ms, "ms_per_step_cuda_graph": graph_ms,
                   "what": "the same 4096-ray batch split over the ranks (no collective in the forward)"}
+        if not args.no_train:
+            # the training step the way the reference shards it (trainer/trainer.py:118: batch_size // world_size rays per rank), gradient
+            # all-reduce on the flat buffer included, eager and as one CUDA graph per rank
+            try:
+                torch.set_grad_enabled(True)
+                from types import SimpleNamespace
+                from nrhints_b200.grad_sync import allreduce_flat
+                from nrhints_b200.workload import synthetic_pixel_bundle
+                pb_s, cam_s = synthetic_pixel_bundle(R, seed=3407)
+                px_s = SimpleNamespace(**{k: (v[rank * Rs:(rank + 1) * Rs].to(dev) if isinstance(v, torch.Tensor) and v.shape[:1] == (R,) else v)
+                                          for k, v in vars(pb_s).items()})
+                pipe_s = nb.NRHintPipeline(cfg, nb.RayGeneratorConfig(), nb.CameraModel(**cam_s), 64, mlp_impl=args.mlp)
+                pipe_s.renderer = model
+                pipe_s = pipe_s.to(dev)
+                opt_s = pipe_s.make_optimizer(capturable=True)
+                sync_s = lambda: allreduce_flat(opt_s.flat_grads())      # noqa: E731
+                t_eager = time_steps(lambda: pipe_s.train_step(px_s, global_step=60000, optimizer=opt_s, grad_sync=sync_s))
+                t_graph = None
+                try:
+                    gs = pipe_s.capture_train_step(px_s, opt_s, grad_sync=sync_s, global_step=60000)
+                    t_graph = time_steps(lambda: gs(px_s, 60000))
+                except Exception as e:
+                    print("CUDA graph capture of the sharded training step failed:", repr(e), file=sys.stderr)
+                tb = min(x for x in (t_eager, t_graph) if x is not None)
+                strong["train_step"] = {"value": R / (tb * 1e-3), "unit": "rays/s", "ms_per_step": tb, "ms_per_step_eager": t_eager,
+                                        "ms_per_step_cuda_graph": t_graph, "rays_per_gpu": Rs,
+                                        "what": "config #3 with the reference's batch split: 4096 rays per step in total, gradient all-reduce on the flat buffer inside the step"}
+                torch.set_grad_enabled(False)
+            except Exception as e:
+                print("strong-scaling training step failed:", repr(e), file=sys.stderr)
 
     cpu = gpu_base = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -586,7 +624,12 @@ def main():
         }
         _emit(line)
     if dist is not None:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down object by object: every rank has printed / finished, a last barrier lines them up, and the
+        # process exits at once (communicator destructors racing CUDA-graph and allocator teardown can stall for minutes)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def _ncu_traffic(engine):

@@ -303,6 +303,12 @@ int nrh_train_loss(const float* rgb, const float* rgb_gt, const float* analytic_
 int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, int64_t step, float grad_scale, void* stream);
 
+/* The same step with the step count and the learning rate on the DEVICE, for callers that capture the training step in a CUDA graph
+ * (a replay must see a new step count / scheduler value): *step_dev (int64) is incremented by the call, *lr_dev (fp32) is read at
+ * execution time, coef_scratch = 2 floats of device scratch owned by the caller.  Same arithmetic (bias corrections in double). */
+int nrh_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev, double beta1,
+                      double beta2, double eps, int64_t* step_dev, float* coef_scratch, float grad_scale, void* stream);
+
 /* Column sums of n_mats row-major fp16 matrices [rows][width] (consecutive matrices `mat_stride` elements apart) -> fp32
  * out [n_mats][width] = scale * sum over rows: the bias gradients of a training step are such point-reductions over the fp16
  * adjoint dumps (db_l = sum_p zb_l / S above).  width: multiple of 8 with 256 % (width / 8) == 0; matrices 16-byte aligned. */

@@ -142,6 +142,8 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrh_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_float, C.c_void_p]),
+    "nrh_adam_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_double,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "nrh_colsum_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "nrh_composite_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,20 +1,24 @@
-"""Differentiable fine pass (training / camera registration) -- interim autograd backend.
+"""Differentiable fine pass as COMPOSED autograd nodes -- the second implementation of the training step.
 
-The CUDA library implements the forward of the whole hot path.  Its backward (recompute-in-backward with the
-second-order terms of the analytic normals) is the next milestone; until it lands, a call that needs
-gradients is split exactly where the reference puts its `torch.no_grad()` fences:
+The default route for a call that needs gradients is ONE autograd node on two library calls (fused_step.py:
+nrh_render_train_forward / nrh_render_backward).  This module is the composed route the renderer takes when that node does not
+apply (fp32 engine, `n_importance == 0`, layers without weight norm, `renderer.fused_training = False`) and the one the parity
+tests hold against the fused node: the call is split exactly where the reference puts its `torch.no_grad()` fences:
 
   * everything the reference computes WITHOUT gradients -- the hierarchical sampler on both rays (7 + 6 SDF
     passes), the shadow visibility, depth / hit point and the specular cue
     (/root/reference/models/neus_hint_model.py:697-713, :379, :531-533, :589) -- runs in the CUDA kernels;
   * the differentiable remainder -- SDF + feature at the 128 section mid-points, d sdf/dx with create_graph
     (fields/sdf_field.py:136-148), NeuS alpha, weights, reflectance MLP, compositing (:504-525, :583-637) --
-    is expressed here with torch ops on the same device, so autograd produces the reference's gradients
-    (parameters, ray origins / directions / light positions; near / far only when n_importance == 0, because the
-    reference's up-sampling block re-assigns z_vals under no_grad, :696-713).
+    is a handful of autograd nodes with hand-written CUDA forwards AND backwards on the tcgen05 engine (sdf_autograd._SdfFine,
+    _ReflectanceF16 on nrh_color_train_forward / _backward + nrh_wgrad_f16, _CompositeTrain) glued by torch ops, or plain torch
+    expressions of the same functions on the fp32 engine, so autograd produces the reference's gradients (parameters, ray origins /
+    directions / light positions; near / far only when n_importance == 0, because the reference's up-sampling block re-assigns
+    z_vals under no_grad, :696-713).
 
-This module only uses torch; it never touches the oracle and never runs on the CPU in the product path
-(the renderer rejects CPU tensors).  The CPU test-suite exercises it against the oracle.
+This module only uses torch and the CUDA library; it never touches the oracle and never runs on the CPU in the product path
+(the renderer rejects CPU tensors).  The CPU test-suite exercises its chain rule against the oracle with library calls replaced
+by fp32 stand-ins.
 """
 from __future__ import annotations
 

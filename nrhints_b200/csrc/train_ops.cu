@@ -102,6 +102,30 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     }
 }
 
+// The same step with its scalars on the device (CUDA-graph capturable: a replay must see a new step count and learning rate):
+// k_adam_prepare advances *step and derives the two step-dependent factors in double, k_adam_dev reads them.
+__global__ void k_adam_prepare(long long* __restrict__ step, const float* __restrict__ lr, double beta1, double beta2, float* __restrict__ coef) {
+    const long long t = *step + 1;
+    *step = t;
+    const double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
+    coef[0] = (float)(-((double)lr[0] / bc1));      // -step_size
+    coef[1] = (float)sqrt(bc2);                      // sqrt(bias_correction2)
+}
+__global__ void __launch_bounds__(TL_THREADS)
+k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+           float w1, float beta2, float w2, float eps, const float* __restrict__ coef, float grad_scale) {
+    const float neg_step_size = __ldg(coef), bc2_sqrt = __ldg(coef + 1);
+    const int64_t stride = (int64_t)gridDim.x * TL_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * TL_THREADS + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        const float mi = __fmaf_rn(w1, gi - m[i], m[i]);
+        const float vi = __fmaf_rn(w2 * gi, gi, v[i] * beta2);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        m[i] = mi; v[i] = vi;
+        p[i] = __fmaf_rn(neg_step_size, mi / denom, p[i]);
+    }
+}
+
 // column sums of `n_mats` row-major fp16 matrices [rows][width] -> fp32 [n_mats][width] (bias gradients = point-reductions over
 // the fp16 adjoint dumps).  One pass at HBM speed: a thread owns 8 consecutive columns (one 16-byte load per row), a CTA walks a
 // contiguous slab of rows, partial sums meet in shared memory and leave as one atomicAdd per column and CTA.
@@ -224,6 +248,19 @@ int nrh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
     k_adam<<<grid_for(n), TL_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
                                                                   (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-step_size),
                                                                   grad_scale);
+    NRH_LAUNCH_CHECK();
+    return NRH_OK;
+}
+
+int nrh_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev, double beta1,
+                      double beta2, double eps, int64_t* step_dev, float* coef_scratch, float grad_scale, void* stream) {
+    if (n == 0) return NRH_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !coef_scratch || n < 0) { set_error("nrh_adam_step_dev: null argument"); return NRH_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_adam_prepare<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_dev), lr_dev, beta1, beta2, coef_scratch);
+    NRH_LAUNCH_CHECK();
+    k_adam_dev<<<grid_for(n), TL_THREADS, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                   (float)eps, coef_scratch, grad_scale);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

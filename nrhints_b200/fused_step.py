@@ -206,6 +206,8 @@ class FusedTrainStep:
         cos_anneal = min(1.0, global_step / rn.config.anneal_end) if rn.config.anneal_end > 0 else 1.0
         jit_p = torch.rand([R, 1], device=dev)                                     # RNG order of the reference (:682, :394)
         jit_s = torch.rand([R, r.n_shadow_samples], device=dev) if (rn.has_shadow_hint and not warmup and r.shadow_hint) else None
+        if torch.cuda.is_current_stream_capturing():
+            rn._packed_key = None                     # a captured step must always carry its own weight pack
         packed = rn._ensure_packed(dev)
         need = lib.nrh_train_workspace_bytes(C.byref(cfg), R)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:

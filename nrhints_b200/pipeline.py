@@ -44,9 +44,16 @@ class NRHintPipeline(nn.Module):
         """base_pipeline.py:50-69; the values are 0-d device tensors (no host sync)."""
         return train_loss_dict(rendering_res, pixel_bundle.rgb_gt, self.model_config.igr_weight)
 
-    def make_optimizer(self) -> FlatAdam:
-        """trainer/trainer.py:99 with flat buffers (one Adam launch per parameter group; empty groups are skipped)."""
-        return FlatAdam([g for g in self.get_param_groups() if len(g["params"]) > 0])
+    def make_optimizer(self, capturable: bool = False) -> FlatAdam:
+        """trainer/trainer.py:99 with flat buffers (one Adam launch per parameter group; empty groups are skipped).
+        capturable=True: step count / learning rate on the device, for `capture_train_step`."""
+        return FlatAdam([g for g in self.get_param_groups() if len(g["params"]) > 0], capturable=capturable)
+
+    def capture_train_step(self, pixel_bundle, optimizer: FlatAdam, grad_sync=None, global_step: int = 0) -> "GraphedTrainStep":
+        """`train_step` (ray generation -> forward -> loss -> backward -> [gradient all-reduce] -> Adam) captured ONCE as a CUDA graph and
+        replayed per step: at the reference's data-parallel batch split (trainer/trainer.py:118: batch_size // world_size rays per
+        rank) the ~75 launches of a step are launch-latency bound otherwise.  The optimizer must be FlatAdam(capturable=True)."""
+        return GraphedTrainStep(self, pixel_bundle, optimizer, grad_sync, global_step)
 
     def train_step(self, pixel_bundle, global_step: int = 0, optimizer: Optional[torch.optim.Optimizer] = None,
                    grad_sync=None) -> Dict[str, torch.Tensor]:
@@ -102,3 +109,67 @@ class NRHintPipeline(nn.Module):
             for p, flag in frozen:
                 p.requires_grad_(flag)
         return torch.stack(losses) if losses else torch.empty(0)
+
+
+class GraphedTrainStep:
+    """A captured NRHintPipeline.train_step.  Calling it copies the pixel bundle into the static input buffers, pushes the current
+    learning rates to the device and replays the graph.  Without a gradient exchange the graph holds the whole step (weight pack, ray
+    generation, forward, loss, backward, Adam with its step count on the device); with `grad_sync` (data parallel) it ends after the
+    backward and the collective + Adam launches follow eagerly on the same stream -- three launches, and no NCCL kernel inside a graph.
+    The graph bakes the two host scalars of a step that depend on `global_step` -- cos_anneal = min(1, step / anneal_end) and the
+    geometry warm-up flag -- so it is re-captured when they change and the step runs eagerly while cos_anneal still moves
+    (global_step < anneal_end)."""
+
+    def __init__(self, pipe: NRHintPipeline, pixel_bundle, optimizer: FlatAdam, grad_sync, global_step: int):
+        if grad_sync is None and not getattr(optimizer, "capturable", False):
+            raise ValueError("capture_train_step needs FlatAdam(capturable=True) (make_optimizer(capturable=True))")
+        self.pipe, self.opt, self.grad_sync = pipe, optimizer, grad_sync
+        self.fields = [k for k, v in vars(pixel_bundle).items() if isinstance(v, torch.Tensor)]
+        self.static = type(pixel_bundle)(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in vars(pixel_bundle).items()})
+        self.graph, self.key, self.out = None, None, None
+        self.first = self._capture(global_step)            # loss dict of the step taken while capturing
+
+    def _key(self, global_step: int):
+        m = self.pipe.model_config
+        cos = min(1.0, global_step / m.anneal_end) if m.anneal_end > 0 else 1.0
+        return (cos, bool(global_step < m.geometry_warmup_end))
+
+    def _finish(self):
+        """data-parallel tail of a step: the one collective of the loop and the optimizer launch(es), eager."""
+        if self.grad_sync is not None:
+            scale = self.grad_sync()
+            self.opt.step(grad_scale=scale) if scale is not None else self.opt.step()
+
+    def _capture(self, global_step: int):
+        dev = self.static.poses.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # one REAL step outside the capture (lazy allocations, library loading)
+            res = self.pipe.train_step(self.static, global_step=global_step, optimizer=self.opt, grad_sync=self.grad_sync)
+            res = {k: v.clone() for k, v in res.items()}
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):                 # nothing executes here: the launches are recorded
+            if self.grad_sync is None:
+                self.out = self.pipe.train_step(self.static, global_step=global_step, optimizer=self.opt)
+            else:
+                self.opt.zero_grad()
+                self.out = self.pipe.train_step(self.static, global_step=global_step, optimizer=None)
+        self.key = self._key(global_step)
+        return res
+
+    def __call__(self, pixel_bundle, global_step: int):
+        for k in self.fields:
+            getattr(self.static, k).copy_(getattr(pixel_bundle, k), non_blocking=True)
+        key = self._key(global_step)
+        if key != self.key:
+            if key[0] < 1.0:                               # still annealing: a new scalar every step -> eager
+                return self.pipe.train_step(self.static, global_step=global_step, optimizer=self.opt, grad_sync=self.grad_sync)
+            return self._capture(global_step)              # performs this step for real during its warm-up
+        self.opt.sync_lr()
+        self.graph.replay()
+        self._finish()
+        # the step updated the parameters through raw pointers: version-keyed caches (the renderer's packed weights) must see it
+        torch.autograd.graph.increment_version([p for p in self.pipe.parameters() if p.requires_grad])
+        return self.out

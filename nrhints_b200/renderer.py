@@ -673,8 +673,8 @@ class NeuSHintRenderer(nn.Module):
         inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6).to(device)
         s_val = (1.0 / inv_s).reshape(1, 1).expand(R, S)
         if needs_grad and R > 0:
-            # interim autograd backend (nrhints_b200/autograd_fine.py): the no_grad parts of the reference ran in the
-            # CUDA kernels above; the differentiable fine pass is re-expressed with torch ops on the same device
+            # composed autograd route (nrhints_b200/autograd_fine.py; the fused node above did not apply): the no_grad parts of the
+            # reference ran in the CUDA kernels above; the differentiable fine pass is a handful of autograd nodes on the same device
             fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured)
             out["rgb"], out["weights"] = fine["rgb"], fine["weights"]
             out["analytic_normals"], out["normalized_normals"] = fine["analytic_normals"], fine["normalized_analytic_normals"]

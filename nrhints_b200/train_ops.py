@@ -152,8 +152,12 @@ class FlatAdam(torch.optim.Optimizer):
     """Adam over flat per-group buffers (see the module docstring).  Accepts torch.optim.Adam's param-group dicts
     ({'params': ..., 'lr': ...}); betas / eps / lr can be changed per group like in torch (LambdaLR works unchanged)."""
 
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, capturable: bool = False):
+        """capturable=True keeps the step count and the learning rate of every group on the device (nrh_adam_step_dev), so that a
+        CUDA graph holding the step stays valid from replay to replay; call `sync_lr()` before a replay when a scheduler changed
+        `group['lr']`.  All parameters of a group must then take part in every step (no frozen subsets)."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = bool(capturable)
         self._flat: List[Dict[str, torch.Tensor]] = []
         for group in self.param_groups:
             ps = [p for p in group["params"]]
@@ -174,7 +178,21 @@ class FlatAdam(torch.optim.Optimizer):
                     p.grad = buf["grad"][off:off + k].view_as(p)
                     off += k
             buf["steps"] = [0] * len(ps)                       # per parameter, as torch.optim.Adam counts them
+            if self.capturable:
+                buf["step_dev"] = torch.zeros(1, dtype=torch.int64, device=dev)
+                buf["lr_dev"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+                buf["coef"] = torch.zeros(2, dtype=torch.float32, device=dev)
+                buf["lr_host"] = float(group["lr"])
             self._flat.append(buf)
+
+    def sync_lr(self):
+        """capturable mode: push every group's current `lr` to its device scalar (one tiny fill per group whose lr changed)."""
+        if not self.capturable:
+            return
+        for group, buf in zip(self.param_groups, self._flat):
+            if buf and buf["lr_host"] != float(group["lr"]):
+                buf["lr_dev"].fill_(float(group["lr"]))
+                buf["lr_host"] = float(group["lr"])
 
     def flat_grads(self) -> List[torch.Tensor]:
         """One flat gradient tensor per parameter group: the all-reduce operand (nrhints_b200/grad_sync.py)."""
@@ -222,6 +240,19 @@ class FlatAdam(torch.optim.Optimizer):
                 off += k
             b1, b2 = group["betas"]
             dev = buf["param"].device
+            if self.capturable:
+                if len(runs) != 1 or runs[0][1] != buf["param"].numel():
+                    raise RuntimeError("FlatAdam(capturable=True) steps whole groups only (a parameter of the group is frozen)")
+                if not torch.cuda.is_current_stream_capturing():
+                    self.sync_lr()
+                with torch.cuda.device(dev):
+                    _lib.check(lib.nrh_adam_step_dev(buf["param"].data_ptr(), buf["grad"].data_ptr(), buf["exp_avg"].data_ptr(),
+                                                     buf["exp_avg_sq"].data_ptr(), buf["param"].numel(), buf["lr_dev"].data_ptr(),
+                                                     float(b1), float(b2), float(group["eps"]), buf["step_dev"].data_ptr(),
+                                                     buf["coef"].data_ptr(), float(grad_scale),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "nrh_adam_step_dev")
+                torch.autograd.graph.increment_version([p for p in group["params"] if p.requires_grad])
+                continue
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 for o, k, st in runs:
@@ -234,7 +265,14 @@ class FlatAdam(torch.optim.Optimizer):
         return loss
 
     # torch.optim.Adam-compatible checkpoints (trainer/trainer.py:156,223)
+    def _pull_steps(self):
+        """capturable mode: the per-parameter step counts follow the device counter (graph replays advance it without Python)."""
+        for buf in self._flat:
+            if buf and self.capturable:
+                buf["steps"] = [int(buf["step_dev"].item())] * len(buf["steps"])
+
     def state_dict(self):
+        self._pull_steps()
         state, groups, idx = {}, [], 0
         for group, buf in zip(self.param_groups, self._flat):
             ids, off = [], 0
@@ -286,3 +324,6 @@ class FlatAdam(torch.optim.Optimizer):
                     buf["exp_avg_sq"][off:off + k].zero_()
                     buf["steps"][i] = 0
                 idx += 1; off += k
+            if buf and self.capturable:
+                buf["step_dev"].fill_(max(buf["steps"]) if buf["steps"] else 0)
+                buf["lr_dev"].fill_(float(group["lr"])); buf["lr_host"] = float(group["lr"])
