@@ -130,8 +130,11 @@ typedef struct NrhTrainCapture {
     void* tape; size_t tape_bytes;   /* nrh_sdf_train_layout(cfg, S * R).tape_bytes                         */
     float* sdf;                      /* [N]                                                                 */
     float* grad_soa;                 /* [3][N]  d sdf / d x, one plane per coordinate                       */
-    float* feat;                     /* [N,256] fp32 feature head output                                    */
+    float* feat;                     /* [N,256] fp32 feature head output (nullable when feat16 is given)    */
     float* pts_soa;                  /* [3][N]  the section mid-points the kernels evaluated                */
+    void* feat16; int64_t feat16_ld; /* nullable: the features as unscaled fp16 rows [N][feat16_ld] instead  */
+                                     /* (16-byte aligned, ld a multiple of 8): the feature block of the      */
+                                     /* reflectance operand, written in place by the fine-pass kernel        */
 } NrhTrainCapture;
 
 typedef struct NrhOutputs {       /* RenderOutput fields (models/neus_hint_model.py:216-233); S = n_samples+n_importance;

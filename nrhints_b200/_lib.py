@@ -69,7 +69,7 @@ class NrhOutputs(C.Structure):
 
 class NrhTrainCapture(C.Structure):
     _fields_ = [("tape", C.c_void_p), ("tape_bytes", C.c_size_t), ("sdf", C.c_void_p), ("grad_soa", C.c_void_p),
-                ("feat", C.c_void_p), ("pts_soa", C.c_void_p)]
+                ("feat", C.c_void_p), ("pts_soa", C.c_void_p), ("feat16", C.c_void_p), ("feat16_ld", C.c_int64)]
 
 
 class NrhTrainLayout(C.Structure):

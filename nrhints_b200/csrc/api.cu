@@ -180,7 +180,7 @@ Workspace carve(const NrhConfig& cfg, int64_t R, char* base, int num_sms) {
 struct TrainWs {
     char* render; size_t render_bytes;          // the render workspace (carve)
     void* tape; size_t tape_bytes;
-    float* cap_sdf; float* cap_grad; float* cap_feat; float* cap_pts;      // [N], [3][N], [N][256], [3][N]
+    float* cap_sdf; float* cap_grad; float* cap_pts;                       // [N], [3][N], [3][N] (the features go straight into x16)
     float* z_rm;                                 // [R][S] final sample positions, ray-major
     float* dists; float* mid_z;                  // [R][S], [N]
     __half* x16; __half* acts; float* y; float* color; float* grad_aos;    // [N][384], [4][N][256], [N][4], [N][3], [N][3]
@@ -221,7 +221,7 @@ TrainWs carve_train(const NrhConfig& cfg, int64_t R, char* base, int num_sms) {
     t.render_bytes = carve(cfg, R, nullptr, num_sms).total_bytes;
     t.render = take(t.render_bytes);
     t.tape_bytes = t.lay.tape_bytes; t.tape = take(t.tape_bytes);
-    t.cap_sdf = (float*)take(4 * N); t.cap_grad = (float*)take(12 * N); t.cap_feat = (float*)take(1024 * N); t.cap_pts = (float*)take(12 * N);
+    t.cap_sdf = (float*)take(4 * N); t.cap_grad = (float*)take(12 * N); t.cap_pts = (float*)take(12 * N);
     t.z_rm = (float*)take(4 * N); t.dists = (float*)take(4 * N); t.mid_z = (float*)take(4 * N);
     t.x16 = (__half*)take(768 * N); t.acts = (__half*)take(2048 * N); t.y = (float*)take(16 * N); t.color = (float*)take(12 * N);
     t.grad_aos = (float*)take(12 * N);
@@ -564,7 +564,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
     const NrhTrainCapture* cap = out->train_capture;
     if (cap) {
         if (resolve_impl(*cfg) != NRH_MLP_TCGEN05 || cfg->use_outside_nerf) { set_error("train_capture needs the tcgen05 engine without the outside NeRF"); return NRH_ERR_UNSUPPORTED; }
-        if (!cap->tape || !cap->sdf || !cap->grad_soa || !cap->feat || !cap->pts_soa) { set_error("train_capture: null buffer"); return NRH_ERR_INVALID; }
+        if (!cap->tape || !cap->sdf || !cap->grad_soa || (!cap->feat && !cap->feat16) || !cap->pts_soa) { set_error("train_capture: null buffer"); return NRH_ERR_INVALID; }
         if (cap->tape_bytes < sdf_train_layout((int64_t)S * R, sms).tape_bytes) { set_error("train_capture: tape too small"); return NRH_ERR_WORKSPACE; }
     }
     const bool streamed = !cap && resolve_impl(*cfg) == NRH_MLP_TCGEN05 && (R % 128 == 0);
@@ -573,7 +573,7 @@ int nrh_render_forward(const NrhConfig* cfg, const void* packed, const NrhRays* 
         // the training forward (same arithmetic + tape) straight into the caller's buffers; the compositor reads them there
         const int64_t N = (int64_t)S * R;
         if ((rc = sdf_train_forward_tc_strided(packed, L, P, N, cap->sdf, cap->grad_soa, cap->grad_soa + N, cap->grad_soa + 2 * N, 1,
-                                               cap->feat, cap->tape, w.mlp_scratch, w.mlp_scratch_bytes, sms, st))) return rc;
+                                               cap->feat, cap->tape, w.mlp_scratch, w.mlp_scratch_bytes, sms, st, cap->feat16, cap->feat16_ld))) return rc;
         NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.sdf, cap->sdf, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
         NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.gx, cap->grad_soa, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
         NRH_CUDA_CHECK(cudaMemcpyAsync(w.fine.gy, cap->grad_soa + N, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
@@ -738,7 +738,7 @@ int nrh_render_train_forward(const NrhConfig* cfg, const void* packed, const Nrh
     const int64_t N = (int64_t)S * R;
     // 1. everything the reference computes without gradients + the primary fine pass with its tape (NrhTrainCapture); the final
     //    sample positions come back ray-major in z_rm
-    NrhTrainCapture cap{t.tape, t.tape_bytes, t.cap_sdf, t.cap_grad, t.cap_feat, t.cap_pts};
+    NrhTrainCapture cap{t.tape, t.tape_bytes, t.cap_sdf, t.cap_grad, nullptr, t.cap_pts, t.x16, 384};     // features: fp16 rows of x16
     NrhOutputs o = *out;
     o.train_capture = &cap;
     o.z_vals = t.z_rm;
@@ -753,7 +753,8 @@ int nrh_render_train_forward(const NrhConfig* cfg, const void* packed, const Nrh
     TrainAssembleArgs A{};
     A.N = N; A.R = R; A.gx = t.cap_grad; A.gy = t.cap_grad + N; A.gz = t.cap_grad + 2 * N;
     A.px = t.cap_pts; A.py = t.cap_pts + N; A.pz = t.cap_pts + 2 * N;
-    A.feat = t.cap_feat; A.rayfeat = w.rayfeat; A.normalized = cfg->normalized_normals; A.x16 = t.x16; A.grad_aos = t.grad_aos;
+    A.feat = nullptr;                              // the feature block of x16 was written by the fine-pass kernel itself
+    A.rayfeat = w.rayfeat; A.normalized = cfg->normalized_normals; A.x16 = t.x16; A.grad_aos = t.grad_aos;
     if ((rc = launch_train_assemble(A, st))) return rc;
     if ((rc = color_train_forward_tc(packed, L, t.x16, N, t.acts, t.y, sms, st, true))) return rc;
     if ((rc = launch_color_sigmoid(t.y, N, t.color, st))) return rc;

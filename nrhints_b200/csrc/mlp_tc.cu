@@ -270,6 +270,8 @@ struct SdfTcParams {
     __half* tape_act;                  // [8][P_pad][256] fp16: a_1 .. a_8 (x ACT_SCALE), row-major
     __half* tape_u;                    // [8][P_pad][256] fp16: u_0 .. u_7 (x G_SCALE), row-major
     int64_t p_pad;
+    __half* feat16; int64_t feat16_ld; // fused training step: features leave as unscaled fp16 rows [N][feat16_ld] (the first 256
+                                       // columns of the reflectance operand) instead of fp32 rows; nullptr = off
 };
 
 // One gemm = `nsub` sub-chunks of 32 K-columns.  Every weight image serves exactly one sub-chunk: its 64 "K" columns are
@@ -443,7 +445,8 @@ __device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int
 // feature head epilogue: write feat (fp32 row-major, or the fp16 operand image of the tile) and, with GRAD, seed the reverse sweep
 template <bool GRAD, class EP, class WaitAcc>
 __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const float* __restrict__ bias, const float* __restrict__ head_w,
-                                         float* __restrict__ feat_row, uint8_t* __restrict__ feat_tile_img, bool valid) {
+                                         float* __restrict__ feat_row, uint8_t* __restrict__ feat_tile_img, bool valid,
+                                         __half* __restrict__ feat16_row = nullptr) {
     float vA[8], bA[8], vB[8], bB[8];
     const int cq = E.gq * 8;
     ldg8(bias + cq, bA);
@@ -468,6 +471,8 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
 #pragma unroll
             for (int i = 0; i < 8; ++i) t16[i] = valid ? v[i] * ACT_SCALE : 0.f;
             store_half8(feat_tile_img + (sc >> 1) * A_CHUNK, E.off[sc & 1], t16);
+        } else if (feat16_row) {                       // unscaled fp16 row (same rounding as a later fp32 -> fp16 conversion pass)
+            if (valid) store_half8(reinterpret_cast<uint8_t*>(feat16_row + cq + sc * 32), 0u, v);
         } else if (valid) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -773,7 +778,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             if (FEAT) {
                 if (TRAIN) E.dump = P.tape_u + ((size_t)(SDF_LAYERS - 1) * P.p_pad + p) * 256;    // reverse seed u_7
                 epi_feat<GRAD>(E, wait_acc, P.feat_b, P.head_w, feat_out + (valid ? p : 0) * 256,
-                               P.feat_image ? reinterpret_cast<uint8_t*>(feat_out) + (size_t)tile * TC_TILE_FEAT_BYTES : nullptr, valid);
+                               P.feat_image ? reinterpret_cast<uint8_t*>(feat_out) + (size_t)tile * TC_TILE_FEAT_BYTES : nullptr, valid,
+                               (TRAIN && P.feat16) ? P.feat16 + (valid ? p : 0) * P.feat16_ld : nullptr);
                 tc_fence_before();
             }
             if (GRAD) {
@@ -1266,6 +1272,7 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     const float* Pf = reinterpret_cast<const float*>(packed);
     SdfTcParams P;
     P.feat_image = feat_as_image ? 1 : 0;
+    P.feat16 = nullptr; P.feat16_ld = 0;
     P.tc = reinterpret_cast<const uint8_t*>(packed) + L.tc_offset_bytes;
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
@@ -1322,7 +1329,7 @@ SdfTrainLayout sdf_train_layout(int64_t N, int num_sms) {
 
 int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf, float* gx, float* gy,
                                  float* gz, int64_t gstride, float* feat, void* tape, float* scratch, size_t scratch_bytes, int num_sms,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, void* feat16, int64_t feat16_ld) {
     if (N <= 0) return NRH_OK;
     const float* Pf = reinterpret_cast<const float*>(packed);
     const SdfTrainLayout TL = sdf_train_layout(N, num_sms);
@@ -1337,6 +1344,8 @@ int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Stri
     P.tape_act = reinterpret_cast<__half*>(tb + TL.tape_act_off);
     P.tape_u = reinterpret_cast<__half*>(tb + TL.tape_u_off);
     P.p_pad = TL.p_pad;
+    P.feat16 = reinterpret_cast<__half*>(feat16); P.feat16_ld = feat16_ld;
+    if (feat16 && ((reinterpret_cast<uintptr_t>(feat16) & 15) || (feat16_ld & 7))) { set_error("sdf_train_forward_tc: feat16 rows must be 16-byte aligned"); return NRH_ERR_INVALID; }
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_train_forward_tc: scratch too small"); return NRH_ERR_WORKSPACE; }

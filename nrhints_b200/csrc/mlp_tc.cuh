@@ -49,7 +49,9 @@ int sdf_train_forward_tc(const void* packed, const PackedLayout& L, const float*
 // the same for points / gradients given as strided coordinate arrays (the render pipeline's sample-major SoA buffers)
 int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N, float* sdf, float* gx, float* gy,
                                  float* gz, int64_t gstride, float* feat, void* tape, float* scratch, size_t scratch_bytes, int num_sms,
-                                 cudaStream_t st);
+                                 cudaStream_t st, void* feat16 = nullptr, int64_t feat16_ld = 0);
+// feat16 != nullptr: the features leave as unscaled fp16 rows [N][feat16_ld] (the feature block of the fused step's reflectance
+// operand) and `feat` is not written
 // feat16 (fused training step): d_feat as fp16 rows [N][ld] already in units of another power-of-two loss scale, *mul converts to S;
 // pts_strided: the points as strided coordinate arrays instead of [N][3]
 struct SdfBwdFeat16 { const void* rows; int64_t ld; const float* mul; };

@@ -5,8 +5,9 @@
 // The reference issues ~25 small ATen kernels per batch (stack, gather, bmm, normalize, sums) plus the autograd graph of the
 // exp map; here it is ONE launch forward and ONE launch backward, one thread per ray.  Both are trivially HBM/launch bound:
 // 104 B in + 44 B out per ray forward.  The backward re-derives the forward intermediates from the same inputs (cheaper than a
-// tape) and reduces the per-image gradients inside the warp before touching global memory: with the reference's default
-// SAME_IMAGE pixel sampling (data/data_loader.py:66-68) every ray of a batch hits the same row of the parameter.
+// tape) and reduces the per-image gradients inside the warp before touching global memory when all lanes of a warp share an image
+// index (SAME_IMAGE pixel sampling, data/data_loader.py:66-68; the reference trainer's ALL_IMAGES sampling, trainer/trainer.py:118-125,
+// mixes images inside a warp and takes the per-lane atomic path).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nrh_common.cuh"
@@ -28,8 +29,11 @@ struct RayGenArgs {
 
 __device__ __forceinline__ int64_t image_of(const RayGenArgs& A, int64_t r) {
     if (!A.img_idx) return -1;
-    const int64_t i = A.img_idx[r];
-    return (i >= 0 && i < A.n_cameras) ? i : -1;       // out-of-range indices are rejected on the host side; never dereferenced here
+    int64_t i = A.img_idx[r];
+    if (i < 0) i += A.n_cameras;                        // negative indices wrap, as torch indexing does in the reference (:92-98,:121-126)
+    // indices outside [-n, n) raise an IndexError in the reference; RayGenerator.forward asserts the range on the device
+    // (validate_indices), and the kernel never dereferences such an index: the ray then gets no noise / adjustment / gradient
+    return (i >= 0 && i < A.n_cameras) ? i : -1;
 }
 
 __global__ void __launch_bounds__(RG_THREADS)

@@ -127,9 +127,11 @@ k_train_assemble(TrainAssembleArgs A) {
         A.grad_aos[p * 3] = gx; A.grad_aos[p * 3 + 1] = gy; A.grad_aos[p * 3 + 2] = gz;
     }
     __half* row = A.x16 + p * 384;
-    const float* frow = A.feat + p * 256;
+    if (A.feat) {                                         // nullptr: the SDF kernel already wrote the feature block (fp16 rows of x16)
+        const float* frow = A.feat + p * 256;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) row[k * 32 + lane] = __float2half_rn(frow[k * 32 + lane]);
+        for (int k = 0; k < 8; ++k) row[k * 32 + lane] = __float2half_rn(frow[k * 32 + lane]);
+    }
     // auxiliary block, columns 256 .. 383: [pts 3 | PE(view) 27 | normal 3 | PE(light) 27 | PE(vis) 9 | PE(spec) 36 | 0 ...] -- the fixed
     // positions of the inference kernel's layer-0 operand (csrc/mlp_tc.cu::tc_pack); rayfeat rows of a disabled hint are zero
 #pragma unroll

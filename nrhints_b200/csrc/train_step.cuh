@@ -20,7 +20,7 @@ struct TrainAssembleArgs {
     int64_t N, R;
     const float* gx; const float* gy; const float* gz;      // grad sdf, SoA [N]
     const float* px; const float* py; const float* pz;      // fine points, SoA [N]
-    const float* feat;                                      // [N][256]
+    const float* feat;                                      // [N][256], or nullptr when the feature block of x16 is already in place
     const float* rayfeat;                                   // [99][R] per-ray encodings (k_shade_prep)
     int normalized;
     __half* x16;                                            // [N][384]

@@ -126,6 +126,10 @@ class RayGenerator(nn.Module):
         self.camera = camera
         self.config = config
         self.num_cameras = int(num_cameras)
+        # the reference indexes its per-image tables with torch indexing: negative indices wrap, anything outside [-n, n) raises an
+        # IndexError.  Here the range is asserted on the device (torch._assert_async: no host sync, the error surfaces at the next
+        # synchronisation); switch off to save the three tiny launches once a data loader is trusted.
+        self.validate_indices = True
         if config.cam_opt_mode not in _lib.CAM_OPT_MODES:
             raise ValueError(f"Unknown camera pose optimization mode: {config.cam_opt_mode}")
         self._mode = _lib.CAM_OPT_MODES[config.cam_opt_mode]
@@ -165,6 +169,10 @@ class RayGenerator(nn.Module):
         img_idx = None
         if pixel_bundle.img_indices is not None:
             img_idx = pixel_bundle.img_indices[..., 0].to(device=dev, dtype=torch.int64).contiguous()
+            if self.validate_indices and img_idx.numel() > 0:
+                lo, hi = torch.aminmax(img_idx)
+                torch._assert_async((lo >= -self.num_cameras) & (hi < self.num_cameras),
+                                    f"RayGenerator: img_indices outside [-{self.num_cameras}, {self.num_cameras})")
         poses = poses.detach().to(**f32).contiguous()
         pls = pixel_bundle.pls.detach().to(**f32).contiguous()
         for name in ("cam_pose_adjustment", "pl_adjustment", "cam_pose_noise", "pl_noise"):

@@ -49,7 +49,7 @@ def test_struct_layout_matches_header():
     assert _lib.NRH_ABI_VERSION == int(re.search(r"#define NRH_ABI_VERSION (\d+)", HEADER).group(1))
     assert C.sizeof(_lib.NrhRays) == 7 * 8
     assert C.sizeof(_lib.NrhOutputs) == 19 * 8
-    assert C.sizeof(_lib.NrhTrainCapture) == 6 * 8 and C.sizeof(_lib.NrhRayGenInputs) == 10 * 8 and C.sizeof(_lib.NrhCamera) == 6 * 4
+    assert C.sizeof(_lib.NrhTrainCapture) == 8 * 8 and C.sizeof(_lib.NrhRayGenInputs) == 10 * 8 and C.sizeof(_lib.NrhCamera) == 6 * 4
     fields = re.findall(r"(?:float|void|const NrhTrainCapture)\*\s+(\w+);", HEADER[HEADER.index("typedef struct NrhOutputs"):HEADER.index("} NrhOutputs;")])
     assert fields == [n for n, _ in _lib.NrhOutputs._fields_]
 

@@ -209,3 +209,28 @@ def test_constructor_matches_the_reference_state_dict_and_rng_draws():
             np.testing.assert_array_equal(v.numpy(), ref)                      # a plain torch.normal draw
         else:
             np.testing.assert_allclose(v.numpy(), ref, rtol=0, atol=1e-7, err_msg=k)   # exp_map_SE3 of the draw
+
+
+@pytest.mark.gpu
+def test_negative_image_indices_wrap_like_torch_indexing():
+    """The reference indexes its per-image tables with torch indexing (camera/ray_generator.py:92-98,:121-126): index -k means
+    image n - k.  (Indices outside [-n, n) raise an IndexError there; here RayGenerator.validate_indices asserts the range on the
+    device -- a device-side assert poisons the CUDA context, so that branch is not exercised in this process.)"""
+    import nrhints_b200 as nb
+    name = next(n for n, c in T.RAYGEN_CASES.items() if c["cam_opt_mode"] != "off" and c["noise"])
+    case = T.RAYGEN_CASES[name]
+    inp = T.raygen_inputs(case)
+    cfg = nb.RayGeneratorConfig(override_near_far_from_sphere=case["override_near_far"], cam_opt_mode=case["cam_opt_mode"],
+                                pl_opt=case["pl_opt"], cam_position_noise_std=0.01, cam_orientation_noise_std=0.01,
+                                pl_position_noise_std=0.01)
+    gen = nb.RayGenerator(nb.CameraModel(**inp["camera"]), inp["n_cameras"], cfg).cuda()
+    with torch.no_grad():
+        gen.cam_pose_adjustment.copy_(inp["cam_pose_adjustment"])
+        if case["pl_opt"]:
+            gen.pl_adjustment.copy_(inp["pl_adjustment"])
+        gen.cam_pose_noise.copy_(inp["cam_pose_noise"]); gen.pl_noise.copy_(inp["pl_noise"])
+        a = gen(_bundle(inp, "cuda"))
+        neg = dict(inp); neg["img_indices"] = inp["img_indices"] - inp["n_cameras"]
+        b = gen(_bundle(neg, "cuda"))
+    for k in FIELDS:
+        assert torch.equal(getattr(a, k), getattr(b, k)), k

@@ -58,6 +58,17 @@ def test_wgrad_skinny_rows():
     WgradBatch().add(A, B, out, scale=0.5, m=3).run()
     torch.cuda.synchronize()
     assert float((out - _ref(A[:, :3], B, 0.5)).abs().max()) < 2e-2
+    # one result row (the sdf head's d_sdf row), a column window of a wider matrix, and the scalar-load path (odd column count)
+    W = (torch.randn(P, 384, generator=g) * 0.5).half().cuda()
+    o1 = torch.zeros(1, 256, device="cuda")
+    WgradBatch().add(A, W, o1, m=1, n=256, b_col0=128).run()
+    assert float((o1 - _ref(A[:, :1], W[:, 128:384], 1.0)).abs().max()) < 2e-2
+    o2 = torch.zeros(2, 256, device="cuda")
+    WgradBatch().add(A, B, o2, m=2, n=100, cols_valid=100).run()
+    assert float((o2[:, :100] - _ref(A[:, :2], B[:, :100], 1.0)).abs().max()) < 2e-2 and float(o2[:, 100:].abs().max()) == 0.0
+    o3 = torch.zeros(3, 256, device="cuda")
+    WgradBatch().add(A, B, o3, m=3, n=99, cols_valid=99).run()
+    assert float((o3[:, :99] - _ref(A[:, :3], B[:, :99], 1.0)).abs().max()) < 2e-2 and float(o3[:, 99:].abs().max()) == 0.0
 
 
 def test_wgrad_many_jobs_one_launch():
