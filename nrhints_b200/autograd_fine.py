@@ -286,7 +286,8 @@ def _linear_f16_ok(x: Tensor) -> bool:
 def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays_pl: Tensor, z_vals: Tensor,
                 sample_dist: float, visibilities: Optional[Tensor], specular_cue: Optional[Tensor],
                 background_rgb: Optional[Tensor], cos_anneal: float, inv_s: Tensor, normalized_normals: bool,
-                refl_freq: int = 4, sdf_fn=None, sample_major: bool = False, renderer=None) -> Dict[str, Tensor]:
+                refl_freq: int = 4, sdf_fn=None, sample_major: bool = False, renderer=None,
+                outside: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
     """render_core's differentiable part (models/neus_hint_model.py:475-651) given the sample positions and hints.
 
     weights: dict(sdf_w, sdf_b: lists of 8; sdf_w_head, sdf_b_head, feat_w, feat_b; col_w, col_b: lists of 5).
@@ -294,6 +295,9 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
     sdf_fn: optional callable pts [N,3] -> (sdf [N,1], feat [N,256], grad [N,3]) replacing the torch evaluation of the SDF
     network and its create_graph input gradient by ONE autograd node with a hand-written CUDA forward and backward
     (nrhints_b200/sdf_autograd.py, the tcgen05 engine).
+    outside: the background model's terms on the merged sample set (alpha [R,S+n_out], color [R,S+n_out,3]) and the inside-sphere
+    mask [R,S]: alpha / colour are blended outside the unit sphere and the appended outside samples join the compositing
+    (models/neus_hint_model.py:517-524,:628-633); the returned weights / colours then have S + n_out entries per ray.
     sample_major: evaluate the points in the render pipeline's order (p = j * R + r instead of r * S + j), so that a tape captured
     by nrh_render_forward (NrhTrainCapture) lines up with them; results are returned ray-major either way."""
     R, S = z_vals.shape
@@ -322,7 +326,7 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
             grad = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
     # compositing: ONE CUDA autograd node on the tcgen05 path (the sample positions carry no gradient there: importance sampling
     # detaches them, so `dists` is data), the torch expression otherwise (fp32 engine, CPU tests, n_importance == 0)
-    fused_composite = (sdf_fn is not None and pts.is_cuda and not dists.requires_grad and S <= 128
+    fused_composite = (sdf_fn is not None and pts.is_cuda and not dists.requires_grad and S <= 128 and outside is None
                        and os.environ.get("NRH_COMPOSITE", "cuda") != "torch")
     w = wsum = None
     if not fused_composite:
@@ -332,6 +336,10 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
         prev_cdf = torch.sigmoid((sdf - half) * inv_s)
         next_cdf = torch.sigmoid((sdf + half) * inv_s)
         alpha = per_ray(((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0, 1))[..., 0]
+        if outside is not None:
+            ins = outside["inside"]
+            alpha = alpha * ins + outside["alpha"][:, :S] * (1.0 - ins)
+            alpha = torch.cat([alpha, outside["alpha"][:, S:]], dim=-1)
         trans = torch.cumprod(torch.cat([torch.ones((R, 1), device=dev, dtype=dt), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
         w = alpha * trans
         wsum = w.sum(-1, keepdim=True)
@@ -362,6 +370,9 @@ def render_fine(weights: Dict[str, object], rays_o: Tensor, rays_d: Tensor, rays
                 hcol = torch.relu(hcol)
     color_pt = torch.sigmoid(hcol)
     color = per_ray(color_pt)
+    if outside is not None:
+        ins = outside["inside"][..., None]
+        color = torch.cat([color * ins + outside["color"][:, :S] * (1.0 - ins), outside["color"][:, S:]], dim=1)
     if fused_composite:
         rgb, w = _CompositeTrain.apply(sdf, grad, color_pt, rays_d, inv_s, dists, background_rgb, float(cos_anneal), bool(sample_major))
     else:

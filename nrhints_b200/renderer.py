@@ -285,8 +285,24 @@ class OutsideNeRF(nn.Module):
         self.alpha_linear = nn.Linear(W, 1)
         self.rgb_linear = nn.Linear(W // 2, 3)
 
-    def forward(self, *args, **kwargs):
-        raise RuntimeError("the outside NeRF is evaluated inside NeuSHintRenderer.forward (fused CUDA pipeline)")
+    def forward(self, input_pts, input_views, input_pls):
+        """NeRF.forward with the reference's signature (fields/nerf_density_field.py:66-89: PE(10) of the 4-D inverted-sphere point,
+        8 x 256 ReLU trunk with the encoded point re-concatenated IN FRONT after layer 4, density head, feature layer, one 128-wide
+        layer on [feature | PE(4) of (view, light)], rgb head) in plain fp32 torch -> (density [N,1], rgb logits [N,3]).
+        The render path never calls this -- NeuSHintRenderer.forward evaluates the network inside the fused CUDA pipeline
+        (csrc/mlp_simt.cu::nerf_mlp_kernel); it is the DIFFERENTIABLE route of the outside model when a call needs gradients."""
+        F = torch.nn.functional
+        e = autograd_fine._fourier(input_pts, self.config.multi_res)
+        ev = autograd_fine._fourier(torch.cat([input_views, input_pls], dim=-1), self.config.multi_res_view)
+        h = e
+        for i, lin in enumerate(self.pts_linears):
+            h = F.relu(lin(h))
+            if i in self.skips:
+                h = torch.cat([e, h], -1)
+        density = self.alpha_linear(h)
+        h = torch.cat([self.feature_linear(h), ev], -1)
+        h = F.relu(self.views_linears[0](h))
+        return density, self.rgb_linear(h)
 
 
 class SingleVarianceNetwork(nn.Module):
@@ -587,9 +603,6 @@ class NeuSHintRenderer(nn.Module):
         needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                                   or any(t.requires_grad for t in ray_fields))
         want_z = return_extras or needs_grad
-        if needs_grad and self.has_outside_nerf:
-            raise NotImplementedError("gradients with use_outside_nerf=True are not implemented: the outside NeRF runs in the "
-                                      "CUDA forward only (wrap the call in torch.no_grad(), as the reference's evaluation does)")
 
         def prep(t):
             return t.detach().to(**f32).contiguous()
@@ -675,7 +688,7 @@ class NeuSHintRenderer(nn.Module):
         if needs_grad and R > 0:
             # composed autograd route (nrhints_b200/autograd_fine.py; the fused node above did not apply): the no_grad parts of the
             # reference ran in the CUDA kernels above; the differentiable fine pass is a handful of autograd nodes on the same device
-            fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured)
+            fine = self._differentiable_fine(ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured, jit_o)
             out["rgb"], out["weights"] = fine["rgb"], fine["weights"]
             out["analytic_normals"], out["normalized_normals"] = fine["analytic_normals"], fine["normalized_analytic_normals"]
             if out["sampled_color"] is not None:
@@ -699,7 +712,32 @@ class NeuSHintRenderer(nn.Module):
             "col_b": [getattr(cn, f"lin{l}").bias for l in range(5)],
         }
 
-    def _differentiable_fine(self, ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured=None):
+    def _outside_terms(self, rays_o, rays_d, rays_pl, fars, z_inner, jit_o, f32):
+        """Differentiable background model of a call that needs gradients (models/neus_hint_model.py:677-694,:716-724,:434-473):
+        the outside sample positions (inverse-depth spacing beyond `far`, stratified jitter = the same torch.rand draw the CUDA forward
+        received), merged and sorted with the inner positions, evaluated by the torch NeRF -> per-section alpha and colour of the
+        merged set.  The fused forward computes the same quantities in nerf_mlp_kernel; this route exists for autograd."""
+        r = self.config.renderer
+        R, S = z_inner.shape
+        n, n_out = r.n_samples, r.n_outside_samples
+        zo = torch.linspace(1e-3, 1.0 - 1.0 / (n_out + 1.0), n_out, **f32)
+        if jit_o is not None:
+            mids = 0.5 * (zo[1:] + zo[:-1])
+            upper, lower = torch.cat([mids, zo[-1:]]), torch.cat([zo[:1], mids])
+            zo = lower[None, :] + (upper - lower)[None, :] * jit_o
+        zo = (fars / torch.flip(zo, dims=[-1]) + 1.0 / n).expand(R, n_out)
+        z_feed, _ = torch.sort(torch.cat([z_inner, zo], dim=-1), dim=-1)
+        dists = torch.cat([z_feed[:, 1:] - z_feed[:, :-1], torch.full((R, 1), 2.0 / n, **f32)], -1)
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * (z_feed + dists * 0.5)[..., None]
+        dis = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
+        pts4 = torch.cat([pts / dis, 1.0 / dis], dim=-1).reshape(-1, 4)
+        St = S + n_out
+        density, col = self.outside_nerf(pts4, rays_d[:, None, :].expand(R, St, 3).reshape(-1, 3),
+                                         rays_pl[:, None, :].expand(R, St, 3).reshape(-1, 3))
+        alpha = 1.0 - torch.exp(-torch.nn.functional.softplus(density.reshape(R, St)) * dists)
+        return {"alpha": alpha, "color": torch.sigmoid(col).reshape(R, St, 3)}
+
+    def _differentiable_fine(self, ray_fields, out, jit_p, background_rgb, cos_anneal, inv_s, f32, captured=None, jit_o=None):
         r = self.config.renderer
         rays_o, rays_d, rays_pl, nears, fars = (t.to(**f32) for t in ray_fields)
         n = r.n_samples
@@ -722,10 +760,15 @@ class NeuSHintRenderer(nn.Module):
             cap = dict(tape=captured["tape"], sdf=captured["sdf"], feat=captured["feat"], grad=captured["grad_soa"].t().contiguous(),
                        pts=captured["pts_soa"].t().contiguous())
         sdf_fn = (lambda pts: sdf_autograd.sdf_fine(self, pts, w, cap)) if self.mlp_impl in ("auto", "tcgen05") else None
+        outside = None
+        if self.has_outside_nerf:
+            outside = self._outside_terms(rays_o, rays_d, rays_pl, fars, out["z_vals"], jit_o, f32)
+            outside["inside"] = out["inside_sphere"]
         return autograd_fine.render_fine(w, rays_o, rays_d, rays_pl, z, 2.0 / n, vis, spec, bg,
                                          float(cos_anneal), inv_s, normalized, refl_freq=self.config.reflectance_network.multi_res,
                                          sdf_fn=sdf_fn, sample_major=captured is not None,
-                                         renderer=self if (sdf_fn is not None and self.color_network.d_in_total <= 384) else None)
+                                         renderer=self if (sdf_fn is not None and self.color_network.d_in_total <= 384) else None,
+                                         outside=outside)
 
     # -- device -> host hand-off of a RenderOutput (the reference does `rendering_res.to('cpu')` per 512-ray chunk,
     #    pipelines/base_pipeline.py:120, through pageable memory; here: pinned buffers owned by the returned object (recycled by

@@ -228,19 +228,25 @@ def test_full_size_sharp_all_fields_match_oracle():
 
 
 @pytest.mark.parametrize("impl", IMPLS + ["auto-composed"])
-@pytest.mark.parametrize("name", list(T.GRAD_CASES))
+@pytest.mark.parametrize("name", list(T.GRAD_CASES) + ["outside_train_64x128"])
 def test_training_gradients_match_oracle(name, impl):
-    """Training-mode forward + loss.backward() through the CUDA path (fused SDF forward-with-tape / second-order backward, CUDA
-    compositing node, reflectance MLP) against the oracle's autograd gradients -- which tests/test_oracle_golden.py pins to the
+    """Training-mode forward + loss.backward() through the CUDA path (the fused node by default, the composed autograd nodes as
+    "auto-composed", and -- with the outside NeRF -- the composed route plus the torch evaluation of the background model: all 70
+    parameter tensors incl. outside_nerf.*) against the oracle's autograd gradients -- which tests/test_oracle_golden.py pins to the
     reference's own loss.backward() fixtures -- for all 46 parameter tensors INCLUDING deviation_network.variance and for the ray
     inputs (origins / directions / light positions).  Two cases: init weights half way through annealing, and trained-like sharp
     weights (inv_s ~ 403) at global_step 60000 (cos_anneal = 1)."""
-    case = T.CASES[name]
+    # outside NeRF: the training-mode fixture case with 64 rays instead of 8 (at 8 rays the parameter gradients are ~1e-6 and the
+    # tcgen05 engine's fp16x3 noise at inv_s ~ 403 reaches 2-6 % of them; measured at 64 rays: <= 9e-3, gpurun_out r2 logs)
+    case = dict(T.CASES["outside_train_8x128"], R=64) if name == "outside_train_64x128" else T.CASES[name]
     m, cfg, sd = build_module(case, impl)
     rays, bg = T.case_inputs(case)
     R = case["R"]
+    if cfg.renderer.use_outside_nerf and impl == "auto-composed":
+        pytest.skip("with the outside NeRF the tcgen05 engine always takes the composed route (covered by impl 'auto')")
     torch.manual_seed(7)
     jp = torch.rand([R, 1], device="cuda")
+    jo = torch.rand([R, cfg.renderer.n_outside_samples], device="cuda") if cfg.renderer.use_outside_nerf else None
     js = torch.rand([R, cfg.renderer.n_shadow_samples], device="cuda")
     torch.manual_seed(7)
     dev_rays = {k: v.cuda() for k, v in rays.items()}
@@ -249,7 +255,7 @@ def test_training_gradients_match_oracle(name, impl):
     out = m(nb.RayBundle(**dev_rays), is_training=True, background_rgb=bg.cuda(), global_step=case["global_step"])
     assert out.rgb.requires_grad and out.weights.requires_grad and out.analytic_normals.requires_grad and out.s_val.requires_grad
     assert not out.depth.requires_grad and not out.visibilities.requires_grad
-    gt = torch.rand(R, 3, generator=torch.Generator().manual_seed(T.GRAD_CASES[name]))
+    gt = torch.rand(R, 3, generator=torch.Generator().manual_seed(T.GRAD_CASES.get(name, 79)))
     loss = orc.training_loss({"rgb": out.rgb, "analytic_normals": out.analytic_normals,
                               "relax_inside_sphere": out.relax_inside_sphere}, gt.cuda())
     loss.backward()
@@ -258,7 +264,7 @@ def test_training_gradients_match_oracle(name, impl):
     ocfg = orc.OracleConfig.from_model_config(cfg)
     want = orc.render_forward(sdr, ocfg, leaves["origins"], leaves["directions"], leaves["pl_positions"], rays["nears"], rays["fars"],
                               is_training=True, background_rgb=bg, cos_anneal=min(1.0, case["global_step"] / cfg.anneal_end),
-                              jitter_primary=jp.cpu(), jitter_shadow=js.cpu())
+                              jitter_primary=jp.cpu(), jitter_shadow=js.cpu(), jitter_outside=jo.cpu() if jo is not None else None)
     loss_o = orc.training_loss(want, gt)
     assert abs(float(loss) - float(loss_o)) < 1e-4
     keys = sorted(sdr)
