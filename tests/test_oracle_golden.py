@@ -19,6 +19,14 @@ def test_oracle_matches_reference_fixture(name):
         np.testing.assert_array_equal(v.numpy(), fx["in_" + k])
     got = T.to_np(T.run_oracle(case))
     want = {k[4:]: fx[k] for k in fx.files if k.startswith("out_")}
+    if name.startswith("sphere"):
+        # sphere tracing is chaotic on grazing rays (float noise decides where the 2000-iteration march ends, in the reference
+        # too, and the host's GEMM kernels decide the noise): compare the rays whose traced depth is robust, judged by the oracle
+        # alone (fp32 and fp64 evaluations agree) -- the same rule as tests/test_gpu_parity.py
+        w64 = T.to_np(T.run_oracle(case, dtype=torch.float64))
+        robust = np.abs(got["depth"] - w64["depth"])[:, 0] < 5e-6         # 10x tighter than there: the gate below is 1e-4, not 1e-3
+        assert robust.mean() >= 0.7
+        got, want = ({k: v[robust] for k, v in d.items()} for d in (got, want))
     stats = T.compare_outputs(got, want, label=f"oracle-vs-fixture[{name}]", **T.TOL_ORACLE_VS_REF[case["weights"]])
     assert stats["psnr_between"] > 80.0
 
