@@ -47,6 +47,12 @@ constexpr float INV_SQRT2 = 0.70710678f;
 constexpr int TC_MAX_JOBS = 208;                     // operand images per weight set (156 today)
 constexpr int TC_GENERATION_DEFAULT = 1;
 constexpr uint32_t TC_FENCE_MASK_DEFAULT = 0xFFu;     // every sub-chunk handed off on its own
+// fp16 MMA passes per logical product outside the forward layers (SdfTcParams::rev_passes / feat_passes).  The forward SDF needs the
+// 3-MMA split (its error is multiplied by inv_s ~ 400 in the NeuS alpha); the reverse sweep only feeds the normals and the cosine
+// in alpha, whose sensitivity is O(1): see DESIGN.md section 4 for the measured error of each setting.
+constexpr int TC_REV_PASSES_DEFAULT = 3;
+constexpr int TC_FEAT_PASSES_DEFAULT = 3;
+constexpr int TC_BWD_PASSES_DEFAULT = 3;              // sdf_bwd_tc_kernel (training backward): SdfBwdParams::passes
 constexpr float OS_F = 1.0f / (W_SCALE * ACT_SCALE);   // accumulator -> forward pre-activation
 constexpr float OS_R = 1.0f / W_SCALE;                 // accumulator -> reverse signal (stays in G_SCALE units)
 
@@ -207,6 +213,14 @@ __device__ __forceinline__ void store_split8s_hw(uint32_t s_hi, uint32_t s_lo, c
     sts128(s_hi, hw[0], hw[1], hw[2], hw[3]);
     sts128(s_lo, lw[0], lw[1], lw[2], lw[3]);
 }
+__device__ __forceinline__ void store_half8s_hw(uint32_t s_a, const float* x, uint32_t (&hw)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    sts128(s_a, hw[0], hw[1], hw[2], hw[3]);
+}
 __device__ __forceinline__ void store_half8s(uint32_t s_a, const float* x) {
     uint32_t hw[4];
 #pragma unroll
@@ -265,6 +279,9 @@ struct SdfTcParams {
     long long* tlog;                   // developer timeline (NRH_TC_TLOG): clock64 stamps of block 0, third tile
     uint32_t fmask;                    // hand-off steps of the epilogue (EpiT::fence_mask)
     int dbg;                           // developer ablations (NRH_TC_DEBUG): 1 = epilogue skips the math, 2 = no MMAs, 3 = no weight loads, 4 = neither
+    int rev_passes;                    // fp16 MMA passes per product of the REVERSE sweep: 3 = hi/lo split of both operands (as the forward),
+                                       // 2 = signal published as one fp16 tile (z_hi W_hi + z_hi W_lo), 1 = z_hi W_hi only
+    int feat_passes;                   // the same for the feature head (3 or 1): its result leaves as fp16 anyway
     // training tape (TRAIN instantiation only; see SdfTape in mlp_tc.cuh)
     uint8_t* tape_tiles;               // per tile: TAPE_TILE_BYTES (softplus' of the 8 layers, reverse adjoints g_1..g_7, g_e)
     __half* tape_act;                  // [8][P_pad][256] fp16: a_1 .. a_8 (x ACT_SCALE), row-major
@@ -318,6 +335,7 @@ struct EpiT {
     uint32_t off[2];                       // swizzled byte offset of this thread's 8 columns inside a chunk (even / odd sub-chunk)
     uint32_t s_hi, s_lo;                   // shared-space addresses of A_hi / A_lo
     long long* tl;                         // timeline slot of the current gemm (nullptr = off)
+    long long* tw;                         // developer timeline, every epilogue warp: [8] publish stamps of the logged layer (nullptr = off)
     // 8 values -> sub-chunk sc of the A operand (hi/lo split), then signal the MMA issuer (one arrival per warp).
     // NOTE: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it drains every outstanding memory
     // operation of the thread, so callers issue their global loads / stores right AFTER publish(), never before.
@@ -326,10 +344,13 @@ struct EpiT {
     // since the previous hand-off.  Sub-chunks 0 and 7 are always handed off on their own (they bound the pipeline bubble at both
     // ends of a layer).
     uint32_t fence_mask;
-    __device__ __forceinline__ void publish(int sc, const float* o) const {
+    bool rev_lo;                           // reverse-sweep operands are published as hi + lo tiles (SdfTcParams::rev_passes == 3)
+    // `lo` = false: the consumer gemm reads only the hi tile of this operand (reduced-pass reverse sweep), so the lo split is skipped
+    __device__ __forceinline__ void publish(int sc, const float* o, bool lo = true) const {
         const uint32_t o8 = (uint32_t)(sc >> 1) * A_CHUNK + off[sc & 1];
         uint32_t hw[4];
-        if (TRAIN) store_split8s_hw(s_hi + o8, s_lo + o8, o, hw);
+        if (!lo) store_half8s_hw(s_hi + o8, o, hw);
+        else if (TRAIN) store_split8s_hw(s_hi + o8, s_lo + o8, o, hw);
         else store_split8s(s_hi + o8, s_lo + o8, o);
         if ((fence_mask >> sc) & 1u) {
             fence_proxy_async_smem();
@@ -341,6 +362,7 @@ struct EpiT {
             }
         }
         if (TRAIN) { if (dump) *reinterpret_cast<uint4*>(dump + sc * 32 + gq * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]); }
+        if (tw && lane == 0) tw[sc] = clock64();
     }
 };
 using Epi = EpiT<false>;
@@ -422,7 +444,7 @@ __device__ __forceinline__ void epi_forward(const EP& E, WaitAcc&& wait_acc, int
         } else if (OUT == 2) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
-            E.publish(sc, v);
+            E.publish(sc, v, E.rev_lo);
         }
         if (E.tl) E.tl[4 + sc * 3] = clock64();
         // global traffic goes after the fence inside publish(): softplus' stores, bias of the sub-chunk after next
@@ -481,7 +503,7 @@ __device__ __forceinline__ void epi_feat(const EP& E, WaitAcc&& wait_acc, const 
         if (GRAD) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = w[i] * dsig_from_packed(s[i]) * (W_SCALE * G_SCALE / SDF_SCALE);
-            E.publish(sc, v);
+            E.publish(sc, v, E.rev_lo);
         }
     };
     step(vA, bA, vB, bB, 0);
@@ -534,7 +556,7 @@ __device__ __forceinline__ void epi_reverse(const EP& E, WaitAcc&& wait_acc, int
             }
             if (TRAIN) gpk[TRAIN ? i : 0] = pack_sig2(graw[0], graw[1]);
         }
-        E.publish(sc, v);
+        E.publish(sc, v, E.rev_lo);
         if (!TRAIN && E.discard) pk_discard(E.sig, l - 1, sc, E.gq, E.r);       // sg of this step has been consumed above
         if (TRAIN) pk_store(E.gnx, l - 1, sc, E.gq, E.r, gpk[0], gpk[TRAIN ? 1 : 0], gpk[TRAIN ? 2 : 0], gpk[TRAIN ? 3 : 0]);
         if (SKIP) {
@@ -605,7 +627,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     for (int img = 0; img < G.nsub; ++img, ++it) {
                         const uint32_t s = it % NSTAGES, u = it / NSTAGES;
                         mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                        if (NRH_DBG(P) >= 3) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
+                        if (NRH_DBG(P) == 3 || NRH_DBG(P) == 4) { mbar_arrive(&b_full[s]); continue; }      // ablation: no weight traffic (ncta == 1 only)
                         mbar_arrive_expect_tx(&b_full[s], G.img_bytes);
                         bulk_g2s(Bst + s * STAGE, P.tc + G.b_off + (size_t)img * G.img_bytes, G.img_bytes, &b_full[s]);
                     }
@@ -646,6 +668,8 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                     const Gemm G = get_gemm<GRAD, FEAT>(T, gi);
                     const uint32_t acc = tmem_base + (gc & 1) * 256;
                     const uint32_t idesc = make_idesc_f16(TM, G.n);
+                    // forward layers: always the 3-MMA split; feature head / reverse sweep: SdfTcParams::feat_passes / rev_passes
+                    const int passes = gi < SDF_LAYERS ? 3 : ((FEAT && gi == SDF_LAYERS) ? P.feat_passes : P.rev_passes);
                     const int lgi = (NRH_DBG(P) == 9) ? gi - 8 : gi;
                     const bool lg = lane == 0 && NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && lgi >= 0 && lgi < 8;
                     for (int sc = 0; sc < G.nsub; ++sc, ++it) {
@@ -666,7 +690,9 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
                             // A: K-steps 2 sc, 2 sc + 1 of the 64-wide chunk sc / 2 (32 B per K-step inside the swizzled rows)
                             const uint32_t ko = (uint32_t)(sc >> 1) * (A_CHUNK >> 4) + (uint32_t)(sc & 1) * 4;
                             const uint32_t ah = a_hi_lo + ko, al = a_lo_lo + ko, bl = b_lo0 + s * (STAGE >> 4);
-                            umma_group6_ss_w(acc, ah, al, bl, idesc, (uint32_t)(sc != 0));  // A_hi * W_hi, A_lo * W_hi, A_hi * W_lo behind one election
+                            if (passes == 3) umma_group6_ss_w(acc, ah, al, bl, idesc, (uint32_t)(sc != 0));  // A_hi * W_hi, A_lo * W_hi, A_hi * W_lo behind one election
+                            else if (passes == 2) umma_group4_ss_w(acc, ah, bl, idesc, (uint32_t)(sc != 0));  // A_hi * W_hi, A_hi * W_lo
+                            else umma_group2_ss_w(acc, ah, bl, idesc, (uint32_t)(sc != 0));                   // A_hi * W_hi
                         }
                         umma_commit_w(&b_empty[s]);
                         if (lg) NRH_TLOG(P)[lgi * 32 + sc * 3 + 2] = clock64();
@@ -678,8 +704,9 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
     } else if (warp >= EPI_WARP0) {
         // ======================= epilogue warps =======================
         EpiT<TRAIN> E;
-        E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr;
+        E.A_hi = A_hi; E.A_lo = A_lo; E.a_ready = a_ready; E.lane = lane; E.tl = nullptr; E.tw = nullptr;
         E.dump = nullptr; E.gnx = nullptr; E.fence_mask = P.fmask; E.discard = NRH_DBG(P) != 7;
+        E.rev_lo = P.rev_passes == 3;
         const int q = warp & 3;
         E.gq = (warp - EPI_WARP0) >> 2;
         E.r = q * 32 + lane;                                // row of the tile == TMEM lane
@@ -697,6 +724,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
         auto wait_acc = [&]() -> uint32_t {
             mbar_wait(&acc_full[gc & 1], (gc >> 1) & 1);
             tc_fence_after();
+            if (E.tw && lane == 0) E.tw[8] = clock64();
             const uint32_t a = tmem_base + lane_base + (gc & 1) * 256;
             ++gc;
             return a;
@@ -759,6 +787,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
 #pragma unroll 1
             for (int l = 0; l < SDF_LAYERS - 1; ++l) {
                 E.tl = (NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && warp == EPI_WARP0 + 2 && lane == 0) ? NRH_TLOG(P) + 256 + l * 32 : nullptr;
+                E.tw = (NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && l == 2) ? NRH_TLOG(P) + 512 + (warp - EPI_WARP0) * 16 : nullptr;
                 if (TRAIN) E.dump = P.tape_act + ((size_t)l * P.p_pad + p) * 256;            // this epilogue publishes a_{l+1}
                 if (l == SDF_SKIP - 1) epi_forward<GRAD, 1, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
                 else epi_forward<GRAD, 0, 1>(E, wait_acc, l, P.bias16 + l * 256, P.head_w, dot);
@@ -766,7 +795,7 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             }
             {
                 constexpr int OUT = FEAT ? 1 : (GRAD ? 2 : 0);
-                E.tl = nullptr;
+                E.tl = nullptr; E.tw = nullptr;
                 if (TRAIN) E.dump = P.tape_act + ((size_t)(SDF_LAYERS - 1) * P.p_pad + p) * 256;   // a_8
                 epi_forward<GRAD, 2, OUT>(E, wait_acc, SDF_LAYERS - 1, P.bias16 + (SDF_LAYERS - 1) * 256, P.head_w, dot);
                 tc_fence_before();
@@ -785,12 +814,14 @@ sdf_tc_kernel(SdfTcParams P, Strided3 pts, int64_t N, float* __restrict__ sdf_ou
             if (GRAD) {
 #pragma unroll 1
                 for (int l = SDF_LAYERS - 1; l >= 1; --l) {
+                    E.tw = (NRH_TLOG(P) && blockIdx.x == 0 && tile == tile0 + 2 * tstride && l == 5) ? NRH_TLOG(P) + 768 + (warp - EPI_WARP0) * 16 : nullptr;
                     if (TRAIN) E.dump = P.tape_u + ((size_t)(l - 1) * P.p_pad + p) * 256;           // publishes u_{l-1}
                     if (l == SDF_SKIP) epi_reverse<true, TRAIN>(E, wait_acc, l);
                     else epi_reverse<false, TRAIN>(E, wait_acc, l);
                     tc_fence_before();
                 }
                 // ---- reverse layer 0 + chain through the encoding (39 columns; quarter 0 warps) ----
+                E.tw = nullptr;
                 const uint32_t acc = wait_acc();
                 epi_bar_sync();                       // ge_s written by other threads in the R4 epilogue
                 if (gq == 0) {
@@ -1263,6 +1294,10 @@ int tc_pack(const NrhConfig& cfg, const PackedLayout& L, const NrhRawWeights& ra
 // epilogue hand-off steps (bit sc = fence after sub-chunk sc; bits 0 and 7 are forced) and engine generation
 static uint32_t tc_fence_mask() { return (dev_options().fmask & 0xFFu) | 0x81u; }
 static int tc_generation() { return dev_options().gen; }
+// developer build: dbg 10 / 11 = reverse sweep with 2 / 1 passes, 12 / 13 = the same with a single-pass feature head, 14 = 3 + 1
+static int tc_rev_passes() { const int d = dev_options().dbg; return d == 10 || d == 12 ? 2 : (d == 11 || d == 13 ? 1 : (d == 14 ? 3 : TC_REV_PASSES_DEFAULT)); }
+static int tc_bwd_passes() { const int d = dev_options().dbg; return d == 20 ? 2 : (d == 21 ? 1 : (d == 22 ? 3 : TC_BWD_PASSES_DEFAULT)); }   // dev: dbg 20 / 21 / 22
+static int tc_feat_passes() { const int d = dev_options().dbg; return d == 12 || d == 13 || d == 14 ? 1 : (d == 10 || d == 11 ? 3 : TC_FEAT_PASSES_DEFAULT); }
 
 int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t N,
                float* sdf, float* gx, float* gy, float* gz, int64_t grad_stride, float* feat, bool feat_as_image,
@@ -1277,8 +1312,9 @@ int sdf_mlp_tc(const void* packed, const PackedLayout& L, Strided3 pts, int64_t 
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
     P.tape_tiles = nullptr; P.tape_act = nullptr; P.tape_u = nullptr; P.p_pad = 0;
-    P.dbg = dev_options().dbg; P.tlog = dev_options().tlog;
+    P.dbg = dev_options().dbg >= 10 ? 0 : dev_options().dbg; P.tlog = dev_options().tlog;   // codes >= 10 select pass counts (tc_rev_passes)
     P.fmask = tc_fence_mask();
+    P.rev_passes = tc_rev_passes(); P.feat_passes = tc_feat_passes();
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (scratch_bytes < tc_scratch_bytes(grid)) { set_error("sdf_mlp_tc: scratch too small"); return NRH_ERR_WORKSPACE; }
@@ -1339,6 +1375,7 @@ int sdf_train_forward_tc_strided(const void* packed, const PackedLayout& L, Stri
     P.bias16 = reinterpret_cast<const float*>(P.tc + tc_layout().sdf_bias16);
     P.head_w = Pf + L.head_w; P.head_b = Pf + L.head_b; P.feat_b = Pf + L.feat_b;
     P.dbg = 0; P.tlog = nullptr; P.fmask = tc_fence_mask();
+    P.rev_passes = tc_rev_passes(); P.feat_passes = tc_feat_passes();
     uint8_t* tb = reinterpret_cast<uint8_t*>(tape);
     P.tape_tiles = tb + TL.tape_tiles_off;
     P.tape_act = reinterpret_cast<__half*>(tb + TL.tape_act_off);
@@ -1383,6 +1420,7 @@ int sdf_train_backward_tc(const void* packed, const PackedLayout& L, const float
     P.zb = reinterpret_cast<__half*>(ob + TL.bwd_zb_off);
     P.d_pts = d_pts;
     P.p_pad = TL.p_pad; P.fmask = tc_fence_mask();
+    P.passes = tc_bwd_passes();
     const int64_t ntiles = (N + TM - 1) / TM;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     Strided3 S3{pts, pts + 1, pts + 2, 3};

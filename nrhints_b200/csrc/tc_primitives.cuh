@@ -233,6 +233,36 @@ __device__ __forceinline__ void umma_group6_ss_w(uint32_t d_tmem, uint32_t a_hi,
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b3, %4, 1;\n\t}"
         ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
 }
+// two-pass form of the above: A_hi * W_hi + A_hi * W_lo (the A operand is published as a single fp16 tile; reverse sweep)
+__device__ __forceinline__ void umma_group4_ss_w(uint32_t d_tmem, uint32_t a_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 b0, b1, b2, b3, h0, h1;\n\t.reg .b32 t;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 b0, {%2, %5};\n\t"
+        "add.u32 t, %2, 2;\n\tmov.b64 b1, {t, %5};\n\t"
+        "add.u32 t, %2, 4;\n\tmov.b64 b2, {t, %5};\n\t"
+        "add.u32 t, %2, 6;\n\tmov.b64 b3, {t, %5};\n\t"
+        "mov.b64 h0, {%1, %5};\n\tadd.u32 t, %1, 2;\n\tmov.b64 h1, {t, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h0, b0, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h0, b2, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b3, %3, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a_hi), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
+// single-pass form: A_hi * W_hi only (the W_lo half of the image is streamed but not used)
+__device__ __forceinline__ void umma_group2_ss_w(uint32_t d_tmem, uint32_t a_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 b0, b1, h0, h1;\n\t.reg .b32 t;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 b0, {%2, %5};\n\t"
+        "add.u32 t, %2, 2;\n\tmov.b64 b1, {t, %5};\n\t"
+        "mov.b64 h0, {%1, %5};\n\tadd.u32 t, %1, 2;\n\tmov.b64 h1, {t, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h0, b0, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], h1, b1, %3, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a_hi), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
