@@ -240,7 +240,8 @@ class FusedTrainStep:
         ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
         adj = _lib.NrhTrainAdjoints(self._d_rgb.data_ptr(), self._d_n.data_ptr(), None, None, ptr(g[0]), ptr(g[1]), ptr(g[2]))
         run_backward(rn, cfg, packed, P, rays, R, bgf, cos_anneal, adj, self._ws)
-        res = dict(stats=self._stats, rgb=out["rgb"], s_val=(1.0 / out["inv_s"]).reshape(()))
+        # owned copy (one 32-byte launch): the statistics buffer is rewritten by the next step, and callers keep loss values in lists
+        res = dict(stats=self._stats.clone(), rgb=out["rgb"], s_val=(1.0 / out["inv_s"]).reshape(()))
         if need_ray_grads:
             res.update(d_origins=g[0], d_directions=g[1], d_pl_positions=g[2])
         return res

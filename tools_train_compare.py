@@ -17,6 +17,15 @@ carry noise (RayGeneratorConfig.cam_position_noise_std / cam_orientation_noise_s
 The schedule constants are shortened in proportion to the run (warm_up_end, anneal_end, end_iter), identically for every arm.
 
     python tools_train_compare.py --steps 1000 --out profiles/r2_train_compare.json
+
+Data parallel (the reference's DDP semantics, trainer/trainer.py:88-93,118: the SAME global batch split `batch // world_size` per
+rank, gradients averaged by one all-reduce per step): launch the `native` arm under torchrun --
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools_train_compare.py --steps 1000 --arms native --out profiles/r2_train_compare_2gpu.json
+
+every rank renders the ground truth (deterministic), draws the identical batch sequence and takes its contiguous slice; the step is
+NRHintPipeline.train_step with grad_sync.allreduce_flat on FlatAdam's flat gradient buffers; rank 0 evaluates and reports.
 """
 import argparse
 import json
@@ -52,7 +61,16 @@ def main():
     ap.add_argument("--preset", default="NRHintsCamOpt", choices=["NRHints", "NRHintsCamOpt"])
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    dev = torch.device("cuda")
+    import os
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+        assert args.arms == "native", "only the native arm is data parallel (the reference arms need its own DDP trainer)"
+        assert args.batch % world == 0
+    dev = torch.device("cuda", torch.cuda.current_device())
     import ref_loader
     import nrh_testlib as T
     import nrhints_b200 as nb
@@ -157,12 +175,25 @@ def main():
         gen = batches()
         losses, psnrs = [], []
         psnr0 = evaluate(pipe)
-        torch.manual_seed(17); torch.cuda.manual_seed(17)
+        torch.manual_seed(17 + rank); torch.cuda.manual_seed(17 + rank)
+        sync = None
+        if world > 1:
+            from nrhints_b200.grad_sync import allreduce_flat
+            sync = lambda: allreduce_flat(opt.flat_grads())      # noqa: E731
+            per = args.batch // world
         t_start = None
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for step in range(S):
             if step == S // 10:
                 torch.cuda.synchronize(); ev_a.record()
+            if world > 1:                                   # this rank's contiguous slice of the global batch; fused step + one all-reduce
+                pb = mk({k: v[rank * per:(rank + 1) * per] for k, v in next(gen).items()})
+                with torch.device(dev):
+                    ld = pipe.train_step(pb, global_step=step, optimizer=opt, grad_sync=sync)
+                sched.step()
+                losses.append(ld["loss"].detach())
+                psnrs.append(ld["psnr"].detach())
+                continue
             pb = mk(next(gen))
             with torch.device(dev):
                 res = pipe(pb, global_step=step)
@@ -175,8 +206,11 @@ def main():
             psnrs.append(ld["psnr"] if torch.is_tensor(ld["psnr"]) else torch.tensor(ld["psnr"], device=dev))
         ev_b.record(); torch.cuda.synchronize()
         ms = ev_a.elapsed_time(ev_b) / (S - S // 10)
-        L = torch.stack(losses).float().cpu().numpy()
-        P = torch.stack([p.float().reshape(()) for p in psnrs]).cpu().numpy()
+        Lt, Pt = torch.stack(losses).float(), torch.stack([p.float().reshape(()) for p in psnrs])
+        if world > 1:                                       # report the mean over ranks (= the loss of the global batch) and the slowest rank
+            dist.all_reduce(Lt); dist.all_reduce(Pt); Lt /= world; Pt /= world
+            mt = torch.tensor([ms], device=dev); dist.all_reduce(mt, op=dist.ReduceOp.MAX); ms = float(mt)
+        L, P = Lt.cpu().numpy(), Pt.cpu().numpy()
         k = max(S // 100, 1)
         results[arm] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "rays_per_s": args.batch * 1e3 / ms,
                         "loss_curve": [float(L[i:i + k].mean()) for i in range(0, S, k)],
@@ -189,7 +223,10 @@ def main():
               file=sys.stderr)
         del pipe, opt
         torch.cuda.empty_cache()
-    summary = {"config": {"preset": args.preset, "steps": S, "batch": args.batch, "views": n_views, "res": args.res, **model_kw, **rg_kw,
+    if rank != 0:
+        dist.barrier(); dist.destroy_process_group()
+        return
+    summary = {"config": {"preset": args.preset, "steps": S, "batch": args.batch, "world_size": world, "views": n_views, "res": args.res, **model_kw, **rg_kw,
                           "curve_bin_steps": max(S // 100, 1)}, "arms": results}
     if "ref" in results:
         for arm in results:
@@ -206,6 +243,8 @@ def main():
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
         Path(args.out).write_text(txt + "\n")
     print(txt)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
 
 
 if __name__ == "__main__":
