@@ -113,8 +113,13 @@ NRH_HD float interval_alpha(const float o[3], const float d[3], int j, CSoA z, C
     return (prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f);
 }
 
-// wbuf holds the k-1 alphas on entry and is overwritten with the weights (+1e-5).
-NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
+// The sampler of one importance step in three parts, so that the kernel can run the middle one on all its threads:
+//   weights_from_alphas : wbuf[j] (k-1 alphas) -> w_j = alpha_j * T_j + 1e-5 (exclusive transmittance product), returns sum w
+//   normalize_weights   : wbuf[j] -> w_j / wsum   (the pdf; one IEEE division per interval, independent of each other)
+//   inverse_cdf_samples : running cdf over the pdf + inverse CDF at u = linspace(0,1,n_new)  (:21-65)
+// `c_below + w / wsum` of the one-piece formulation is a division followed by an addition (nothing to contract), so hoisting
+// the divisions out of the walk leaves every bit unchanged.
+NRH_HD float weights_from_alphas(int k, SoA wbuf) {
     float T = 1.0f, wsum = 0.0f;
     for (int j = 0; j + 1 < k; ++j) {
         const float alpha = wbuf[j];
@@ -123,7 +128,13 @@ NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
         wbuf[j] = w;
         wsum += w;
     }
-    // inverse CDF at u = linspace(0,1,n_new); cdf has k entries, cdf[0]=0.
+    return wsum;
+}
+NRH_HD void normalize_weights(int k, SoA wbuf, float wsum) {
+    for (int j = 0; j + 1 < k; ++j) wbuf[j] = wbuf[j] / wsum;
+}
+NRH_HD void inverse_cdf_samples(int k, CSoA z, int n_new, CSoA pdf, SoA z_new) {
+    // cdf has k entries, cdf[0]=0.
     int m = 0;                 // running searchsorted(right=True) result
     float c_m = 0.0f;          // cdf[m]
     float c_below = 0.0f;      // cdf[m-1]
@@ -132,7 +143,7 @@ NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
         while (m < k && c_m <= u) {
             c_below = c_m;
             ++m;
-            if (m < k) c_m = c_below + wbuf[m - 1] / wsum;
+            if (m < k) c_m = c_below + pdf[m - 1];
         }
         const int below = m - 1 > 0 ? m - 1 : 0;
         const int above = m < k - 1 ? m : k - 1;
@@ -143,6 +154,12 @@ NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
         const float zb = z[below], za = z[above];
         z_new[t] = zb + tt * (za - zb);
     }
+}
+// wbuf holds the k-1 alphas on entry and is overwritten with the pdf.
+NRH_HD void sample_from_alphas(int k, CSoA z, int n_new, SoA wbuf, SoA z_new) {
+    const float wsum = weights_from_alphas(k, wbuf);
+    normalize_weights(k, wbuf, wsum);
+    inverse_cdf_samples(k, z, n_new, CSoA{wbuf.p, wbuf.stride}, z_new);
 }
 
 NRH_HD void upsample_new_z(const float o[3], const float d[3], int k, CSoA z, CSoA sdf,
@@ -170,6 +187,19 @@ NRH_HD void merge_sorted(int k, CSoA z_old, CSoA s_old, int n, CSoA z_new, CSoA 
             ++b; if (b < n) zb = z_new[b];
         }
     }
+}
+
+// Parallel form of the same stable merge (ties: old first): the final slot of old entry a is a + #{new < z_old[a]}, that of new
+// entry b is k + ... = b + #{old <= z_new[b]}; every (ray, entry) pair can compute its slot on its own.
+NRH_HD int count_less(CSoA v, int n, float x) {           // #{i < n : v[i] < x}, v ascending
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+NRH_HD int count_less_equal(CSoA v, int n, float x) {     // #{i < n : v[i] <= x}
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] <= x) lo = mid + 1; else hi = mid; }
+    return lo;
 }
 
 // The same merge, in place and from the back: z/s hold the k old entries in slots [0,k) and have room for

@@ -50,6 +50,42 @@ constexpr size_t IS_SMEM = (size_t)IS_ROWS * IS_RAYS * sizeof(float);
 // A CTA owns 64 rays.  Data movement and the per-interval alphas (two precise sigmoids + three divisions each, the bulk
 // of the arithmetic) are spread over all 512 threads; the short sequential parts (merge, prefix products, cdf walk)
 // run one thread per ray on the shared-memory copies.  Arithmetic and its order are exactly those of ray_math.cuh.
+// Stable merge of the n_new sorted new entries (szn / ssn) into the k_old sorted old ones (sz / ss), in place, on ALL threads: every
+// (ray, entry) pair finds its own slot by binary search in the other run (ray_math.cuh: count_less / count_less_equal), all slots
+// are computed before any is written.  Same result as merge_sorted / merge_sorted_backward (tests/test_ray_math_host.py).
+constexpr int IS_ITEMS = NRH_MAX_SAMPLES * IS_RAYS / IS_THREADS;           // (ray, entry) pairs per thread
+__device__ __forceinline__ void merge_parallel(int tid, int nr, int k_old, int n_new, float* sz, float* ss, const float* szn,
+                                               const float* ssn, bool with_sdf) {
+    float vz[IS_ITEMS], vs[IS_ITEMS];
+    int vp[IS_ITEMS];
+    const int total = (k_old + n_new) * IS_RAYS;
+#pragma unroll
+    for (int i = 0; i < IS_ITEMS; ++i) {
+        const int idx = tid + i * IS_THREADS;
+        vp[i] = -1; vz[i] = 0.f; vs[i] = 0.f;
+        if (idx < total) {
+            const int j = idx / IS_RAYS, t = idx % IS_RAYS;
+            if (t < nr) {
+                if (j < k_old) {
+                    vz[i] = sz[idx];
+                    if (with_sdf) vs[i] = ss[idx];
+                    vp[i] = (j + count_less(CSoA{szn + t, IS_RAYS}, n_new, vz[i])) * IS_RAYS + t;
+                } else {
+                    const int b = j - k_old;
+                    vz[i] = szn[b * IS_RAYS + t];
+                    if (with_sdf) vs[i] = ssn[b * IS_RAYS + t];
+                    vp[i] = (b + count_less_equal(CSoA{sz + t, IS_RAYS}, k_old, vz[i])) * IS_RAYS + t;
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IS_ITEMS; ++i)
+        if (vp[i] >= 0) { sz[vp[i]] = vz[i]; if (with_sdf) ss[vp[i]] = vs[i]; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(IS_THREADS)
 k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool merge_first,
                   float inv_s, bool last, float last_dist_const, const float* last_dist_ray) {
@@ -74,14 +110,11 @@ k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool m
         }
     __syncthreads();
     int k = k_old;
-    // ---- phase 1: merge the samples drawn by the previous step (one thread per ray) ----
+    // ---- phase 1: merge the samples drawn by the previous step (all threads) ----
     if (merge_first) {
-        if (tid < nr)
-            merge_sorted_backward(k_old, SoA{sz + tid, IS_RAYS}, SoA{ss + tid, IS_RAYS}, n_new, CSoA{szn + tid, IS_RAYS},
-                                  CSoA{ssn + tid, IS_RAYS}, true);
+        merge_parallel(tid, nr, k_old, n_new, sz, ss, szn, ssn, true);
         k = k_old + n_new;
         cur ^= 1;
-        __syncthreads();
         if (!last)
             for (int idx = tid; idx < k * IS_RAYS; idx += IS_THREADS) {
                 const int j = idx / IS_RAYS, t = idx % IS_RAYS;
@@ -98,14 +131,19 @@ k_importance_step(int64_t R, MarchState m, int cur, int k_old, int n_new, bool m
         }
     }
     __syncthreads();
-    // ---- phase 3: weights, cdf, inverse-CDF samples (one thread per ray); last step: final merge ----
-    if (tid < nr) {
-        sample_from_alphas(k, CSoA{sz + tid, IS_RAYS}, n_new, SoA{sw + tid, IS_RAYS}, SoA{szn + tid, IS_RAYS});
-        if (last)
-            merge_sorted_backward(k, SoA{sz + tid, IS_RAYS}, SoA{ss + tid, IS_RAYS}, n_new, CSoA{szn + tid, IS_RAYS},
-                                  CSoA{nullptr, 0}, false);
+    // ---- phase 3: sample_from_alphas in its three parts: transmittance product + weights (one thread per ray: a 2-flop chain),
+    //      the k - 1 divisions by the weight sum (all threads), the cdf walk (one thread per ray: adds and compares only);
+    //      last step: final merge of the positions (all threads) ----
+    if (tid < nr) ssn[tid] = weights_from_alphas(k, SoA{sw + tid, IS_RAYS});      // ssn is free after phase 1
+    __syncthreads();
+    for (int idx = tid; idx < (k - 1) * IS_RAYS; idx += IS_THREADS) {
+        const int t = idx % IS_RAYS;
+        if (t < nr) sw[idx] = sw[idx] / ssn[t];
     }
     __syncthreads();
+    if (tid < nr) inverse_cdf_samples(k, CSoA{sz + tid, IS_RAYS}, n_new, CSoA{sw + tid, IS_RAYS}, SoA{szn + tid, IS_RAYS});
+    __syncthreads();
+    if (last) merge_parallel(tid, nr, k, n_new, sz, ss, szn, ssn, false);
     // ---- phase 4: write back (all threads) ----
     if (!last) {
         for (int idx = tid; idx < n_new * IS_RAYS; idx += IS_THREADS) {
@@ -149,20 +187,50 @@ __global__ void k_sections_only(int64_t R, MarchState m, int cur, int S, float l
     }
 }
 
+// ---- staging for the one-thread-per-ray compositors ----------------------------------------------------------------------
+// composite_primary / shadow_transmittance walk 128 samples per ray with a short dependent chain (the transmittance) and five
+// loads per step; with one thread per ray straight on the global arrays every step paid an exposed L2 round trip (131 us / 109 us
+// for 4096 rays, ncu r2q).  A CTA of ST_THREADS threads therefore first copies the sample-major input arrays of its ST_RAYS rays
+// into shared memory (coalesced 128-byte rows, all loads in flight at once), then one warp runs the UNCHANGED ray_math.cuh function
+// on the shared-memory views: same arithmetic, same order, bitwise the same results.
+constexpr int ST_RAYS = 32;
+constexpr int ST_THREADS = 256;
+__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float* __restrict__ src, int S, int64_t R, int64_t r0, int nr) {
+    for (int idx = threadIdx.x; idx < S * ST_RAYS; idx += ST_THREADS) {
+        const int j = idx / ST_RAYS, t = idx % ST_RAYS;
+        if (t < nr) dst[idx] = src[(int64_t)j * R + r0 + t];
+    }
+}
+inline size_t staged_smem(int S) { return (size_t)5 * S * ST_RAYS * sizeof(float); }
+inline int staged_blocks(int64_t R) { return (int)((R + ST_RAYS - 1) / ST_RAYS); }
+
 // ---- primary composite + shadow-ray setup ----------------------------------------------------------
-__global__ void k_composite_primary(int64_t R, MarchState m, int cur, int S, float last_dist,
+__global__ void __launch_bounds__(ST_THREADS)
+k_composite_primary(int64_t R, MarchState m, int cur, int S, float last_dist,
                                     const float* __restrict__ inv_s_ptr, float cos_anneal, FineBuffers f,
                                     RayState rs, const float* __restrict__ pl, bool do_shadow, MarchState sh,
                                     int n_shadow, float shadow_offset, const float* __restrict__ jitter_shadow,
                                     int depth_type, const float* __restrict__ hit_pts, const float* __restrict__ hit_depth,
                                     int n_out, OutsideBuffers ob) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= R) return;
+    extern __shared__ float st_sm[];
+    const int64_t r0 = blockIdx.x * (int64_t)ST_RAYS;
+    const int nr = (int)((R - r0) < ST_RAYS ? (R - r0) : ST_RAYS);
+    const int rows = S * ST_RAYS;
+    stage_rows(st_sm, m.z[cur], S, R, r0, nr);
+    stage_rows(st_sm + rows, f.sdf, S, R, r0, nr);
+    stage_rows(st_sm + 2 * rows, f.gx, S, R, r0, nr);
+    stage_rows(st_sm + 3 * rows, f.gy, S, R, r0, nr);
+    stage_rows(st_sm + 4 * rows, f.gz, S, R, r0, nr);
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= nr) return;
+    const int64_t r = r0 + t;
     float o[3], d[3];
     for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
     const float inv_s = inv_s_ptr[0];
-    PrimaryComposite pc = composite_primary(o, d, S, CSoA{m.z[cur] + r, R}, last_dist, CSoA{f.sdf + r, R},
-                                            CSoA{f.gx + r, R}, CSoA{f.gy + r, R}, CSoA{f.gz + r, R}, inv_s, cos_anneal,
+    PrimaryComposite pc = composite_primary(o, d, S, CSoA{st_sm + t, ST_RAYS}, last_dist, CSoA{st_sm + rows + t, ST_RAYS},
+                                            CSoA{st_sm + 2 * rows + t, ST_RAYS}, CSoA{st_sm + 3 * rows + t, ST_RAYS},
+                                            CSoA{st_sm + 4 * rows + t, ST_RAYS}, inv_s, cos_anneal,
                                             SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R},
                                             n_out, CSoA{n_out > 0 ? ob.density + r : nullptr, R}, CSoA{n_out > 0 ? ob.dist + r : nullptr, R});
     float hit[3], hn[3];
@@ -216,18 +284,33 @@ __global__ void k_specular_cue(int64_t R, NrhConfig cfg, RayState rs, const floa
 }
 
 // ---- shadow transmittance, per-ray reflectance inputs ---------------------------------------------------------
-__global__ void k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, int S_shadow,
+__global__ void __launch_bounds__(ST_THREADS)
+k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, int S_shadow,
                              const float* __restrict__ inv_s_ptr, float cos_anneal, const float* __restrict__ ssdf,
                              const float* __restrict__ sgx, const float* __restrict__ sgy, const float* __restrict__ sgz,
                              RayState rs, const float* __restrict__ pl, const float* __restrict__ dirs, int warmup,
                              bool shadow_marched, float* __restrict__ rayfeat, unsigned char* __restrict__ aux_img) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= R) return;
+    extern __shared__ float st_sm[];
+    const int64_t r0 = blockIdx.x * (int64_t)ST_RAYS;
+    const int nr = (int)((R - r0) < ST_RAYS ? (R - r0) : ST_RAYS);
+    const int rows = S_shadow * ST_RAYS;
+    if (shadow_marched) {                                 // kernel argument: uniform over the grid
+        stage_rows(st_sm, sh.z[cur], S_shadow, R, r0, nr);
+        stage_rows(st_sm + rows, ssdf, S_shadow, R, r0, nr);
+        stage_rows(st_sm + 2 * rows, sgx, S_shadow, R, r0, nr);
+        stage_rows(st_sm + 3 * rows, sgy, S_shadow, R, r0, nr);
+        stage_rows(st_sm + 4 * rows, sgz, S_shadow, R, r0, nr);
+        __syncthreads();
+    }
+    const int t = threadIdx.x;
+    if (t >= nr) return;
+    const int64_t r = r0 + t;
     float vis = 0.f;
     if (shadow_marched) {
         float sd[3] = {sh.d[0][r], sh.d[1][r], sh.d[2][r]};
-        vis = shadow_transmittance(sd, S_shadow, CSoA{sh.z[cur] + r, R}, rs.light_dist[r], CSoA{ssdf + r, R},
-                                   CSoA{sgx + r, R}, CSoA{sgy + r, R}, CSoA{sgz + r, R}, inv_s_ptr[0], cos_anneal);
+        vis = shadow_transmittance(sd, S_shadow, CSoA{st_sm + t, ST_RAYS}, rs.light_dist[r], CSoA{st_sm + rows + t, ST_RAYS},
+                                   CSoA{st_sm + 2 * rows + t, ST_RAYS}, CSoA{st_sm + 3 * rows + t, ST_RAYS},
+                                   CSoA{st_sm + 4 * rows + t, ST_RAYS}, inv_s_ptr[0], cos_anneal);
     }
     rs.vis[r] = vis;
     float d[3] = {dirs[r * 3 + 0], dirs[r * 3 + 1], dirs[r * 3 + 2]};
@@ -360,6 +443,10 @@ int launch_coarse_primary(const NrhRays& rays, int64_t R, int n, const float* ji
 int launch_importance_step(int64_t R, const MarchState& m, int cur, int k_old, int n_new, bool merge_first, float inv_s,
                            bool last, float last_dist_const, const float* last_dist_ray, cudaStream_t st) {
     if (n_new > IS_NEW) { set_error("importance step draws at most %d samples per step", IS_NEW); return NRH_ERR_UNSUPPORTED; }
+    const int k_after = k_old + (merge_first ? n_new : 0);            // merge_parallel handles at most NRH_MAX_SAMPLES entries per ray
+    if (k_after + (last ? n_new : 0) > NRH_MAX_SAMPLES) {
+        set_error("importance step: more than %d samples per ray", NRH_MAX_SAMPLES); return NRH_ERR_UNSUPPORTED;
+    }
     NRH_CUDA_CHECK(cudaFuncSetAttribute(k_importance_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_SMEM));
     k_importance_step<<<(unsigned)((R + IS_RAYS - 1) / IS_RAYS), IS_THREADS, IS_SMEM, st>>>(R, m, cur, k_old, n_new, merge_first, inv_s, last, last_dist_const, last_dist_ray);
     NRH_LAUNCH_CHECK();
@@ -377,9 +464,11 @@ int launch_composite_primary(int64_t R, const MarchState& m, int cur, int S, flo
                              const MarchState& sh, int n_shadow, float shadow_offset, const float* jitter_shadow,
                              int depth_type, const float* hit_pts, const float* hit_depth, int n_out, const OutsideBuffers& ob,
                              cudaStream_t st) {
-    k_composite_primary<<<blocks_for(R), TPB, 0, st>>>(R, m, cur, S, last_dist, inv_s, cos_anneal, f, rs, pl, do_shadow, sh,
-                                                       n_shadow, shadow_offset, jitter_shadow, depth_type, hit_pts, hit_depth,
-                                                       n_out, ob);
+    if (S > NRH_MAX_SAMPLES) { set_error("composite: more than %d samples per ray", NRH_MAX_SAMPLES); return NRH_ERR_UNSUPPORTED; }
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(k_composite_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem(NRH_MAX_SAMPLES)));
+    k_composite_primary<<<staged_blocks(R), ST_THREADS, staged_smem(S), st>>>(R, m, cur, S, last_dist, inv_s, cos_anneal, f, rs, pl, do_shadow,
+                                                                              sh, n_shadow, shadow_offset, jitter_shadow, depth_type, hit_pts,
+                                                                              hit_depth, n_out, ob);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }
@@ -408,8 +497,10 @@ int launch_shade_prep(int64_t R, const NrhConfig& cfg, const MarchState& sh, int
                       float cos_anneal, const float* ssdf, const float* sgx, const float* sgy, const float* sgz,
                       const RayState& rs, const float* pl, const float* dirs, int warmup, bool shadow_marched,
                       float* rayfeat, unsigned char* aux_img, cudaStream_t st) {
-    k_shade_prep<<<blocks_for(R), TPB, 0, st>>>(R, cfg, sh, cur, S_shadow, inv_s, cos_anneal, ssdf, sgx, sgy, sgz, rs, pl, dirs,
-                                                warmup, shadow_marched, rayfeat, aux_img);
+    if (S_shadow > NRH_MAX_SAMPLES) { set_error("shade prep: more than %d shadow samples per ray", NRH_MAX_SAMPLES); return NRH_ERR_UNSUPPORTED; }
+    NRH_CUDA_CHECK(cudaFuncSetAttribute(k_shade_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem(NRH_MAX_SAMPLES)));
+    k_shade_prep<<<staged_blocks(R), ST_THREADS, shadow_marched ? staged_smem(S_shadow) : 0, st>>>(
+        R, cfg, sh, cur, S_shadow, inv_s, cos_anneal, ssdf, sgx, sgy, sgz, rs, pl, dirs, warmup, shadow_marched, rayfeat, aux_img);
     NRH_LAUNCH_CHECK();
     return NRH_OK;
 }

@@ -32,6 +32,12 @@ void h_merge_backward(int k, float* z, float* s, int n, const float* z_new, cons
     merge_sorted_backward(k, SoA{z, 1}, SoA{s, 1}, n, CSoA{z_new, 1}, CSoA{s_new, 1}, with_sdf != 0);
 }
 
+// the rank form of the stable merge (what the importance kernel runs on all its threads): every entry computes its own slot
+void h_merge_rank(int k, const float* z_old, const float* s_old, int n, const float* z_new, const float* s_new, float* z_out, float* s_out) {
+    for (int a = 0; a < k; ++a) { const int pos = a + count_less(CSoA{z_new, 1}, n, z_old[a]); z_out[pos] = z_old[a]; s_out[pos] = s_old[a]; }
+    for (int b = 0; b < n; ++b) { const int pos = b + count_less_equal(CSoA{z_old, 1}, k, z_new[b]); z_out[pos] = z_new[b]; s_out[pos] = s_new[b]; }
+}
+
 void h_sections(const float* z, int S, float last_dist, float* dist, float* mid) {
     for (int j = 0; j < S; ++j) section(CSoA{z, 1}, j, S, last_dist, dist[j], mid[j]);
 }

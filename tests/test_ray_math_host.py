@@ -120,6 +120,28 @@ def test_merge_backward_equals_forward(hlib):
         np.testing.assert_array_equal(sb, sf)
 
 
+def test_merge_rank_equals_forward(hlib):
+    """the rank form of the merge (every entry computes its own slot; k_importance_step runs it on all threads) == the sequential
+    stable merge, ties between and inside the runs included"""
+    g = torch.Generator().manual_seed(13)
+    for trial in range(40):
+        k, n = 64 + 16 * (trial % 4), (16 if trial % 3 else 5)
+        zo, _ = torch.sort(torch.rand(k, generator=g))
+        zn, _ = torch.sort(torch.rand(n, generator=g))
+        if trial % 2:                       # force ties: new == old, duplicates inside both runs, both ends
+            zn[1] = zo[10]; zn[2] = zo[10]; zn[-1] = zo[-1]; zn[0] = zo[0]; zo[20] = zo[21]
+            zn, _ = torch.sort(zn); zo, _ = torch.sort(zo)
+        if trial % 5 == 0:                  # all new entries below / above every old one
+            zn = zn * 0.0 - 1.0 if trial % 10 == 0 else zn * 0.0 + 2.0
+        so, sn = torch.randn(k, generator=g), torch.randn(n, generator=g)
+        zf, sf = np.empty(k + n, np.float32), np.empty(k + n, np.float32)
+        hlib.h_merge(k, _p(f32(zo)), _p(f32(so)), n, _p(f32(zn)), _p(f32(sn)), _p(zf), _p(sf), 1)
+        zr, sr = np.full(k + n, np.nan, np.float32), np.full(k + n, np.nan, np.float32)
+        hlib.h_merge_rank(k, _p(f32(zo)), _p(f32(so)), n, _p(f32(zn)), _p(f32(sn)), _p(zr), _p(sr))
+        np.testing.assert_array_equal(zr, zf)
+        np.testing.assert_array_equal(sr, sf)
+
+
 @pytest.mark.parametrize("cos_anneal", [1.0, 0.5])
 def test_composite_primary(hlib, cos_anneal):
     S = 128
