@@ -314,31 +314,38 @@ struct PrimaryComposite {
 // With the outside model (n_out > 0; bg_density / bg_dist hold S + n_out entries from render_outside) the NeuS alpha is
 // replaced by the background alpha outside the unit sphere and the n_out far samples are appended (:517-519);
 // w_out then has S + n_out entries, depth / normals still use the first S (`neus_weights`, :525).
-NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], int S, CSoA z, float last_dist,
-                                          CSoA sdf, CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal,
-                                          SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz,
-                                          int n_out = 0, CSoA bg_density = CSoA{nullptr, 0}, CSoA bg_dist = CSoA{nullptr, 0}) {
-    PrimaryComposite r; r.wsum = 0.f; r.depth = 0.f; r.nsum[0] = r.nsum[1] = r.nsum[2] = 0.f;
+// composite_primary in two parts, so that the kernel can evaluate the per-sample terms (two sigmoids, four divisions, two square roots
+// per sample, independent of each other) on all its threads and keep only the transmittance scan on one thread per ray:
+//   composite_sample     : alpha of sample j (blended with the background alpha outside the unit sphere), inside flag, unit normal
+//   composite_accumulate : w = alpha * T, T update, running sums / arg-max -- in sample order
+struct SampleTerms { float a, inside, n0, n1, n2, mid; };
+NRH_HD SampleTerms composite_sample(const float o[3], const float d[3], int S, CSoA z, int j, float last_dist, float sdf_j,
+                                    float g0, float g1, float g2, float inv_s, float cos_anneal, int n_out, float bg_density_j, float bg_dist_j) {
+    SampleTerms t;
+    float dist; section(z, j, S, last_dist, dist, t.mid);
+    const float px = o[0] + d[0] * t.mid, py = o[1] + d[1] * t.mid, pz = o[2] + d[2] * t.mid;
+    float a = neus_alpha(sdf_j, g0, g1, g2, d, dist, inv_s, cos_anneal);
+    t.inside = norm3(px, py, pz) < 1.0f ? 1.0f : 0.0f;
+    if (n_out > 0) a = a * t.inside + outside_alpha(bg_density_j, bg_dist_j) * (1.0f - t.inside);
+    t.a = a;
+    const float gn = fmaxf(norm3(g0, g1, g2), 1e-12f);       // F.normalize eps
+    t.n0 = g0 / gn; t.n1 = g1 / gn; t.n2 = g2 / gn;
+    return t;
+}
+NRH_HD float composite_accumulate(PrimaryComposite& r, float& T, float a, float mid, float n0, float n1, float n2) {
+    const float w = a * T;
+    T = T * (1.0f - a + 1e-7f);
+    if (w > r.max_w) { r.max_w = w; r.max_mid = mid; }
+    r.wsum += w; r.depth += mid * w;
+    r.nsum[0] += n0 * w; r.nsum[1] += n1 * w; r.nsum[2] += n2 * w;
+    return w;
+}
+NRH_HD void composite_init(PrimaryComposite& r) {
+    r.wsum = 0.f; r.depth = 0.f; r.nsum[0] = r.nsum[1] = r.nsum[2] = 0.f;
     r.max_w = -1.f; r.max_mid = 0.f;
-    float T = 1.0f;
-    for (int j = 0; j < S; ++j) {
-        float dist, mid; section(z, j, S, last_dist, dist, mid);
-        const float px = o[0] + d[0] * mid, py = o[1] + d[1] * mid, pz = o[2] + d[2] * mid;
-        const float g0 = gx[j], g1 = gy[j], g2 = gz[j];
-        float a = neus_alpha(sdf[j], g0, g1, g2, d, dist, inv_s, cos_anneal);
-        const float inside = norm3(px, py, pz) < 1.0f ? 1.0f : 0.0f;
-        if (n_out > 0) a = a * inside + outside_alpha(bg_density[j], bg_dist[j]) * (1.0f - inside);
-        const float w = a * T;
-        T = T * (1.0f - a + 1e-7f);
-        w_out[j] = w;
-        inside_out[j] = inside;
-        const float gn = fmaxf(norm3(g0, g1, g2), 1e-12f);       // F.normalize eps
-        const float n0 = g0 / gn, n1 = g1 / gn, n2 = g2 / gn;
-        nx[j] = n0; ny[j] = n1; nz[j] = n2;
-        if (w > r.max_w) { r.max_w = w; r.max_mid = mid; }
-        r.wsum += w; r.depth += mid * w;
-        r.nsum[0] += n0 * w; r.nsum[1] += n1 * w; r.nsum[2] += n2 * w;
-    }
+}
+// the n_out samples of the outside model appended behind the S primary ones (:517-519)
+NRH_HD void composite_append_outside(PrimaryComposite& r, float& T, int S, int n_out, CSoA bg_density, CSoA bg_dist, SoA w_out) {
     for (int j = S; j < S + n_out; ++j) {
         const float a = outside_alpha(bg_density[j], bg_dist[j]);
         const float w = a * T;
@@ -346,6 +353,21 @@ NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], in
         w_out[j] = w;
         r.wsum += w;
     }
+}
+NRH_HD PrimaryComposite composite_primary(const float o[3], const float d[3], int S, CSoA z, float last_dist,
+                                          CSoA sdf, CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal,
+                                          SoA w_out, SoA inside_out, SoA nx, SoA ny, SoA nz,
+                                          int n_out = 0, CSoA bg_density = CSoA{nullptr, 0}, CSoA bg_dist = CSoA{nullptr, 0}) {
+    PrimaryComposite r; composite_init(r);
+    float T = 1.0f;
+    for (int j = 0; j < S; ++j) {
+        const SampleTerms t = composite_sample(o, d, S, z, j, last_dist, sdf[j], gx[j], gy[j], gz[j], inv_s, cos_anneal, n_out,
+                                               n_out > 0 ? bg_density[j] : 0.f, n_out > 0 ? bg_dist[j] : 0.f);
+        w_out[j] = composite_accumulate(r, T, t.a, t.mid, t.n0, t.n1, t.n2);
+        inside_out[j] = t.inside;
+        nx[j] = t.n0; ny[j] = t.n1; nz[j] = t.n2;
+    }
+    composite_append_outside(r, T, S, n_out, bg_density, bg_dist, w_out);
     return r;
 }
 
@@ -371,13 +393,17 @@ NRH_HD float shadow_ray_init(const float pl[3], const float hit[3], int n, float
     return L;
 }
 
-// taus[:, -1]: transmittance in front of the last sample (get_visibility :427-432)
+// taus[:, -1]: transmittance in front of the last sample (get_visibility :427-432); shadow_alpha = its per-sample term
+NRH_HD float shadow_alpha(const float d[3], int S, CSoA z, int j, float last_dist, float sdf_j, float g0, float g1, float g2,
+                          float inv_s, float cos_anneal) {
+    float dist, mid; section(z, j, S, last_dist, dist, mid);
+    return neus_alpha(sdf_j, g0, g1, g2, d, dist, inv_s, cos_anneal);
+}
 NRH_HD float shadow_transmittance(const float d[3], int S, CSoA z, float last_dist, CSoA sdf,
                                   CSoA gx, CSoA gy, CSoA gz, float inv_s, float cos_anneal) {
     float T = 1.0f;
     for (int j = 0; j + 1 < S; ++j) {
-        float dist, mid; section(z, j, S, last_dist, dist, mid);
-        const float a = neus_alpha(sdf[j], gx[j], gy[j], gz[j], d, dist, inv_s, cos_anneal);
+        const float a = shadow_alpha(d, S, z, j, last_dist, sdf[j], gx[j], gy[j], gz[j], inv_s, cos_anneal);
         T = T * (1.0f - a + 1e-7f);
     }
     return T;

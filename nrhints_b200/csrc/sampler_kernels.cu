@@ -222,17 +222,41 @@ k_composite_primary(int64_t R, MarchState m, int cur, int S, float last_dist,
     stage_rows(st_sm + 3 * rows, f.gy, S, R, r0, nr);
     stage_rows(st_sm + 4 * rows, f.gz, S, R, r0, nr);
     __syncthreads();
+    const float inv_s = inv_s_ptr[0];
+    // per-sample terms on all threads (composite_sample): alpha replaces sdf, the unit normal replaces the gradient in shared memory
+    // (every (sample, ray) slot is read and written by the same thread; z is read-only: section() looks at the next sample)
+    for (int idx = threadIdx.x; idx < rows; idx += ST_THREADS) {
+        const int j = idx / ST_RAYS, tt = idx % ST_RAYS;
+        if (tt < nr) {
+            const int64_t rr = r0 + tt;
+            const float oo[3] = {m.o[0][rr], m.o[1][rr], m.o[2][rr]}, dd[3] = {m.d[0][rr], m.d[1][rr], m.d[2][rr]};
+            const SampleTerms ts = composite_sample(oo, dd, S, CSoA{st_sm + tt, ST_RAYS}, j, last_dist, st_sm[rows + idx], st_sm[2 * rows + idx],
+                                                    st_sm[3 * rows + idx], st_sm[4 * rows + idx], inv_s, cos_anneal, n_out,
+                                                    n_out > 0 ? ob.density[(int64_t)j * R + rr] : 0.f, n_out > 0 ? ob.dist[(int64_t)j * R + rr] : 0.f);
+            st_sm[rows + idx] = ts.a; st_sm[2 * rows + idx] = ts.n0; st_sm[3 * rows + idx] = ts.n1; st_sm[4 * rows + idx] = ts.n2;
+            const int64_t g = (int64_t)j * R + rr;
+            f.inside[g] = ts.inside; f.nx[g] = ts.n0; f.ny[g] = ts.n1; f.nz[g] = ts.n2;
+        }
+    }
+    __syncthreads();
     const int t = threadIdx.x;
     if (t >= nr) return;
     const int64_t r = r0 + t;
     float o[3], d[3];
     for (int c = 0; c < 3; ++c) { o[c] = m.o[c][r]; d[c] = m.d[c][r]; }
-    const float inv_s = inv_s_ptr[0];
-    PrimaryComposite pc = composite_primary(o, d, S, CSoA{st_sm + t, ST_RAYS}, last_dist, CSoA{st_sm + rows + t, ST_RAYS},
-                                            CSoA{st_sm + 2 * rows + t, ST_RAYS}, CSoA{st_sm + 3 * rows + t, ST_RAYS},
-                                            CSoA{st_sm + 4 * rows + t, ST_RAYS}, inv_s, cos_anneal,
-                                            SoA{f.w + r, R}, SoA{f.inside + r, R}, SoA{f.nx + r, R}, SoA{f.ny + r, R}, SoA{f.nz + r, R},
-                                            n_out, CSoA{n_out > 0 ? ob.density + r : nullptr, R}, CSoA{n_out > 0 ? ob.dist + r : nullptr, R});
+    // the scan, one thread per ray, in sample order (composite_accumulate)
+    PrimaryComposite pc; composite_init(pc);
+    {
+        float T = 1.0f;
+        const CSoA z{st_sm + t, ST_RAYS};
+        for (int j = 0; j < S; ++j) {
+            float dist, mid; section(z, j, S, last_dist, dist, mid);
+            const int idx = j * ST_RAYS + t;
+            f.w[(int64_t)j * R + r] = composite_accumulate(pc, T, st_sm[rows + idx], mid, st_sm[2 * rows + idx], st_sm[3 * rows + idx], st_sm[4 * rows + idx]);
+        }
+        composite_append_outside(pc, T, S, n_out, CSoA{n_out > 0 ? ob.density + r : nullptr, R}, CSoA{n_out > 0 ? ob.dist + r : nullptr, R},
+                                 SoA{f.w + r, R});
+    }
     float hit[3], hn[3];
     float depth = pc.depth;                                              // AlphaBlend (:530-533)
     if (depth_type == NRH_DEPTH_MAX_WEIGHT) depth = pc.max_mid;           // MaximalWeightPoint (:534-538)
@@ -302,15 +326,28 @@ k_shade_prep(int64_t R, NrhConfig cfg, MarchState sh, int cur, int S_shadow,
         stage_rows(st_sm + 4 * rows, sgz, S_shadow, R, r0, nr);
         __syncthreads();
     }
+    if (shadow_marched) {
+        // per-sample alphas on all threads (shadow_alpha), written over the sdf slots; the last sample does not enter taus[:, -1]
+        const float inv_s = inv_s_ptr[0];
+        for (int idx = threadIdx.x; idx < rows - ST_RAYS; idx += ST_THREADS) {
+            const int j = idx / ST_RAYS, tt = idx % ST_RAYS;
+            if (tt < nr) {
+                const int64_t rr = r0 + tt;
+                const float sd[3] = {sh.d[0][rr], sh.d[1][rr], sh.d[2][rr]};
+                st_sm[rows + idx] = shadow_alpha(sd, S_shadow, CSoA{st_sm + tt, ST_RAYS}, j, rs.light_dist[rr], st_sm[rows + idx],
+                                                 st_sm[2 * rows + idx], st_sm[3 * rows + idx], st_sm[4 * rows + idx], inv_s, cos_anneal);
+            }
+        }
+        __syncthreads();
+    }
     const int t = threadIdx.x;
     if (t >= nr) return;
     const int64_t r = r0 + t;
     float vis = 0.f;
-    if (shadow_marched) {
-        float sd[3] = {sh.d[0][r], sh.d[1][r], sh.d[2][r]};
-        vis = shadow_transmittance(sd, S_shadow, CSoA{st_sm + t, ST_RAYS}, rs.light_dist[r], CSoA{st_sm + rows + t, ST_RAYS},
-                                   CSoA{st_sm + 2 * rows + t, ST_RAYS}, CSoA{st_sm + 3 * rows + t, ST_RAYS},
-                                   CSoA{st_sm + 4 * rows + t, ST_RAYS}, inv_s_ptr[0], cos_anneal);
+    if (shadow_marched) {                                  // the transmittance product, in sample order (shadow_transmittance)
+        float T = 1.0f;
+        for (int j = 0; j + 1 < S_shadow; ++j) T = T * (1.0f - st_sm[rows + j * ST_RAYS + t] + 1e-7f);
+        vis = T;
     }
     rs.vis[r] = vis;
     float d[3] = {dirs[r * 3 + 0], dirs[r * 3 + 1], dirs[r * 3 + 2]};
