@@ -41,15 +41,16 @@ __global__ void k_coarse_primary(NrhRays rays, int64_t R, int n, const float* __
 // The per-ray algorithm is a chain of short dependent steps over <= 128 samples, so each thread first stages its
 // ray's arrays in shared memory (coalesced, fully overlapped global loads), runs ray_math.cuh on them, and writes
 // the results back: the dependent chain then pays shared-memory latency instead of L2 latency per step.
-constexpr int IS_RAYS = 64;                                 // rays per CTA
-constexpr int IS_THREADS = 512;                             // 8 threads per ray for the parallel phases
+constexpr int IS_RAYS = 32;                                 // rays per CTA (128 CTAs for 4096 rays: the parallel phases use most SMs)
+constexpr int IS_THREADS = 512;                             // 16 threads per ray for the parallel phases
 constexpr int IS_NEW = 32;                                   // max samples drawn per step
 constexpr int IS_ROWS = 3 * NRH_MAX_SAMPLES + 2 * IS_NEW;   // z[128] s[128] w[128] z_new[32] s_new[32]
 constexpr size_t IS_SMEM = (size_t)IS_ROWS * IS_RAYS * sizeof(float);
 
-// A CTA owns 64 rays.  Data movement and the per-interval alphas (two precise sigmoids + three divisions each, the bulk
-// of the arithmetic) are spread over all 512 threads; the short sequential parts (merge, prefix products, cdf walk)
-// run one thread per ray on the shared-memory copies.  Arithmetic and its order are exactly those of ray_math.cuh.
+// A CTA owns IS_RAYS rays.  Data movement, the per-interval alphas (two precise sigmoids + three divisions each, the bulk
+// of the arithmetic), the merges (rank form) and the pdf divisions are spread over all 512 threads; only the two genuinely
+// sequential parts (transmittance product + weight sum, cdf walk) run one thread per ray on the shared-memory copies.
+// Arithmetic and its order are exactly those of ray_math.cuh.
 // Stable merge of the n_new sorted new entries (szn / ssn) into the k_old sorted old ones (sz / ss), in place, on ALL threads: every
 // (ray, entry) pair finds its own slot by binary search in the other run (ray_math.cuh: count_less / count_less_equal), all slots
 // are computed before any is written.  Same result as merge_sorted / merge_sorted_backward (tests/test_ray_math_host.py).
