@@ -6,12 +6,15 @@ import torch
 if sys.argv[1] == "--compare":
     a, b = torch.load(sys.argv[2]), torch.load(sys.argv[3])
     bad = 0
+    diffs = []
     for k in a:
         if k.startswith("time"):
             continue
         if not torch.equal(a[k], b[k]):
             bad += 1
-            print("DIFF", k, float((a[k].float() - b[k].float()).abs().max()))
+            diffs.append((float((a[k].float() - b[k].float()).abs().max()), k))
+    for dmax, k in sorted(diffs, reverse=True)[:12]:
+        print("DIFF", k, dmax)
     print(f"{len(a)} tensors compared, {bad} differ;", {k: (a[k], b[k]) for k in a if k.startswith("time")})
     sys.exit(1 if bad else 0)
 import numpy as np
