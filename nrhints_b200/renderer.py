@@ -325,7 +325,12 @@ class NeuSHintRenderer(nn.Module):
         if r.use_outside_nerf and not (1 <= r.n_outside_samples <= _lib.NRH_MAX_OUTSIDE):
             raise NotImplementedError(f"n_outside_samples must be in [1, {_lib.NRH_MAX_OUTSIDE}]")
         if r.n_shadow_importance_clip != -1:
-            raise NotImplementedError("n_shadow_importance_clip != -1 is not implemented (reference default is -1)")
+            # one shadow march per GROUP of samples (models/neus_hint_model.py:554-576; off in every preset of the reference): served by
+            # the composed evaluation route of hint_fallback.py (inference only), not by the fused pipeline
+            S_all = r.n_samples + r.n_importance_samples
+            if not (r.n_shadow_importance_clip > 0 and r.shadow_hint and not r.use_outside_nerf and S_all % r.n_shadow_importance_clip == 0):
+                raise NotImplementedError("n_shadow_importance_clip must be -1, or a positive divisor of n_samples + n_importance_samples "
+                                          "with the shadow hint on and the outside NeRF off; got " + repr(r.n_shadow_importance_clip))
         if r.shadow_hint_gradient or r.specular_hint_gradient:
             raise NotImplementedError("hint gradients are not implemented (reference default is off)")
         if (r.force_shadow_map and not r.shadow_hint) or (r.force_specular_cue and not r.specular_hint):
@@ -586,6 +591,40 @@ class NeuSHintRenderer(nn.Module):
     # -- the hot path ------------------------------------------------------------------------------------
     def forward(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
                 global_step: int = 0, return_extras: bool = False, _early_event=None, _fine_events=None) -> RenderOutput:
+        if self.config.renderer.n_shadow_importance_clip > 0:
+            return self._forward_grouped_shadow(ray_bundle, is_training, background_rgb, global_step, return_extras, _early_event)
+        return self._forward_fused(ray_bundle, is_training, background_rgb, global_step, return_extras, _early_event, _fine_events)
+
+    def _forward_grouped_shadow(self, ray_bundle, is_training, background_rgb, global_step, return_extras, _early_event=None) -> RenderOutput:
+        """`n_shadow_importance_clip > 0` (models/neus_hint_model.py:554-576): evaluation route composed of the fused forward (sample
+        positions, weights, normals, depth, specular cue: nothing of that depends on the visibility), nrh_sdf_query for the grouped
+        shadow marches and the features, and the stand-alone reflectance network (nrhints_b200/hint_fallback.py).  Inference only."""
+        from . import hint_fallback as hf
+        fields = (ray_bundle.origins, ray_bundle.directions, ray_bundle.pl_positions)
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in fields))
+        if is_training or needs_grad:
+            raise NotImplementedError("n_shadow_importance_clip > 0 is served by an evaluation-only route: call it with is_training=False "
+                                      "under torch.no_grad() (training with this option stays with the reference renderer)")
+        r = self.config.renderer
+        with torch.no_grad():
+            base = self._forward_fused(ray_bundle, False, background_rgb, global_step, True, None, None)
+            o, d, pl = (t.detach().to(torch.float32).contiguous() for t in fields)
+            inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6).to(o.device).reshape(())
+            vis, shadow_map = hf.grouped_visibility(self.sdf_query, o, d, pl, base.z_vals, base.weights, r.n_shadow_importance_clip,
+                                                    r.n_shadow_samples, r.n_shadow_importance_samples, inv_s, r.shadow_ray_offset,
+                                                    chunk=int(getattr(self.config, "shadow_mini_chunk_size", 2048)))
+            normalized = getattr(r.normal_type, "value", r.normal_type) == NormalComputationType.NormalizedAnalytic.value
+            normals = base.normalized_analytic_normals if normalized else base.analytic_normals
+            bg = background_rgb.detach().to(o.device, torch.float32) if background_rgb is not None else None
+            rgb, colour = hf.shade_samples(self.sdf_query, self.color_network, o, d, pl, base.z_vals, base.weights, normals, vis,
+                                           base.specular_cue if self.has_specular_hint else None, 2.0 / r.n_samples, bg)
+        if _early_event is not None:                     # render_to_host: every field is final only here
+            _early_event.record(torch.cuda.current_stream(o.device))
+        return dataclasses.replace(base, rgb=rgb, visibilities=shadow_map, sampled_color=colour if return_extras else None,
+                                   z_vals=base.z_vals if return_extras else None, z_shadow=None)
+
+    def _forward_fused(self, ray_bundle, is_training: bool = False, background_rgb: Optional[torch.Tensor] = None,
+                       global_step: int = 0, return_extras: bool = False, _early_event=None, _fine_events=None) -> RenderOutput:
         lib = _lib.load()
         rays_o = ray_bundle.origins
         device = rays_o.device

@@ -73,8 +73,11 @@ def test_unsupported_configs_raise():
                                                outside_nerf=nb.NeRFConfig(multi_res=6)))
     with pytest.raises(NotImplementedError):
         nb.NeuSHintRenderer(nb.NeuSModelConfig(sdf_network=nb.SDFNetConfig(d_hidden=128)))
+    with pytest.raises(NotImplementedError):                   # must divide the 128 samples of a ray (hint_fallback.py serves the rest)
+        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_shadow_importance_clip=5)))
     with pytest.raises(NotImplementedError):
-        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_shadow_importance_clip=4)))
+        nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_shadow_importance_clip=4, shadow_hint=False)))
+    nb.NeuSHintRenderer(nb.NeuSModelConfig(renderer=nb.NeuSRendererConfig(n_shadow_importance_clip=4)))
 
 
 def test_state_dict_layout_matches_reference_inventory():
